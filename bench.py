@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the VQ hot path (BASELINE.json metric: VQ latents quantised / second).
+
+Workload (BASELINE.json configs[1]): the VectorQuantize work of ONE stage-1 training step at batch
+1024 synthetic trajectories of configs/config.yaml shape — LF codebook 18*1024 = 18 432 latents +
+HF codebook 75*1024 = 76 800 latents, K = 32, D = 128, train mode: distance + argmin + gather +
+straight-through + commitment loss + EMA statistics + EMA update, then the backward.  One "step"
+= both codebooks, forward + backward, through the reference-shaped module (tvq_b200.VectorQuantize).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-sweep]
+
+Output: ONE JSON line (rank 0).  See DESIGN.md section 6 for how every field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+B_TRAJ = 1024
+TOK_LF, TOK_HF = 18, 75           # tokens per trajectory at L=200, n_fft=4
+K_CODES, DIM = 32, 128            # configs/config.yaml: codebook_sizes 32/32, hid_dim 128
+LATENTS_PER_STEP = B_TRAJ * (TOK_LF + TOK_HF)
+N_INPUT_SETS = 4                  # rotate inputs: 4 x 195 MB of x/g per rank > 126 MB L2
+METRIC = "vq_latents_per_sec"
+UNIT = "latents/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured"
+        except Exception:
+            pass
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------- reference arm
+
+def make_cpu_inputs(seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(B_TRAJ, TOK_LF, DIM, generator=g), torch.randn(B_TRAJ, TOK_HF, DIM, generator=g),
+            torch.randn(B_TRAJ, TOK_LF, DIM, generator=g), torch.randn(B_TRAJ, TOK_HF, DIM, generator=g))
+
+
+def cpu_reference_step(states, xl, xh, gl, gh):
+    """The reference's CPU torch path for the same step (oracle/vq_oracle.py restates vq.py bitwise)."""
+    import vq_oracle as O
+    total = 0.0
+    for state, x, g in ((states[0], xl, gl), (states[1], xh, gh)):
+        xr = x.clone().requires_grad_(True)
+        q, ind, loss, ppl = O.vq_forward(state, xr, training=True)
+        ((q * g).sum() + loss["loss"].sum()).backward()
+        total += float(loss["loss"])
+    return total
+
+
+def run_cpu_baseline(steps, warmup):
+    import vq_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    states = [O.new_state(K_CODES, DIM), O.new_state(K_CODES, DIM)]
+    inputs = make_cpu_inputs(1)
+    for _ in range(warmup):
+        cpu_reference_step(states, *inputs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(states, *inputs)
+    dt = time.perf_counter() - t0
+    return LATENTS_PER_STEP * steps / dt, dt / steps, cores
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, s_per_step, cores = run_cpu_baseline(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full steps (B=1024: {LATENTS_PER_STEP} latents each), torch "
+                                   f"{torch.__version__} CPU fp32, oracle/vq_oracle.py (bitwise restatement of the "
+                                   f"reference's vq.py; the Python reference itself cannot travel to the GPU box)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "stage1_vq_train_step_B1024 (BASELINE configs[1]): LF 18432 + HF 76800 latents per GPU, "
+                        "K=32, D=128, VectorQuantize train forward (assign+gather+ST+commit loss+EMA) + backward",
+            "latents_per_step_per_gpu": LATENTS_PER_STEP, "codebook": [K_CODES, DIM], "batch_trajectories_per_gpu": B_TRAJ,
+            "parallelism": f"dp{n_gpus} (batch-sharded, packed EMA-statistics all-reduce)",
+            "l2_policy": f"inputs rotate over {N_INPUT_SETS} resident batches (> 126 MB L2 between reuses)"}
+
+
+# -------------------------------------------------------------------------------------- our arm
+
+def our_arm(args):
+    import torch.distributed as dist
+    import tvq_b200 as tvq
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 kernels have no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_gbs, bf16_tf, peak_src = load_peaks()
+
+    torch.manual_seed(0)                                        # identical replicas
+    vq_l = tvq.VectorQuantize(DIM, K_CODES, sync_codebook=world > 1).to(dev).train()
+    vq_h = tvq.VectorQuantize(DIM, K_CODES, sync_codebook=world > 1).to(dev).train()
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    sets = []
+    for _ in range(N_INPUT_SETS):
+        sets.append(tuple(torch.randn(B_TRAJ, t, DIM, device=dev, generator=gen).requires_grad_(r)
+                          for t, r in ((TOK_LF, True), (TOK_HF, True), (TOK_LF, False), (TOK_HF, False))))
+
+    ones = torch.ones(1, device=dev)
+
+    def step(xl, xh, gl, gh):
+        """One VQ train step (both codebooks), forward + backward, via the public module API."""
+        ql, il, ll, pl = vq_l(xl)
+        qh, ih, lh, ph = vq_h(xh)
+        torch.autograd.grad([ql, qh, ll["loss"], lh["loss"]], [xl, xh], [gl, gh, ones, ones])
+        return ll["loss"], lh["loss"], il, ih
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def clear_grads():
+        pass
+
+    # ---- eager path (public API, one Python call per module) -----------------------------------
+    def eager(i):
+        step(*sets[i % N_INPUT_SETS])
+    for i in range(max(args.warmup, 3)):
+        eager(i)
+    clear_grads()
+    eager_ms = timed(eager, args.steps)
+    clear_grads()
+
+    # ---- CUDA-graph replay of the same step (launch-bound regime: 8 small kernels per step) -------
+    graphs = None
+    graph_ms = None
+    if world == 1 and not args.no_graph:
+        try:
+            graphs = []
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for s in sets:
+                    step(*s)
+            torch.cuda.current_stream().wait_stream(side)
+            clear_grads()
+            for s in sets:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step(*s)
+                graphs.append(g)
+            for i in range(max(args.warmup, 3)):
+                graphs[i % N_INPUT_SETS].replay()
+            graph_ms = timed(lambda i: graphs[i % N_INPUT_SETS].replay(), args.steps)
+        except Exception as exc:   # report, never hide
+            print(f"[bench] CUDA-graph capture failed: {exc}", file=sys.stderr)
+            graphs, graph_ms = None, None
+        clear_grads()
+
+    # ---- the timed region that `value` reports, with clocks sampled during it -----------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if graphs is not None:
+        main_ms = timed(lambda i: graphs[i % N_INPUT_SETS].replay(), args.steps)
+        mode = "cuda_graph_replay"
+    else:
+        main_ms = timed(eager, args.steps)
+        mode = "eager"
+    clocks = sampler.stop() if rank == 0 else None
+    clear_grads()
+    value = world * LATENTS_PER_STEP * args.steps / (main_ms * 1e-3)
+
+    # ---- e2e: pinned host inputs -> H2D -> step -> D2H of the step's result -------------------------
+    host_sets = [(s[0].detach().cpu().pin_memory(), s[1].detach().cpu().pin_memory()) for s in sets]
+    dxl = torch.empty_like(sets[0][0]).requires_grad_(True)
+    dxh = torch.empty_like(sets[0][1]).requires_grad_(True)
+    h_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+    h_il = torch.empty(B_TRAJ, TOK_LF, dtype=torch.int64).pin_memory()
+    h_ih = torch.empty(B_TRAJ, TOK_HF, dtype=torch.int64).pin_memory()
+    h2d = (dxl.numel() + dxh.numel()) * 4
+    d2h = 8 + (h_il.numel() + h_ih.numel()) * 8
+
+    def e2e_step(i):
+        hx_l, hx_h = host_sets[i % N_INPUT_SETS]
+        with torch.no_grad():
+            dxl.copy_(hx_l, non_blocking=True)
+            dxh.copy_(hx_h, non_blocking=True)
+        loss_l, loss_h, il, ih = step(dxl, dxh, sets[0][2], sets[0][3])
+        h_loss[0:1].copy_(loss_l.detach(), non_blocking=True)
+        h_loss[1:2].copy_(loss_h.detach(), non_blocking=True)
+        h_il.copy_(il, non_blocking=True)
+        h_ih.copy_(ih, non_blocking=True)
+    for i in range(max(args.warmup, 3)):
+        e2e_step(i)
+    e2e_ms = timed(e2e_step, args.steps)
+    e2e_value = world * LATENTS_PER_STEP * args.steps / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (the HF fused forward), timed alone with CUDA events --------
+    cb = vq_h._codebook
+    ws = cb._workspace(dev)
+    flats = [s[1].detach().reshape(-1, DIM) for s in sets]
+    n_hf = flats[0].shape[0]
+    lib = tvq._lib.load()
+    idx = torch.empty(n_hf, dtype=torch.int64, device=dev)
+    q = torch.empty_like(flats[0])
+    scal = torch.empty(8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fwd_kernel(i):
+        x = flats[i % N_INPUT_SETS]
+        rc = lib.tvq_forward(x.data_ptr(), cb.embed.data_ptr(), n_hf, K_CODES, DIM, tvq._lib.F_TRAIN | tvq._lib.F_WRITE_Q,
+                             1.0, idx.data_ptr(), q.data_ptr(), ws.stats.data_ptr(), scal.data_ptr(), ws.buf.data_ptr(),
+                             ws.nbytes, st)
+        assert rc == 0
+    for i in range(5):
+        fwd_kernel(i)
+    reps = max(args.steps, 20)
+    k_ms = timed(fwd_kernel, reps) / reps
+    alg_bytes = n_hf * (8 * DIM + 8)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "tvq_forward (prep + fused forward) on the HF codebook, N=76800",
+                "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": k_ms * 1e3,
+                "note": "76 800 latents = 12 us of HBM time: launch/tail-latency regime (SURVEY 7.3-4); see `sweep` "
+                        "for the large-N fractions"}
+
+    # ---- large-N sweep points (BASELINE configs[2]) ---------------------------------------------------
+    sweep = []
+    if rank == 0 and not args.no_sweep:
+        for (n, k, d) in ((1 << 22, 32, 128), (1 << 22, 512, 64), (1 << 20, 4096, 128)):
+            try:
+                sweep.append(sweep_point(tvq, dev, n, k, d, hbm_gbs, bf16_tf))
+            except Exception as exc:
+                sweep.append({"n": n, "k": k, "d": d, "error": str(exc)})
+
+    # ---- CPU baseline on this host (rank 0, N=1 only) --------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, s_per, cores = run_cpu_baseline(5, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"5 full steps of the same workload ({LATENTS_PER_STEP} latents each, {s_per * 1e3:.1f} ms/step), "
+                         "oracle/vq_oracle.py on torch CPU fp32"}
+
+    launches_per_step = 2 * (2 + 1 + 1)     # per codebook: prep + fused forward, EMA update, backward
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": main_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(world), timed_mode=mode),
+            "trajectories_per_sec": value / (TOK_LF + TOK_HF),
+            "eager_ms_per_step": eager_ms / args.steps, "graph_ms_per_step": (graph_ms / args.steps) if graph_ms else None,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "what": "pinned host x (LF+HF) -> H2D -> VectorQuantize fwd+bwd (eager, public API) -> D2H of loss + indices"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "sweep": sweep,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sweep_point(tvq, dev, n, k, d, hbm_gbs, bf16_tf):
+    """Isolated quantise (train forward incl. EMA statistics) at a BASELINE configs[2] size."""
+    g = torch.Generator(device=dev).manual_seed(1)
+    reps_in = max(2, int(2.6e8 // (n * d * 4)) + 1)            # distinct inputs totalling > 2 x L2
+    xs = [torch.randn(n, d, device=dev, generator=g) for _ in range(min(reps_in, 3))]
+    e = torch.randn(k, d, device=dev, generator=g)
+    ws = tvq.Workspace(k, d, dev)
+    for i in range(3):
+        tvq.vq_forward_raw(xs[i % len(xs)], e, ws, train=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for i in range(reps):
+        tvq.vq_forward_raw(xs[i % len(xs)], e, ws, train=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    by = n * (8 * d + 8) / (ms * 1e-3) / 1e9
+    fl = 2.0 * n * k * d / (ms * 1e-3) / 1e12
+    hb, tc = by / hbm_gbs, fl / bf16_tf
+    return {"n": n, "k": k, "d": d, "mode": "train_forward", "ms": ms, "latents_per_sec": n / (ms * 1e-3),
+            "hbm_gbs": by, "tflops": fl, "bound": "hbm" if hb >= tc else "tensor", "frac": max(hb, tc)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        our_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+/* tvq.h — C ABI of the B200 (sm_100a) vector-quantisation kernels.
+ *
+ * This is the drop-in boundary underneath the reference's Python seam,
+ * `timevqvae.models.vq.VectorQuantize` (/root/reference/timevqvae/models/vq.py:255-407):
+ * the host module in t-vq-vae-trajgen_b200/vq.py keeps that class surface and calls these
+ * entry points through ctypes.  Plain pointers and sizes only — no torch types, no C++
+ * exceptions; every function returns 0 (TVQ_OK) or a negative tvq error / positive
+ * cudaError_t.  All pointers are DEVICE pointers on the current CUDA device unless
+ * marked host.  Kernels are enqueued on `stream` (a cudaStream_t passed as void*) and
+ * never allocate, free or synchronise; buffers are owned by the caller.
+ *
+ * Shapes:  x, q      [n, d] fp32 row-major (the reference's `flatten`, vq.py:200)
+ *          codebook  [k, d] fp32 row-major (`_codebook.embed`, vq.py:165)
+ *          idx       [n]    int64          (`embed_ind`, vq.py:218-224)
+ *          stats     [TVQ_STATS_OFFSET(k) + k*d] fp32: counts[k] (zero-padded to a multiple of
+ *                    4 so that embed_sum stays 16-byte aligned) then embed_sum[k][d] — the two
+ *                    tensors the reference all-reduces at vq.py:229 and :234 (embed_sum stored
+ *                    K-major, i.e. already transposed as vq.py:236 uses it), packed so that
+ *                    data-parallel ranks need ONE all-reduce
+ */
+#ifndef TVQ_H_
+#define TVQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TVQ_API __attribute__((visibility("default")))
+#else
+#define TVQ_API
+#endif
+
+#define TVQ_OK 0
+#define TVQ_ERR_UNSUPPORTED (-1) /* shape outside the kernels' range (d % 4 != 0, d > 256, k < 1 ...) */
+#define TVQ_ERR_BAD_ARG (-2)     /* null pointer, misaligned pointer, workspace too small */
+#define TVQ_ERR_DEVICE (-3)      /* not an sm_100 device */
+
+/* element offset of embed_sum inside `stats`, and the total element count */
+#define TVQ_STATS_OFFSET(k) ((((int64_t)(k)) + 3) & ~(int64_t)3)
+#define TVQ_STATS_LEN(k, d) (TVQ_STATS_OFFSET(k) + (int64_t)(k) * (int64_t)(d))
+
+#define TVQ_NUM_SCALARS 8
+
+/* flags for tvq_forward */
+#define TVQ_F_TRAIN 1u      /* straight-through output + commitment-loss sum + embed_sum statistics  */
+#define TVQ_F_WRITE_Q 2u    /* write q (eval: codebook[idx]; train: x + (codebook[idx] - x))         */
+#define TVQ_F_EXACT 4u      /* debug: decide every row with the fp64 canonical scan (no fast scoring) */
+#define TVQ_F_NO_UMMA 8u    /* force the SIMT scoring path even where the tcgen05 path applies        */
+#define TVQ_F_GIVEN_IDX 16u /* idx is an INPUT (codes sampled by the caller, vq.py:55-56): skip scoring */
+
+/* Library / device probes. */
+TVQ_API int tvq_abi_version(void);
+TVQ_API const char *tvq_error_string(int code);
+/* 0 if `device` is compute capability 10.x; fills sm_count (may be NULL). */
+TVQ_API int tvq_device_check(int device, int *sm_count);
+
+/* Bytes of scratch the forward needs for (n, k, d): header + per-code constants.
+ * The scratch must be zero-filled ONCE when allocated (it holds a launch ticket). */
+TVQ_API size_t tvq_workspace_bytes(int64_t n, int k, int d);
+
+/* Distance + assignment (+ gather / straight-through / loss / EMA statistics).
+ *   Replaces EuclideanCodebook.forward vq.py:210-234 and the ST + commit-loss lines
+ *   VectorQuantize.forward vq.py:357-366, for temperature 0.
+ *   idx      out [n]
+ *   q        out [n,d] or NULL (needs TVQ_F_WRITE_Q)
+ *   stats    out [TVQ_STATS_LEN(k,d)]; zeroed inside; counts always, embed_sum only with TVQ_F_TRAIN
+ *   scalars  out float[TVQ_NUM_SCALARS]: [0] commit loss = mean((q_st - x)^2) (train),
+ *            [1] perplexity (vq.py:246-247, from this call's counts), [2] commitment_weight *
+ *            commit loss (the reference's vq_loss["loss"], vq.py:366), [3] unused, [4],[5] uint32
+ *            diagnostics: rows decided by the fp64 re-score, rows that needed the full exact scan. */
+TVQ_API int tvq_forward(const float *x, const float *codebook, int64_t n, int k, int d, unsigned flags,
+                float commitment_weight, int64_t *idx, float *q, float *stats, float *scalars,
+                void *workspace, size_t workspace_bytes, void *stream);
+
+/* EMA codebook update from (all-reduced) statistics: vq.py:231, :236-242 with helpers :59-64.
+ *   cluster_size [k], embed_avg [k,d], embed [k,d] are updated in place; embed_prev [k,d]
+ *   (optional, may be NULL) receives the codebook as it was before the update, which is the
+ *   one the forward's outputs were gathered from (vq.py:225 precedes :242) and the one
+ *   tvq_backward needs.                                                                      */
+TVQ_API int tvq_ema_update(const float *stats, float *cluster_size, float *embed_avg, float *embed,
+                   float *embed_prev, int k, int d, double decay, double eps, void *workspace,
+                   size_t workspace_bytes, void *stream);
+
+/* Backward of the train forward (autograd through vq.py:357-366):
+ *   g_x = g_q + (g_scalars[0] + commitment_weight * g_scalars[2]) * 2/(n*d) * (x - q_st)
+ *   with q_st recomputed from x, idx and the codebook the forward used.  g_scalars is the
+ *   device gradient w.r.t. the forward's `scalars` ([0] commit loss, [2] weighted loss);
+ *   NULL means zero.                                                                          */
+TVQ_API int tvq_backward(const float *g_q, const float *g_scalars, const float *x, const int64_t *idx,
+                 const float *codebook, int64_t n, int k, int d, float commitment_weight,
+                 float *g_x, void *stream);
+
+/* Codeword gather for de-tokenising, F.embedding + rearrange of
+ * /root/reference/timevqvae/models/maskgit.py:465-470.
+ *   tokens [b*t] int64; layout 0: out[b, t, d]; layout 1: out[b, d, t] (decoder layout).      */
+TVQ_API int tvq_gather(const int64_t *tokens, const float *codebook, int64_t b, int64_t t, int k, int d,
+               int layout, float *out, void *stream);
+
+/* Full negative squared-distance matrix dist[n,k] (vq.py:210-214) for the stochastic
+ * `svq_temp` branch (vq.py:55-56), whose sampling stays in torch to share its RNG stream.   */
+TVQ_API int tvq_neg_dist(const float *x, const float *codebook, int64_t n, int k, int d, float *dist,
+                 void *stream);
+
+/* Dead-code re-seed (vq.py:181-195): embed[j] = x[rows[j]] where cluster_size[j] < threshold.
+ * Only `embed` is touched, as in the reference.  rows [k] int64 (drawn by the host).          */
+TVQ_API int tvq_reseed(const float *x, const int64_t *rows, const float *cluster_size, float threshold,
+               float *embed, int64_t n, int k, int d, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVQ_H_ */

@@ -1,0 +1,16 @@
+"""tvq_b200 — B200-native (sm_100a) vector quantisation for TimeVQVAE.
+
+Public surface = the reference's: `VectorQuantize` (timevqvae/models/vq.py) and the `quantize`
+layout glue (timevqvae/utils/train_utils.py), running on hand-written CUDA kernels behind the C
+ABI of include/tvq.h.  The directory name carries the project name (`t-vq-vae-trajgen_b200`);
+import it as `tvq_b200` through the loader module of that name at the repository root.
+"""
+from . import _lib
+from .functional import (VQTrainStep, Workspace, stats_len, stats_offset, vq_backward, vq_ema_update,
+                         vq_forward_raw, vq_gather, vq_neg_dist, vq_reseed)
+from .glue import decode_tokens, quantize
+from .vq import EuclideanCodebook, VectorQuantize
+
+__all__ = ["VectorQuantize", "EuclideanCodebook", "quantize", "decode_tokens", "vq_forward_raw", "vq_ema_update",
+           "vq_backward", "vq_gather", "vq_neg_dist", "vq_reseed", "Workspace", "VQTrainStep", "stats_len",
+           "stats_offset", "_lib"]

@@ -1,0 +1,58 @@
+"""ctypes binding of the C ABI in include/tvq.h (libtvq_b200.so, built in-tree by __graft_entry__.build()).
+
+There is no fallback: if the shared library is missing or the device is not a B200 the
+import / first call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtvq_b200.so")
+
+# flags of tvq_forward (include/tvq.h)
+F_TRAIN, F_WRITE_Q, F_EXACT, F_NO_UMMA, F_GIVEN_IDX = 1, 2, 4, 8, 16
+NUM_SCALARS = 8      # [0] commit, [1] perplexity, [2] weight*commit, [4:6] uint32 diagnostics
+
+EXPORTS = ("tvq_abi_version", "tvq_error_string", "tvq_device_check", "tvq_workspace_bytes", "tvq_forward",
+           "tvq_ema_update", "tvq_backward", "tvq_gather", "tvq_neg_dist", "tvq_reseed")
+
+_c = ctypes
+_vp, _i, _i64, _u, _f, _d, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint, _c.c_float, _c.c_double, _c.c_size_t
+_SIGNATURES = {
+    "tvq_abi_version": (_i, []),
+    "tvq_error_string": (_c.c_char_p, [_i]),
+    "tvq_device_check": (_i, [_i, _c.POINTER(_i)]),
+    "tvq_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "tvq_forward": (_i, [_vp, _vp, _i64, _i, _i, _u, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "tvq_ema_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _vp, _sz, _vp]),
+    "tvq_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _vp, _vp]),
+    "tvq_gather": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp]),
+    "tvq_neg_dist": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    "tvq_reseed": (_i, [_vp, _vp, _vp, _f, _vp, _i64, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libtvq_b200.so; raises if it has not been built (no CPU or eager fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: the B200 VQ kernels are not built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root (needs nvcc, sm_100a).")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().tvq_error_string(rc)
+        raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else 'unknown'}")

@@ -1,0 +1,252 @@
+// tvq_api.cu — the C ABI declared in include/tvq.h: argument checks, kernel selection, launches.
+// Built for sm_100a only (see __graft_entry__.build); no torch, no C++ exceptions across the ABI.
+#include "../../include/tvq.h"
+
+#include <cuda_runtime.h>
+
+#include "tvq_aux.cuh"
+#include "tvq_common.cuh"
+#include "tvq_fwd_simt.cuh"
+
+using namespace tvq;
+
+namespace {
+
+struct DeviceInfo {
+    int checked = 0;
+    int ok = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+};
+DeviceInfo g_dev[64];
+
+int device_info(DeviceInfo** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64) return TVQ_ERR_DEVICE;
+    DeviceInfo& di = g_dev[dev];
+    if (!di.checked) {
+        int major = 0;
+        if ((e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess) return (int)e;
+        cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&di.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        di.ok = (major == 10);
+        di.checked = 1;
+    }
+    *out = &di;
+    return di.ok ? TVQ_OK : TVQ_ERR_DEVICE;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int pad_dim(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : d <= 128 ? 128 : 256; }
+
+inline int launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? TVQ_OK : (int)e;
+}
+
+template <int DP, bool TRAIN>
+int launch_fwd_simt(const FwdParams& p, const SmemPlan& pl, const DeviceInfo& di, cudaStream_t stream) {
+    auto kern = fwd_simt_kernel<DP, TRAIN>;
+    static int configured_smem = -1;   // per instantiation (host-side caches; benign if raced)
+    static int occ_smem = -1, occ_val = 0;
+    if (pl.total > configured_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total);
+        if (e != cudaSuccess) return (int)e;
+        configured_smem = pl.total;
+    }
+    if (occ_smem != pl.total) {
+        int o = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, pl.total);
+        if (e != cudaSuccess) return (int)e;
+        occ_val = o;
+        occ_smem = pl.total;
+    }
+    const int occ = occ_val;
+    if (occ < 1) return TVQ_ERR_UNSUPPORTED;
+    long long grid = (long long)occ * di.sm_count;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    kern<<<(unsigned)grid, kThreads, pl.total, stream>>>(p);
+    return launch_status();
+}
+
+template <bool TRAIN>
+int dispatch_fwd_simt(int dp, const FwdParams& p, const SmemPlan& pl, const DeviceInfo& di, cudaStream_t s) {
+    switch (dp) {
+        case 32: return launch_fwd_simt<32, TRAIN>(p, pl, di, s);
+        case 64: return launch_fwd_simt<64, TRAIN>(p, pl, di, s);
+        case 128: return launch_fwd_simt<128, TRAIN>(p, pl, di, s);
+        case 256: return launch_fwd_simt<256, TRAIN>(p, pl, di, s);
+    }
+    return TVQ_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tvq_abi_version(void) { return 1; }
+
+const char* tvq_error_string(int code) {
+    switch (code) {
+        case TVQ_OK: return "ok";
+        case TVQ_ERR_UNSUPPORTED: return "tvq: unsupported shape (need 1 <= d <= 256, d % 4 == 0, k >= 1, k*d < 2^31)";
+        case TVQ_ERR_BAD_ARG: return "tvq: bad argument (null or misaligned pointer, or workspace too small)";
+        case TVQ_ERR_DEVICE: return "tvq: current device is not an sm_100 (B200) GPU";
+    }
+    return code > 0 ? cudaGetErrorString((cudaError_t)code) : "tvq: unknown error";
+}
+
+int tvq_device_check(int device, int* sm_count) {
+    int major = 0, sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (sm_count) *sm_count = sms;
+    return major == 10 ? TVQ_OK : TVQ_ERR_DEVICE;
+}
+
+size_t tvq_workspace_bytes(int64_t n, int k, int d) {
+    (void)n;
+    (void)d;
+    return sizeof(WsHeader) + (((size_t)(k > 0 ? k : 0) + 3) & ~(size_t)3) * sizeof(float) + 64;
+}
+
+int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, unsigned flags,
+                float commitment_weight, int64_t* idx, float* q, float* stats, float* scalars, void* workspace,
+                size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (k < 1 || d < 4 || d > 256 || (d & 3) || n < 0 || (int64_t)k * d >= (int64_t(1) << 31)) return TVQ_ERR_UNSUPPORTED;
+    if (!x || !codebook || !idx || !stats || !scalars || !workspace) return TVQ_ERR_BAD_ARG;
+    if (!aligned16(x) || !aligned16(codebook) || !aligned16(stats) || !aligned16(workspace) || (q && !aligned16(q)))
+        return TVQ_ERR_BAD_ARG;
+    if ((flags & TVQ_F_WRITE_Q) && !q) return TVQ_ERR_BAD_ARG;
+    if (workspace_bytes < tvq_workspace_bytes(n, k, d)) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+
+    WsHeader* hdr = reinterpret_cast<WsHeader*>(workspace);
+    float* e2 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + sizeof(WsHeader));
+    const bool train = flags & TVQ_F_TRAIN;
+    const int64_t stats_len = TVQ_STATS_LEN(k, d);
+
+    {   // per-call preparation: |e|^2, zero statistics / loss
+        int64_t work = stats_len / 4 > (int64_t)k * 32 ? stats_len / 4 : (int64_t)k * 32;
+        int blocks = (int)((work + 255) / 256);
+        if (blocks > 4 * di->sm_count) blocks = 4 * di->sm_count;
+        if (blocks < 1) blocks = 1;
+        prep_kernel<<<blocks, 256, 0, stream>>>(codebook, k, d, e2, hdr, stats, stats_len);
+        if ((rc = launch_status()) != TVQ_OK) return rc;
+    }
+    if (n == 0) return TVQ_OK;   // nothing to assign; scalars are left to the caller (reference yields NaN)
+
+    const int dp = pad_dim(d);
+    FwdParams p;
+    p.x = x; p.cb = codebook; p.n = n; p.k = k; p.d = d;
+    p.idx = idx; p.q = (flags & TVQ_F_WRITE_Q) ? q : nullptr; p.stats = stats; p.scalars = scalars;
+    p.hdr = hdr; p.e2 = e2; p.commitment_weight = commitment_weight;
+    p.num_tiles = (int)((n + kBM - 1) / kBM);
+    p.exact = (flags & TVQ_F_EXACT) ? 1 : 0;
+    p.given_idx = (flags & TVQ_F_GIVEN_IDX) ? 1 : 0;
+    p.use_hist = k <= 2048;
+    p.stats_mode = kStatsNone;
+    if (train) p.stats_mode = ((int64_t)k * dp <= 8192 && k <= 512) ? kStatsSmall : kStatsLarge;
+    SmemPlan pl = make_smem_plan(dp, k, p.stats_mode, p.use_hist, kBN);
+    if (pl.total > di->max_smem_optin) return TVQ_ERR_UNSUPPORTED;
+    return train ? dispatch_fwd_simt<true>(dp, p, pl, *di, stream) : dispatch_fwd_simt<false>(dp, p, pl, *di, stream);
+}
+
+int tvq_ema_update(const float* stats, float* cluster_size, float* embed_avg, float* embed, float* embed_prev,
+                   int k, int d, double decay, double eps, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (k < 1 || d < 4 || (d & 3)) return TVQ_ERR_UNSUPPORTED;
+    if (!stats || !cluster_size || !embed_avg || !embed || !workspace || workspace_bytes < sizeof(WsHeader)) return TVQ_ERR_BAD_ARG;
+    if (!aligned16(stats) || !aligned16(embed_avg) || !aligned16(embed) || (embed_prev && !aligned16(embed_prev))) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    EmaParams p;
+    p.stats = stats; p.cluster_size = cluster_size; p.embed_avg = embed_avg; p.embed = embed; p.embed_prev = embed_prev;
+    p.k = k; p.d = d;
+    p.decay = (float)decay;                 // python double -> tensor dtype, as mul_(decay) does
+    p.one_minus_decay = (float)(1.0 - decay);
+    p.eps = (float)eps;
+    p.k_eps = (float)((double)k * eps);
+    p.hdr = reinterpret_cast<WsHeader*>(workspace);
+    int64_t work = (int64_t)k * (d / 4);
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > di->sm_count) blocks = di->sm_count;
+    if (blocks < 1) blocks = 1;
+    ema_kernel<<<blocks, 256, 0, stream>>>(p);
+    return launch_status();
+}
+
+int tvq_backward(const float* g_q, const float* g_scalars, const float* x, const int64_t* idx, const float* codebook,
+                 int64_t n, int k, int d, float commitment_weight, float* g_x, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    (void)k;
+    if (d < 4 || (d & 3) || n < 0) return TVQ_ERR_UNSUPPORTED;
+    if (n == 0) return TVQ_OK;
+    if (!g_q || !x || !idx || !codebook || !g_x) return TVQ_ERR_BAD_ARG;
+    if (!aligned16(g_q) || !aligned16(x) || !aligned16(codebook) || !aligned16(g_x)) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    const float scale = (float)(2.0 / ((double)n * (double)d));
+    int64_t work = n * (d / 4);
+    int64_t blocks = (work + 255) / 256;
+    if (blocks > 8LL * di->sm_count) blocks = 8LL * di->sm_count;
+    backward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g_q, g_scalars, x, idx, codebook, n, d, commitment_weight, scale, g_x);
+    return launch_status();
+}
+
+int tvq_gather(const int64_t* tokens, const float* codebook, int64_t b, int64_t t, int k, int d, int layout,
+               float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (k < 1 || d < 1 || b < 0 || t < 0 || (layout != 0 && layout != 1)) return TVQ_ERR_UNSUPPORTED;
+    if (b * t == 0) return TVQ_OK;
+    if (!tokens || !codebook || !out) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    if (layout == 0) {
+        if ((d & 3) || !aligned16(codebook) || !aligned16(out)) return TVQ_ERR_UNSUPPORTED;
+        int64_t blocks = (b * t + 7) / 8;
+        if (blocks > 16LL * di->sm_count) blocks = 16LL * di->sm_count;
+        gather_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tokens, codebook, b * t, k, d, out);
+    } else {
+        int64_t tiles = b * ((t + 31) / 32) * ((d + 31) / 32);
+        if (tiles > 16LL * di->sm_count) tiles = 16LL * di->sm_count;
+        gather_transposed_kernel<<<(unsigned)tiles, 256, 0, stream>>>(tokens, codebook, b, t, k, d, out);
+    }
+    return launch_status();
+}
+
+int tvq_neg_dist(const float* x, const float* codebook, int64_t n, int k, int d, float* dist, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (k < 1 || d < 4 || (d & 3) || n < 0) return TVQ_ERR_UNSUPPORTED;
+    if (n == 0) return TVQ_OK;
+    if (!x || !codebook || !dist || !aligned16(x) || !aligned16(codebook)) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > 16LL * di->sm_count) blocks = 16LL * di->sm_count;
+    neg_dist_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, codebook, n, k, d, dist);
+    return launch_status();
+}
+
+int tvq_reseed(const float* x, const int64_t* rows, const float* cluster_size, float threshold, float* embed,
+               int64_t n, int k, int d, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (k < 1 || d < 4 || (d & 3) || n < 1) return TVQ_ERR_UNSUPPORTED;
+    if (!x || !rows || !cluster_size || !embed || !aligned16(x) || !aligned16(embed)) return TVQ_ERR_BAD_ARG;
+    int blocks = (k + 7) / 8;
+    reseed_kernel<<<blocks, 256, 0, stream>>>(x, rows, cluster_size, threshold, embed, n, k, d);
+    return launch_status();
+}
+
+}  // extern "C"

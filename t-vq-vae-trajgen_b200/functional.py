@@ -1,0 +1,180 @@
+"""Tensor-level wrappers of the C ABI (include/tvq.h) and the autograd step built on them.
+
+PyTorch is plumbing here: it owns the device memory and the stream; every arithmetic step of
+the hot path runs in libtvq_b200.so.  All functions need contiguous fp32 CUDA tensors and raise
+otherwise — there is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+__all__ = ["Workspace", "vq_forward_raw", "vq_ema_update", "vq_backward", "vq_gather", "vq_neg_dist",
+           "vq_reseed", "stats_offset", "stats_len", "VQTrainStep"]
+
+
+def stats_offset(k: int) -> int:
+    """Element offset of embed_sum inside the packed statistics buffer (TVQ_STATS_OFFSET)."""
+    return (k + 3) & ~3
+
+
+def stats_len(k: int, d: int) -> int:
+    return stats_offset(k) + k * d
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: the B200 VQ kernels need a CUDA tensor (got "
+                           f"{getattr(t, 'device', type(t))}); there is no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+
+
+class Workspace:
+    """Per-codebook device scratch: launch-ticket header + |e|^2 table, and the packed statistics."""
+
+    def __init__(self, k: int, d: int, device: torch.device):
+        lib = _lib.load()
+        self.k, self.d, self.device = k, d, device
+        self.nbytes = int(lib.tvq_workspace_bytes(0, k, d))
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)   # zeroed once (ticket)
+        self.stats = torch.empty(stats_len(k, d), dtype=torch.float32, device=device)
+
+    def matches(self, k: int, d: int, device: torch.device) -> bool:
+        return self.k == k and self.d == d and self.device == device
+
+
+def vq_forward_raw(x: torch.Tensor, codebook: torch.Tensor, ws: Workspace, *, train: bool, write_q: bool = True,
+                   idx: Optional[torch.Tensor] = None, flags: int = 0, commitment_weight: float = 1.0
+                   ) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+    """tvq_forward: (idx[n] int64, q[n,d] or None, scalars[8]).  Statistics land in ws.stats.
+
+    `idx` given -> the codes are an input (TVQ_F_GIVEN_IDX) and only gather/ST/loss/statistics run.
+    scalars: [0] commit loss (train), [1] perplexity, [2] commitment_weight * commit loss,
+    [4:6] uint32 diagnostics (view as int32): rows re-scored in fp64, rows fully re-scanned.
+    """
+    _need(x, "x")
+    _need(codebook, "codebook")
+    n, d = x.shape
+    k = codebook.shape[0]
+    if codebook.shape[1] != d:
+        raise ValueError(f"codebook dim {codebook.shape[1]} != latent dim {d}")
+    f = flags | (_lib.F_TRAIN if train else 0) | (_lib.F_WRITE_Q if write_q else 0)
+    if idx is None:
+        idx = torch.empty(n, dtype=torch.int64, device=x.device)
+    else:
+        _need(idx, "idx", torch.int64)
+        f |= _lib.F_GIVEN_IDX
+    q = torch.empty_like(x) if write_q else None
+    scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32, device=x.device)
+    if n == 0:
+        scalars.fill_(float("nan"))     # mean over an empty batch, as in the reference
+    rc = _lib.load().tvq_forward(x.data_ptr(), codebook.data_ptr(), n, k, d, f, float(commitment_weight), idx.data_ptr(),
+                                 q.data_ptr() if write_q else None, ws.stats.data_ptr(), scalars.data_ptr(),
+                                 ws.buf.data_ptr(), ws.nbytes, _stream())
+    _lib.check(rc, "tvq_forward")
+    return idx, q, scalars
+
+
+def vq_ema_update(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg: torch.Tensor, embed: torch.Tensor,
+                  embed_prev: Optional[torch.Tensor], decay: float, eps: float, ws: Workspace) -> None:
+    _need(stats, "stats"); _need(cluster_size, "cluster_size"); _need(embed_avg, "embed_avg"); _need(embed, "embed")
+    k, d = embed.shape
+    rc = _lib.load().tvq_ema_update(stats.data_ptr(), cluster_size.data_ptr(), embed_avg.data_ptr(), embed.data_ptr(),
+                                    embed_prev.data_ptr() if embed_prev is not None else None, k, d, float(decay),
+                                    float(eps), ws.buf.data_ptr(), ws.nbytes, _stream())
+    _lib.check(rc, "tvq_ema_update")
+
+
+def vq_backward(g_q: torch.Tensor, g_scalars: Optional[torch.Tensor], x: torch.Tensor, idx: torch.Tensor,
+                codebook: torch.Tensor, commitment_weight: float) -> torch.Tensor:
+    """g_x = g_q + (g_scalars[0] + w * g_scalars[2]) * 2/(n d) * (x - q_st)."""
+    _need(g_q, "g_q"); _need(x, "x"); _need(idx, "idx", torch.int64); _need(codebook, "codebook")
+    n, d = x.shape
+    g_x = torch.empty_like(x)
+    rc = _lib.load().tvq_backward(g_q.data_ptr(), g_scalars.data_ptr() if g_scalars is not None else None, x.data_ptr(),
+                                  idx.data_ptr(), codebook.data_ptr(), n, codebook.shape[0], d,
+                                  float(commitment_weight), g_x.data_ptr(), _stream())
+    _lib.check(rc, "tvq_backward")
+    return g_x
+
+
+def vq_gather(tokens: torch.Tensor, codebook: torch.Tensor, channels_first: bool = False) -> torch.Tensor:
+    """tokens (b, t) int64 -> (b, t, d), or (b, d, t) when channels_first (models/maskgit.py:465-470)."""
+    _need(tokens, "tokens", torch.int64)
+    _need(codebook, "codebook")
+    if tokens.dim() != 2:
+        raise ValueError("tokens must be (b, t)")
+    b, t = tokens.shape
+    k, d = codebook.shape
+    out = torch.empty((b, d, t) if channels_first else (b, t, d), dtype=torch.float32, device=tokens.device)
+    rc = _lib.load().tvq_gather(tokens.data_ptr(), codebook.data_ptr(), b, t, k, d, 1 if channels_first else 0,
+                                out.data_ptr(), _stream())
+    _lib.check(rc, "tvq_gather")
+    return out
+
+
+def vq_neg_dist(x: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
+    """Dense -(|x|^2 - 2 x.e + |e|^2) [n, k] for the stochastic branch (vq.py:210-214)."""
+    _need(x, "x"); _need(codebook, "codebook")
+    n, d = x.shape
+    k = codebook.shape[0]
+    dist = torch.empty((n, k), dtype=torch.float32, device=x.device)
+    rc = _lib.load().tvq_neg_dist(x.data_ptr(), codebook.data_ptr(), n, k, d, dist.data_ptr(), _stream())
+    _lib.check(rc, "tvq_neg_dist")
+    return dist
+
+
+def vq_reseed(x: torch.Tensor, rows: torch.Tensor, cluster_size: torch.Tensor, threshold: float,
+              embed: torch.Tensor) -> None:
+    _need(x, "x"); _need(rows, "rows", torch.int64); _need(cluster_size, "cluster_size"); _need(embed, "embed")
+    n, d = x.shape
+    rc = _lib.load().tvq_reseed(x.data_ptr(), rows.data_ptr(), cluster_size.data_ptr(), float(threshold),
+                                embed.data_ptr(), n, embed.shape[0], d, _stream())
+    _lib.check(rc, "tvq_reseed")
+
+
+class VQTrainStep(torch.autograd.Function):
+    """One training-mode codebook step: assign + ST + commit loss + EMA, differentiable in x.
+
+    forward(x[n,d], codebook_module, commitment_weight, given_idx|None)
+        -> (q_st[n,d], idx[n], scalars[8])   scalars[0] = commit loss, [1] = perplexity, [2] = w * commit
+    backward: g_x = g_q + (g_scalars[0] + w g_scalars[2]) * 2/(n d) * (x - q_st)   
+    The EMA update runs inside forward (after the optional all-reduce of the packed statistics,
+    vq.py:229/234); the pre-update codebook is kept for the backward.
+    """
+
+    @staticmethod
+    def forward(ctx, x, cb, commitment_weight, given_idx):
+        ws = cb._workspace(x.device)
+        idx, q, scalars = vq_forward_raw(x, cb._embed_data(), ws, train=True, write_q=True, idx=given_idx,
+                                         commitment_weight=commitment_weight)
+        cb._all_reduce_stats(ws.stats)
+        prev = torch.empty_like(cb._embed_data()) if ctx.needs_input_grad[0] else None
+        vq_ema_update(ws.stats, cb.cluster_size, cb.embed_avg, cb._embed_data(), prev, cb.decay, cb.eps, ws)
+        ctx.save_for_backward(x, idx, prev)
+        ctx.commitment_weight = float(commitment_weight)
+        ctx.mark_non_differentiable(idx)
+        return q, idx, scalars
+
+    @staticmethod
+    def backward(ctx, g_q, g_idx, g_scalars):
+        x, idx, prev = ctx.saved_tensors
+        if g_q is None:
+            g_q = torch.zeros_like(x)
+        elif not g_q.is_contiguous():
+            g_q = g_q.contiguous()
+        if g_scalars is None:
+            return g_q, None, None, None
+        if not g_scalars.is_contiguous():
+            g_scalars = g_scalars.contiguous()
+        return vq_backward(g_q, g_scalars, x, idx, prev, ctx.commitment_weight), None, None, None

@@ -1,0 +1,322 @@
+"""`VectorQuantize` / `EuclideanCodebook` with the reference's module surface, running on the
+B200 kernels of libtvq_b200.so.
+
+Drop-in for /root/reference/timevqvae/models/vq.py:124-407: same constructor keywords (unknown
+ones are swallowed, as `**config["VQ-VAE"]` needs, trainers/stage1.py:56-61), same call
+`vq(x, svq_temp=None) -> (quantize, embed_ind, vq_loss, perplexity)`, same attributes read by the
+callers (`_codebook.embed`, `project_out`, `codebook`, `_codebook.perplexity`, `codebook_size`) and the
+same four buffers `_codebook.{initted,cluster_size,embed_avg,embed}` so Lightning checkpoints of
+the reference load unchanged.
+
+What differs is where the arithmetic runs: distance + argmin + gather + straight-through +
+commitment loss + EMA statistics are ONE fused kernel, the EMA normalisation a second one; the
+N x K `dist` and one-hot matrices of the reference are never materialised.  Host-side torch ops
+remain only for what the reference itself leaves to `nn.Linear` / `rearrange` (projections, head
+split, layout) and for the RNG-consuming branches (k-means seeding, dead-code sampling,
+`svq_temp` sampling) so that they share torch's RNG stream with the reference.
+"""
+from __future__ import annotations
+
+from typing import Optional, Union
+
+import torch
+import torch.distributed as distributed
+import torch.nn.functional as F
+from torch import nn
+
+from . import functional as TF
+
+
+def _default(val, d):
+    return val if val is not None else d
+
+
+def sample_vectors(samples: torch.Tensor, num: int) -> torch.Tensor:
+    """Rows for k-means seeding / dead-code replacement; same RNG calls as vq.py:67-75."""
+    n, device = samples.shape[0], samples.device
+    if n >= num:
+        indices = torch.randperm(n, device=device)[:num]
+    else:
+        indices = torch.randint(0, n, (num,), device=device)
+    return indices
+
+
+def orthogonal_loss_fn(t: torch.Tensor) -> torch.Tensor:
+    """Eq. (2) of arXiv:2112.00384 as used at vq.py:112-118 (off by default; plain torch)."""
+    n = t.shape[0]
+    normed = F.normalize(t, p=2, dim=-1)
+    cosine = normed @ normed.t()
+    return ((cosine - torch.eye(n, device=t.device)) ** 2).sum() / (n ** 2)
+
+
+class EuclideanCodebook(nn.Module):
+    """State + kernels of one Euclidean codebook (vq.py:124-251)."""
+
+    def __init__(self, dim, codebook_size, kmeans_init=False, kmeans_iters=10, decay=0.8, eps=1e-5,
+                 threshold_ema_dead_code=2, use_ddp=False, learnable_codebook=False, sample_codebook_temp=0,
+                 emb_dropout=0.0):
+        super().__init__()
+        if dim % 4 != 0 or dim > 256:
+            raise NotImplementedError(
+                f"codebook_dim={dim}: the B200 kernels need codebook_dim % 4 == 0 and <= 256 (no fallback path)")
+        self.decay = decay
+        embed = (torch.randn if not kmeans_init else torch.zeros)(codebook_size, dim)
+        self.dim = dim
+        self.codebook_size = codebook_size
+        self.kmeans_iters = kmeans_iters
+        self.eps = eps
+        self.threshold_ema_dead_code = threshold_ema_dead_code
+        self.sample_codebook_temp = sample_codebook_temp
+        self.emb_dropout = emb_dropout
+        self.use_ddp = use_ddp
+
+        self.register_buffer("initted", torch.Tensor([not kmeans_init]))
+        self.register_buffer("cluster_size", torch.zeros(codebook_size))
+        self.register_buffer("embed_avg", embed.clone())
+        self.learnable_codebook = learnable_codebook
+        if learnable_codebook:
+            self.embed = nn.Parameter(embed)
+        else:
+            self.register_buffer("embed", embed)
+
+        self.perplexity = None
+        self._last_ind = None
+        self._ws: Optional[TF.Workspace] = None
+        # host mirror of `initted` so the hot path never reads a device flag (the reference syncs
+        # on `if self.initted:` every call, vq.py:172)
+        self._initted_host: Optional[bool] = not kmeans_init
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _workspace(self, device: torch.device) -> TF.Workspace:
+        if self._ws is None or not self._ws.matches(self.codebook_size, self.dim, device):
+            self._ws = TF.Workspace(self.codebook_size, self.dim, device)
+        return self._ws
+
+    def _all_reduce_stats(self, stats: torch.Tensor) -> None:
+        """The reference's two all_reduce hooks (vq.py:229, :234) as ONE call on the packed buffer."""
+        if self.use_ddp and distributed.is_available() and distributed.is_initialized() \
+                and distributed.get_world_size() > 1:
+            distributed.all_reduce(stats)
+
+    def _embed_data(self) -> torch.Tensor:
+        e = self.embed.data if self.learnable_codebook else self.embed
+        if not e.is_contiguous():
+            raise ValueError("codebook buffer must be contiguous")
+        return e
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._initted_host = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    @property
+    def embed_onehot(self):
+        """N x K one-hot of the last call (vq.py:248). Nothing reads it; materialised on demand only."""
+        if self._last_ind is None:
+            return None
+        return F.one_hot(self._last_ind.reshape(-1), self.codebook_size).type(torch.float32)
+
+    # -- optional branches that consume torch's RNG ---------------------------------------------
+    @torch.no_grad()
+    def init_embed_(self, data: torch.Tensor) -> None:
+        """k-means initialisation (vq.py:171-179, :78-106): Lloyd iterations on the kernels."""
+        if self._initted_host is None:
+            self._initted_host = bool(self.initted.item())     # one sync, then cached
+        if self._initted_host:
+            return
+        k = self.codebook_size
+        ws = self._workspace(data.device)
+        means = data[sample_vectors(data, k)].contiguous()
+        off = TF.stats_offset(k)
+        bins = None
+        for _ in range(self.kmeans_iters):
+            TF.vq_forward_raw(data, means, ws, train=True, write_q=False)      # counts + per-code sums
+            bins = ws.stats[:k].clone()
+            sums = ws.stats[off:off + k * self.dim].view(k, self.dim)
+            empty = bins == 0
+            new_means = sums / bins.masked_fill(empty, 1)[:, None]
+            means = torch.where(empty[:, None], means, new_means).contiguous()
+        self._embed_data().copy_(means)
+        self.embed_avg.copy_(means)
+        self.cluster_size.copy_(bins)
+        self.initted.fill_(1.0)
+        self._initted_host = True
+
+    @torch.no_grad()
+    def expire_codes_(self, batch_samples: torch.Tensor) -> None:
+        """Dead-code re-seed (vq.py:187-195); only `embed` is replaced, as in the reference."""
+        if self.threshold_ema_dead_code == 0:
+            return
+        expired = self.cluster_size < self.threshold_ema_dead_code
+        if not torch.any(expired):                       # same sync (and same RNG use) as the reference
+            return
+        flat = batch_samples.reshape(-1, batch_samples.shape[-1])
+        rows = sample_vectors(flat, self.codebook_size)
+        TF.vq_reseed(flat.contiguous(), rows, self.cluster_size, self.threshold_ema_dead_code, self._embed_data())
+
+    # -- the step -----------------------------------------------------------------------------
+    def _assign(self, flat: torch.Tensor, svq_temp):
+        """Codes chosen by the caller-visible rule of vq.py:216-222; None means 'let the kernel argmin'."""
+        temp = 0.0 if not svq_temp else svq_temp
+        embed = self._embed_data()
+        scoring = embed
+        if self.emb_dropout and self.training:
+            scoring = F.dropout(embed.t(), self.emb_dropout).t().contiguous()   # vq.py:207-208
+        if temp == 0 and scoring is embed:
+            return None
+        if temp == 0:
+            ws = self._workspace(flat.device)
+            idx, _, _ = TF.vq_forward_raw(flat, scoring, ws, train=False, write_q=False)
+            return idx
+        dist = TF.vq_neg_dist(flat, scoring)
+        return torch.distributions.categorical.Categorical(logits=dist / temp).sample()    # vq.py:55-56
+
+    def step(self, x: torch.Tensor, svq_temp=None, *, commitment_weight: float = 0.0, straight_through: bool = False):
+        """Fused codebook step on x (..., d).
+
+        Returns (quantize, embed_ind, commit_loss or None, weighted_loss[1] or None).  With
+        `straight_through` (training VectorQuantize path) quantize is x + (e[idx] - x), commit_loss
+        the mean squared difference and weighted_loss = commitment_weight * commit_loss, all
+        differentiable in x; otherwise quantize is the plain gather the reference's
+        EuclideanCodebook.forward returns.
+        """
+        shape = x.shape
+        flat = x.reshape(-1, shape[-1])
+        if flat.dtype != torch.float32:
+            flat = flat.float()                              # @autocast(enabled=False) region, vq.py:197
+        if not flat.is_contiguous():
+            flat = flat.contiguous()
+        TF._need(flat, "x")
+        if self._initted_host is not True:
+            self.init_embed_(flat.detach())
+        given = self._assign(flat.detach(), svq_temp)
+        ws = self._workspace(flat.device)
+        commit = weighted = None
+        if self.training:
+            if straight_through:
+                q, idx, scalars = TF.VQTrainStep.apply(flat, self, commitment_weight, given)
+                commit, weighted = scalars[0], scalars[2:3]
+            else:
+                idx, _, scalars = TF.vq_forward_raw(flat.detach(), self._embed_data(), ws, train=True, write_q=False,
+                                                    idx=given)
+                self._all_reduce_stats(ws.stats)
+                q = None
+                prev = torch.empty_like(self._embed_data())
+                TF.vq_ema_update(ws.stats, self.cluster_size, self.embed_avg, self._embed_data(), prev, self.decay,
+                                 self.eps, ws)
+                q = TF.vq_gather(idx.view(1, -1), prev).view(flat.shape)
+            self.expire_codes_(x.detach())
+        else:
+            idx, q, scalars = TF.vq_forward_raw(flat.detach(), self._embed_data(), ws, train=False, write_q=True,
+                                                idx=given)
+        self.perplexity = scalars[1].detach()
+        ind = idx.view(*shape[:-1])
+        self._last_ind = ind
+        return q.view(shape), ind, commit, weighted
+
+    def forward(self, x, svq_temp: Union[float, None] = None):
+        """(quantize, embed_ind) exactly as EuclideanCodebook.forward (vq.py:198-251)."""
+        q, ind, _, _ = self.step(x, svq_temp)
+        return q, ind
+
+
+class VectorQuantize(nn.Module):
+    """Reference-compatible wrapper (vq.py:255-407)."""
+
+    def __init__(self, dim, codebook_size, codebook_dim=None, heads=1, decay=0.8, eps=1e-5, kmeans_init=False,
+                 kmeans_iters=10, use_cosine_sim=False, threshold_ema_dead_code=0, channel_last=True,
+                 accept_image_fmap=False, commitment_weight=1.0, orthogonal_reg_weight=0.0,
+                 orthogonal_reg_active_codes_only=False, orthogonal_reg_max_codes=None, sample_codebook_temp=0.0,
+                 sync_codebook=False, emb_dropout=0.0, **kwargs):
+        super().__init__()
+        self.heads = heads
+        codebook_dim = _default(codebook_dim, dim)
+        codebook_input_dim = codebook_dim * heads
+        requires_projection = codebook_input_dim != dim
+        self.project_in = nn.Linear(dim, codebook_input_dim) if requires_projection else nn.Identity()
+        self.project_out = nn.Linear(codebook_input_dim, dim) if requires_projection else nn.Identity()
+
+        self.eps = eps
+        self.commitment_weight = commitment_weight
+        has_codebook_orthogonal_loss = orthogonal_reg_weight > 0
+        self.orthogonal_reg_weight = orthogonal_reg_weight
+        self.orthogonal_reg_active_codes_only = orthogonal_reg_active_codes_only
+        self.orthogonal_reg_max_codes = orthogonal_reg_max_codes
+
+        # `use_cosine_sim` is accepted and ignored, as in the reference (only the Euclidean class exists, vq.py:300)
+        self._codebook = EuclideanCodebook(
+            dim=codebook_dim, codebook_size=codebook_size, kmeans_init=kmeans_init, kmeans_iters=kmeans_iters,
+            decay=decay, eps=eps, threshold_ema_dead_code=threshold_ema_dead_code, use_ddp=sync_codebook,
+            learnable_codebook=has_codebook_orthogonal_loss, sample_codebook_temp=sample_codebook_temp,
+            emb_dropout=emb_dropout)
+        self.codebook_size = codebook_size
+        self.accept_image_fmap = accept_image_fmap
+        self.channel_last = channel_last
+
+    @property
+    def codebook(self):
+        return self._codebook.embed
+
+    def forward(self, x, svq_temp: Union[float, None] = None):
+        """x: (B, N, D) -> (quantize, embed_ind, vq_loss dict, perplexity)   (vq.py:325-407)"""
+        device, heads = x.device, self.heads
+        need_transpose = not self.channel_last and not self.accept_image_fmap
+        vq_loss = {"loss": None, "commit_loss": 0.0, "orthogonal_reg_loss": 0.0}
+
+        if self.accept_image_fmap:
+            b, c, height, width = x.shape
+            x = x.permute(0, 2, 3, 1).reshape(b, height * width, c)
+        if need_transpose:
+            x = x.transpose(1, 2)
+        x = self.project_in(x)
+        if heads > 1:
+            b, n, hd = x.shape
+            x = x.reshape(b, n, heads, hd // heads).permute(0, 2, 1, 3).reshape(b * heads, n, hd // heads)
+
+        want_commit = self.training and self.commitment_weight > 0
+        quantize, embed_ind, commit_loss, weighted = self._codebook.step(
+            x, svq_temp, commitment_weight=self.commitment_weight if want_commit else 0.0,
+            straight_through=self.training)
+
+        if self.training:
+            if want_commit:
+                # [0.] + commit * w of vq.py:338,366 — the product comes out of the kernel (scalars[2])
+                vq_loss["commit_loss"] = commit_loss
+                vq_loss["loss"] = weighted
+            if self.orthogonal_reg_weight > 0:
+                codebook = self.codebook
+                if self.orthogonal_reg_active_codes_only:
+                    codebook = codebook[torch.unique(embed_ind)]
+                num_codes = codebook.shape[0]
+                if self.orthogonal_reg_max_codes is not None and num_codes > self.orthogonal_reg_max_codes:
+                    rand_ids = torch.randperm(num_codes, device=device)[: self.orthogonal_reg_max_codes]
+                    codebook = codebook[rand_ids]
+                orthogonal_reg_loss = orthogonal_loss_fn(codebook)
+                vq_loss["orthogonal_reg_loss"] = orthogonal_reg_loss
+                base = vq_loss["loss"] if vq_loss["loss"] is not None else torch.zeros(1, device=device)
+                vq_loss["loss"] = base + orthogonal_reg_loss * self.orthogonal_reg_weight
+
+        if vq_loss["loss"] is None:
+            vq_loss["loss"] = torch.zeros(1, device=device, requires_grad=self.training)
+        if heads > 1:
+            bh, n, d = quantize.shape
+            quantize = quantize.reshape(bh // heads, heads, n, d).permute(0, 2, 1, 3).reshape(bh // heads, n, heads * d)
+            embed_ind = embed_ind.reshape(bh // heads, heads, n).permute(0, 2, 1)
+        quantize = self.project_out(quantize)
+        if need_transpose:
+            quantize = quantize.transpose(1, 2)
+        if self.accept_image_fmap:
+            quantize = quantize.reshape(b, height, width, -1).permute(0, 3, 1, 2)
+            embed_ind = embed_ind.reshape(b, height, width, *embed_ind.shape[2:])
+        return quantize, embed_ind, vq_loss, self._codebook.perplexity
+
+    @torch.no_grad()
+    def tokenize(self, x: torch.Tensor) -> torch.Tensor:
+        """Indices only (what stage 2/3 keep of an eval call, models/maskgit.py:130-134): skips the q write."""
+        cb = self._codebook
+        x = self.project_in(x)
+        shape = x.shape
+        flat = x.reshape(-1, shape[-1]).float().contiguous()
+        idx, _, scalars = TF.vq_forward_raw(flat, cb._embed_data(), cb._workspace(flat.device), train=False,
+                                            write_q=False)
+        cb.perplexity = scalars[1]
+        return idx.view(*shape[:-1])

