@@ -76,8 +76,10 @@ def vq_forward_raw(x: torch.Tensor, codebook: torch.Tensor, ws: Workspace, *, tr
         f |= _lib.F_GIVEN_IDX
     q = torch.empty_like(x) if write_q else None
     scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32, device=x.device)
-    if n == 0:
-        scalars.fill_(float("nan"))     # mean over an empty batch, as in the reference
+    if n == 0:                          # nothing to launch: zero statistics, NaN means (as the reference)
+        scalars.fill_(float("nan"))
+        ws.stats.zero_()
+        return idx, q, scalars
     rc = _lib.load().tvq_forward(x.data_ptr(), codebook.data_ptr(), n, k, d, f, float(commitment_weight), idx.data_ptr(),
                                  q.data_ptr() if write_q else None, ws.stats.data_ptr(), scalars.data_ptr(),
                                  ws.buf.data_ptr(), ws.nbytes, _stream())
