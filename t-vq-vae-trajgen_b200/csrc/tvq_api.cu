@@ -2,11 +2,13 @@
 // Built for sm_100a only (see __graft_entry__.build); no torch, no C++ exceptions across the ABI.
 #include "../../include/tvq.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "tvq_aux.cuh"
 #include "tvq_common.cuh"
 #include "tvq_fwd_simt.cuh"
+#include "tvq_fwd_umma.cuh"
 
 using namespace tvq;
 
@@ -83,6 +85,75 @@ int dispatch_fwd_simt(int dp, const FwdParams& p, const SmemPlan& pl, const Devi
     return TVQ_ERR_UNSUPPORTED;
 }
 
+// ---------------------------------------------------------------------------------------------
+// tcgen05 path: TMA tensor map over x, stage count from the shared-memory budget, launch.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// x viewed as a [n, d] fp32 tensor; one box = 32 floats (128 bytes, the swizzle span) x `rows` latents.
+int make_x_tensor_map(CUtensorMap* tm, const float* x, int64_t n, int d, int rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return TVQ_ERR_DEVICE;
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)n};
+    cuuint64_t gstride[1] = {(cuuint64_t)d * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? TVQ_OK : TVQ_ERR_BAD_ARG;
+}
+
+template <int DP, int KP, bool TRAIN>
+int launch_fwd_umma(FwdParams p, const DeviceInfo& di, cudaStream_t stream) {
+    auto kern = fwd_umma_kernel<DP, KP, TRAIN>;
+    const UmmaPlan fixed = make_umma_plan(DP, KP, 0);
+    int stages = (di.max_smem_optin - fixed.total) / (kUM * DP * 4);
+    if (stages > kUMaxStages) stages = kUMaxStages;
+    if (stages < 2) return TVQ_ERR_UNSUPPORTED;
+    const UmmaPlan pl = make_umma_plan(DP, KP, stages);
+    static int configured_smem = -1;
+    if (pl.total > configured_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total);
+        if (e != cudaSuccess) return (int)e;
+        configured_smem = pl.total;
+    }
+    CUtensorMap tm;
+    int rc = make_x_tensor_map(&tm, p.x, p.n, p.d, kUM);
+    if (rc != TVQ_OK) return rc;
+    p.num_tiles = (int)((p.n + kUM - 1) / kUM);
+    int grid = p.num_tiles < di.sm_count ? p.num_tiles : di.sm_count;
+    kern<<<grid, kUThreads, pl.total, stream>>>(tm, p, stages);
+    return launch_status();
+}
+
+template <bool TRAIN>
+int dispatch_fwd_umma(int dp, int kp, const FwdParams& p, const DeviceInfo& di, cudaStream_t s) {
+    if (dp == 64) {
+        if (kp == 16) return launch_fwd_umma<64, 16, TRAIN>(p, di, s);
+        if (kp == 32) return launch_fwd_umma<64, 32, TRAIN>(p, di, s);
+        if (kp == 64) return launch_fwd_umma<64, 64, TRAIN>(p, di, s);
+    } else if (dp == 128) {
+        if (kp == 16) return launch_fwd_umma<128, 16, TRAIN>(p, di, s);
+        if (kp == 32) return launch_fwd_umma<128, 32, TRAIN>(p, di, s);
+        if (kp == 64) return launch_fwd_umma<128, 64, TRAIN>(p, di, s);
+    }
+    return TVQ_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 
 extern "C" {
@@ -143,7 +214,6 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
     }
     if (n == 0) return TVQ_OK;   // nothing to assign; scalars are left to the caller (reference yields NaN)
 
-    const int dp = pad_dim(d);
     FwdParams p;
     p.x = x; p.cb = codebook; p.n = n; p.k = k; p.d = d;
     p.idx = idx; p.q = (flags & TVQ_F_WRITE_Q) ? q : nullptr; p.stats = stats; p.scalars = scalars;
@@ -151,6 +221,15 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
     p.num_tiles = (int)((n + kBM - 1) / kBM);
     p.exact = (flags & TVQ_F_EXACT) ? 1 : 0;
     p.given_idx = (flags & TVQ_F_GIVEN_IDX) ? 1 : 0;
+    // Resident-codebook tcgen05 path: k <= 64, d <= 128 (the configs/config.yaml regime).
+    if (!(flags & (TVQ_F_EXACT | TVQ_F_GIVEN_IDX | TVQ_F_NO_UMMA)) && k <= 64 && d <= 128 && n < (int64_t(1) << 31) - 64) {
+        const int udp = d <= 64 ? 64 : 128;
+        const int ukp = k <= 16 ? 16 : k <= 32 ? 32 : 64;
+        p.use_hist = 1;
+        p.stats_mode = train ? kStatsSmall : kStatsNone;
+        return train ? dispatch_fwd_umma<true>(udp, ukp, p, *di, stream) : dispatch_fwd_umma<false>(udp, ukp, p, *di, stream);
+    }
+    const int dp = pad_dim(d);
     p.use_hist = k <= 2048;
     p.stats_mode = kStatsNone;
     if (train) p.stats_mode = ((int64_t)k * dp <= 8192 && k <= 512) ? kStatsSmall : kStatsLarge;

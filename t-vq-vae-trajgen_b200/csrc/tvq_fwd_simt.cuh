@@ -69,7 +69,7 @@ __host__ __device__ inline SmemPlan make_smem_plan(int dp, int k, int stats_mode
 // ------------------------------------------------------------------------------------------
 // Phase R: canonical fp64 scan of one row against codes [0, k) — warp-cooperative.
 // x row comes from the shared tile, code words from global memory (L1/L2 resident).
-template <int DP>
+template <int DP, int ROWS = kBM>
 __device__ __forceinline__ int canon_scan_row(const float* xt, int row, const float* cb, const float* e2g, int k,
                                               int d, int lane) {
     const int nchunk = d >> 2;
@@ -78,7 +78,7 @@ __device__ __forceinline__ int canon_scan_row(const float* xt, int row, const fl
 #pragma unroll
     for (int i = 0; i < (DP / 128 > 0 ? DP / 128 : 1); ++i) {
         int c = lane + 32 * i;
-        xv[i] = (c < nchunk) ? *reinterpret_cast<const float4*>(xt + tile_off<kBM>(row, c)) : make_float4(0, 0, 0, 0);
+        xv[i] = (c < nchunk) ? *reinterpret_cast<const float4*>(xt + tile_off<ROWS>(row, c)) : make_float4(0, 0, 0, 0);
         if (c < nchunk) p = dot4(p, xv[i], xv[i]);
     }
     const float x2 = __double2float_rn(butterfly_sum(p));
@@ -100,7 +100,7 @@ __device__ __forceinline__ int canon_scan_row(const float* xt, int row, const fl
 }
 
 // Same, restricted to a short candidate list (used by the tcgen05 path).
-template <int DP>
+template <int DP, int ROWS = kBM>
 __device__ __forceinline__ int canon_pick(const float* xt, int row, const float* cb, const float* e2g, int d,
                                           int lane, const int* cand, int ncand) {
     const int nchunk = d >> 2;
@@ -109,7 +109,7 @@ __device__ __forceinline__ int canon_pick(const float* xt, int row, const float*
 #pragma unroll
     for (int i = 0; i < (DP / 128 > 0 ? DP / 128 : 1); ++i) {
         int c = lane + 32 * i;
-        xv[i] = (c < nchunk) ? *reinterpret_cast<const float4*>(xt + tile_off<kBM>(row, c)) : make_float4(0, 0, 0, 0);
+        xv[i] = (c < nchunk) ? *reinterpret_cast<const float4*>(xt + tile_off<ROWS>(row, c)) : make_float4(0, 0, 0, 0);
         if (c < nchunk) p = dot4(p, xv[i], xv[i]);
     }
     const float x2 = __double2float_rn(butterfly_sum(p));
@@ -138,19 +138,20 @@ struct ApplyState {
 };
 
 // Gather / straight-through / loss / large-k statistics for the rows of one tile.
-template <int DP, bool TRAIN>
+template <int DP, bool TRAIN, int ROWS = kBM>
 __device__ __forceinline__ void apply_rows(const FwdParams& p, const float* xt, const int* sidx, int* hist,
-                                           int64_t row0, ApplyState& st) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                           int64_t row0, ApplyState& st, int warp = threadIdx.x >> 5,
+                                           int nwarps = kWarps) {
+    const int lane = threadIdx.x & 31;
     const int nchunk = p.d >> 2;
     float* esum = p.stats + ((p.k + 3) & ~3);
-    for (int r = warp; r < kBM; r += kWarps) {
+    for (int r = warp; r < ROWS; r += nwarps) {
         const int64_t grow = row0 + r;
         if (grow >= p.n) break;
         const int code = sidx[r];
         const float4* er = reinterpret_cast<const float4*>(p.cb + (size_t)code * p.d);
         for (int c = lane; c < nchunk; c += 32) {
-            const float4 xv = *reinterpret_cast<const float4*>(xt + tile_off<kBM>(r, c));
+            const float4 xv = *reinterpret_cast<const float4*>(xt + tile_off<ROWS>(r, c));
             const float4 ev = __ldg(er + c);
             float4 o;
             if (TRAIN) {
@@ -241,6 +242,45 @@ __device__ __forceinline__ void small_stats_tile(const FwdParams& p, const float
     __syncthreads();
 }
 
+// Last-CTA epilogue (threadFenceReduction pattern): the CTA that takes the final ticket turns the
+// global totals into the scalars.  Called by every thread of every CTA after its flush.
+template <bool TRAIN>
+__device__ __forceinline__ void finish_ticket(const FwdParams& p, double* red, int* misc) {
+    const int tid = threadIdx.x;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned t = atomicAdd(&p.hdr->ticket, 1u);
+        misc[1] = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (misc[1]) {
+        __threadfence();
+        // perplexity = exp(-sum p log(p + 1e-10)), p = counts / n  (vq.py:246-247)
+        const float fn = (float)p.n;
+        float part = 0.f;
+        for (int c = tid; c < p.k; c += blockDim.x) {
+            float cnt = __ldcg(p.stats + c);
+            float pr = __fdiv_rn(cnt, fn);
+            part += pr * logf(pr + 1e-10f);
+        }
+        double tot = block_sum((double)part, red);
+        if (tid == 0) {
+            p.scalars[1] = expf(-(float)tot);
+            double ls = *reinterpret_cast<volatile double*>(&p.hdr->loss_sum);
+            const float commit = TRAIN ? (float)(ls / ((double)p.n * (double)p.d)) : 0.f;
+            p.scalars[0] = commit;
+            p.scalars[2] = __fmul_rn(commit, p.commitment_weight);
+            p.scalars[3] = 0.f;
+            reinterpret_cast<unsigned*>(p.scalars)[4] = *reinterpret_cast<volatile unsigned*>(&p.hdr->n_rescored);
+            reinterpret_cast<unsigned*>(p.scalars)[5] = *reinterpret_cast<volatile unsigned*>(&p.hdr->n_exact);
+            p.scalars[6] = 0.f;
+            p.scalars[7] = 0.f;
+            p.hdr->ticket = 0;
+        }
+    }
+}
+
 // End of kernel: flush CTA-local statistics and the loss partial; last CTA computes the scalars.
 template <int DP, bool TRAIN>
 __device__ __forceinline__ void flush_and_finish(const FwdParams& p, int* hist, const float* accs, double* red,
@@ -265,39 +305,7 @@ __device__ __forceinline__ void flush_and_finish(const FwdParams& p, int* hist, 
         double t = block_sum((double)st.loss, red);
         if (tid == 0) atomicAdd(&p.hdr->loss_sum, t);
     }
-    // ---- last-CTA epilogue (threadFenceReduction pattern)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        unsigned t = atomicAdd(&p.hdr->ticket, 1u);
-        misc[1] = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (misc[1]) {
-        __threadfence();
-        // perplexity = exp(-sum p log(p + 1e-10)), p = counts / n  (vq.py:246-247)
-        const float fn = (float)p.n;
-        float part = 0.f;
-        for (int c = tid; c < p.k; c += kThreads) {
-            float cnt = __ldcg(p.stats + c);
-            float pr = __fdiv_rn(cnt, fn);
-            part += pr * logf(pr + 1e-10f);
-        }
-        double tot = block_sum((double)part, red);
-        if (tid == 0) {
-            p.scalars[1] = expf(-(float)tot);
-            double ls = *reinterpret_cast<volatile double*>(&p.hdr->loss_sum);
-            const float commit = TRAIN ? (float)(ls / ((double)p.n * (double)p.d)) : 0.f;
-            p.scalars[0] = commit;
-            p.scalars[2] = __fmul_rn(commit, p.commitment_weight);
-            p.scalars[3] = 0.f;
-            reinterpret_cast<unsigned*>(p.scalars)[4] = *reinterpret_cast<volatile unsigned*>(&p.hdr->n_rescored);
-            reinterpret_cast<unsigned*>(p.scalars)[5] = *reinterpret_cast<volatile unsigned*>(&p.hdr->n_exact);
-            p.scalars[6] = 0.f;
-            p.scalars[7] = 0.f;
-            p.hdr->ticket = 0;
-        }
-    }
+    finish_ticket<TRAIN>(p, red, misc);
 }
 
 // ------------------------------------------------------------------------------------------

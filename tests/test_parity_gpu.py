@@ -218,7 +218,9 @@ def test_sync_codebook_virtual_ranks(tvq):
                               cb._workspace(torch.device(DEV)))
             idx, q, scalars = outs[r]
             assert np.array_equal(idx.cpu().numpy().astype(np.int16).reshape(3, 40), g[f"r{r}_out{step}_ind"])
-            assert torch.equal(q.cpu().reshape(3, 40, 32), T(g[f"r{r}_out{step}_q"]))
+            if step == 0:
+                assert torch.equal(q.cpu().reshape(3, 40, 32), T(g[f"r{r}_out{step}_q"]))
+            close(q.reshape(3, 40, 32), T(g[f"r{r}_out{step}_q"]), what="q")
             close(scalars[1], T(g[f"r{r}_out{step}_perplexity"]), what="local perplexity")
             close(scalars[0:1], T(g[f"r{r}_out{step}_loss"]), what="loss")
             check_state(vqs[r], g, f"r{r}_post{step}_")
@@ -405,4 +407,36 @@ def test_full_size_properties(tvq, n, k, d):
     idx_e, _, _ = tvq.vq_forward_raw(x, e, ws, train=False, write_q=False)
     assert torch.equal(idx_e, idx)
     rescored = int(sc.view(torch.int32)[4])
-    assert rescored < 0.02 * n, f"{rescored} of {n} rows needed the fp64 re-score"
+    # fp32 nomination (k > 64): a handful of rows; tf32 nomination (k <= 64): the rigorous 2^-9 bound
+    # sends ~10 % of Gaussian rows to the re-score
+    limit = 0.25 * n if k <= 64 else 0.02 * n
+    assert rescored < limit, f"{rescored} of {n} rows needed the fp64 re-score"
+
+
+# ----------------------------------------------- tcgen05 path vs CUDA-core path (same canonical rule)
+
+@pytest.mark.parametrize("n,k,d", [(64, 32, 128), (65, 32, 128), (5000, 32, 128), (76800, 32, 128), (3333, 64, 128),
+                                   (4097, 16, 64), (2000, 7, 32), (1999, 50, 100), (10000, 64, 64), (300000, 32, 128)])
+@pytest.mark.parametrize("train", [True, False])
+def test_umma_path_equals_simt_path(tvq, n, k, d, train):
+    """k <= 64, d <= 128 runs on tcgen05 (tf32 nomination + fp64 re-score); forcing the SIMT path
+    (fp32 nomination + fp64 re-score) must give identical indices, q and counts, and the same sums."""
+    torch.manual_seed(n + k + d)
+    x = (torch.randn(n, d) * 1.3 + 0.2).to(DEV)
+    e = torch.randn(k, d).to(DEV)
+    ws = tvq.Workspace(k, d, torch.device(DEV))
+    off = tvq.stats_offset(k)
+    idx_u, q_u, sc_u = tvq.vq_forward_raw(x, e, ws, train=train)
+    st_u = ws.stats.clone()
+    idx_s, q_s, sc_s = tvq.vq_forward_raw(x, e, ws, train=train, flags=tvq._lib.F_NO_UMMA)
+    st_s = ws.stats.clone()
+    torch.cuda.synchronize()
+    assert torch.equal(idx_u, idx_s)
+    assert torch.equal(q_u, q_s)
+    assert torch.equal(st_u[:k], st_s[:k])
+    close(sc_u[1], sc_s[1], what="perplexity")
+    if train:
+        close(st_u[off:], st_s[off:], what="embed_sum")
+        close(sc_u[0], sc_s[0], what="commit")
+    if n <= 5000:
+        assert np.array_equal(idx_u.cpu().numpy(), C.assign(x.cpu().numpy(), e.cpu().numpy()))
