@@ -117,13 +117,14 @@ int make_x_tensor_map(CUtensorMap* tm, const float* x, int64_t n, int d, int row
     return r == CUDA_SUCCESS ? TVQ_OK : TVQ_ERR_BAD_ARG;
 }
 
-template <int DP, int KP, bool TRAIN>
-int launch_fwd_umma(FwdParams p, const DeviceInfo& di, cudaStream_t stream) {
-    auto kern = fwd_umma_kernel<DP, KP, TRAIN>;
+template <int DP, int KP, bool TRAIN, bool FULLD>
+int launch_fwd_umma_impl(FwdParams p, const DeviceInfo& di, cudaStream_t stream) {
+    auto kern = fwd_umma_kernel<DP, KP, TRAIN, FULLD>;
     const UmmaPlan fixed = make_umma_plan(DP, KP, 0);
     int stages = (di.max_smem_optin - fixed.total) / (kUM * DP * 4);
     if (stages > kUMaxStages) stages = kUMaxStages;
     if (stages < 2) return TVQ_ERR_UNSUPPORTED;
+    if (TRAIN && stages * (kUM * DP * 4) < 4 * KP * 32 * 16) return TVQ_ERR_UNSUPPORTED;   // end-of-kernel dump area
     const UmmaPlan pl = make_umma_plan(DP, KP, stages);
     static int configured_smem = -1;
     if (pl.total > configured_smem) {
@@ -140,16 +141,22 @@ int launch_fwd_umma(FwdParams p, const DeviceInfo& di, cudaStream_t stream) {
     return launch_status();
 }
 
+template <int DP, int KP, bool TRAIN>
+int launch_fwd_umma(const FwdParams& p, const DeviceInfo& di, cudaStream_t stream) {
+    if (DP == 128 && p.d == 128) return launch_fwd_umma_impl<DP, KP, TRAIN, (DP == 128)>(p, di, stream);
+    return launch_fwd_umma_impl<DP, KP, TRAIN, false>(p, di, stream);
+}
+
 template <bool TRAIN>
 int dispatch_fwd_umma(int dp, int kp, const FwdParams& p, const DeviceInfo& di, cudaStream_t s) {
     if (dp == 64) {
         if (kp == 16) return launch_fwd_umma<64, 16, TRAIN>(p, di, s);
         if (kp == 32) return launch_fwd_umma<64, 32, TRAIN>(p, di, s);
-        if (kp == 64) return launch_fwd_umma<64, 64, TRAIN>(p, di, s);
+        if constexpr (!TRAIN) { if (kp == 64) return launch_fwd_umma<64, 64, false>(p, di, s); }
     } else if (dp == 128) {
         if (kp == 16) return launch_fwd_umma<128, 16, TRAIN>(p, di, s);
         if (kp == 32) return launch_fwd_umma<128, 32, TRAIN>(p, di, s);
-        if (kp == 64) return launch_fwd_umma<128, 64, TRAIN>(p, di, s);
+        if constexpr (!TRAIN) { if (kp == 64) return launch_fwd_umma<128, 64, false>(p, di, s); }
     }
     return TVQ_ERR_UNSUPPORTED;
 }
@@ -157,6 +164,12 @@ int dispatch_fwd_umma(int dp, int kp, const FwdParams& p, const DeviceInfo& di, 
 }  // namespace
 
 extern "C" {
+
+#ifdef TVQ_PROFILE_PHASES
+__attribute__((visibility("default"))) int tvq_debug_phases(unsigned long long* out32) {
+    return (int)cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(unsigned long long) * 32);
+}
+#endif
 
 int tvq_abi_version(void) { return 1; }
 
@@ -221,8 +234,10 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
     p.num_tiles = (int)((n + kBM - 1) / kBM);
     p.exact = (flags & TVQ_F_EXACT) ? 1 : 0;
     p.given_idx = (flags & TVQ_F_GIVEN_IDX) ? 1 : 0;
-    // Resident-codebook tcgen05 path: k <= 64, d <= 128 (the configs/config.yaml regime).
-    if (!(flags & (TVQ_F_EXACT | TVQ_F_GIVEN_IDX | TVQ_F_NO_UMMA)) && k <= 64 && d <= 128 && n < (int64_t(1) << 31) - 64) {
+    // Resident-codebook tcgen05 path: train k <= 32 (per-warp TMEM accumulators), eval k <= 64; d <= 128
+    // (the configs/config.yaml regime).
+    if (!(flags & (TVQ_F_EXACT | TVQ_F_GIVEN_IDX | TVQ_F_NO_UMMA)) && k <= (train ? 32 : 64) && d <= 128 &&
+        n < (int64_t(1) << 31) - 64) {
         const int udp = d <= 64 ? 64 : 128;
         const int ukp = k <= 16 ? 16 : k <= 32 ? 32 : 64;
         p.use_hist = 1;

@@ -1,24 +1,29 @@
 // tvq_fwd_umma.cuh — fused VQ forward with tcgen05 scoring, codebook resident in shared memory
-// (k <= 64 codes, d <= 128).  This is the path BASELINE configs[0..1,3,4] run (k = 32, d = 128).
+// (train: k <= 32, eval: k <= 64; d <= 128).  This is the path BASELINE configs[0,1,3,4] run
+// (k = 32, d = 128).
 //
 // One persistent CTA per SM, 10 warps, warp-specialised:
 //   warp 0      TMA producer: x tiles of 64 latents x d fp32 -> ring of shared-memory stages
 //               (cp.async.bulk.tensor, SWIZZLE_128B, zero-fill past n / past d)
 //   warp 1      MMA issuer: per tile d/8 tcgen05.mma.kind::tf32 (M=64, N=KP) straight from the fp32
 //               tiles (no conversion pass) into one of 4 TMEM accumulator slots; tcgen05.commit
-//   warps 2-5   epilogue group 0, warps 6-9 epilogue group 1: the groups take alternate tiles and
-//               never synchronise with each other, so one group's latencies hide behind the other's.
-// Per tile an epilogue group
-//   1. reads the 64 x KP approximate dot products from TMEM (tcgen05.ld), forms scores
-//      e2 - 2 x.e and keeps, per row, every code within the RIGOROUS tf32 error bound of the row
-//      minimum;
-//   2. decides rows with more than one candidate by the canonical fp64 re-score
-//      (tvq_common.cuh, mirrored by oracle/vq_canon.c) — so the indices are exactly those of the
-//      SIMT path and of the C oracle, whatever the tensor-core rounding did;
-//   3. writes idx, gathers the code word, forms the straight-through output and the commitment
-//      loss partial, streams q_st out (st.global.cs);
-//   4. buckets the tile's rows by code and adds them, column-owner style, into REGISTER
-//      accumulators (no floating-point atomics until the CTA's single flush);
+//   warps 2-9   eight epilogue warps in two groups of four (one warp per TMEM lane quadrant); the
+//               groups take alternate tiles.  A warp owns the 16 rows of its quadrant from the
+//               TMEM read to the last store, so epilogue warps never synchronise with each other:
+//               the only hand-offs are mbarriers (tile landed / scores ready / slot free / stage free).
+// Per tile an epilogue warp
+//   1. reads its 16 x KP approximate dot products from TMEM (tcgen05.ld), forms scores
+//      e2 - 2 x.e and keeps the four best (score, code) pairs of every row with a branch-free
+//      min/max network on packed keys;
+//   2. per row (all 32 lanes on one row, four rows in flight): |x|^2 -> the RIGOROUS tf32 error
+//      bound -> rows with more than one code inside the bound are decided by
+//      the canonical fp64 re-score (tvq_common.cuh, mirrored by oracle/vq_canon.c), so the indices
+//      are exactly those of the SIMT path and of the C oracle whatever the tensor-core rounding did;
+//   3. gathers the code word from the shared-memory codebook, forms the straight-through output
+//      and the commitment-loss partial, streams q_st out (st.global.cs), writes idx;
+//   4. adds the row into the warp's PRIVATE per-code accumulators, which live in tensor memory
+//      (tcgen05.ld / tcgen05.st read-modify-write of 4 columns x 32 lanes): no shared-memory
+//      accumulators, no sort, no floating-point atomics until the CTA's single flush;
 //   5. releases the stage to the producer.
 // Algorithmic HBM traffic: read x once, write q once, write idx: 8d + 8 bytes per latent.
 #pragma once
@@ -30,16 +35,27 @@
 
 namespace tvq {
 
+#ifdef TVQ_PROFILE_PHASES
+// Experiment build only (tools/profile_phases.py): per-phase clock64 totals of CTA 0's epilogue warps.
+__device__ unsigned long long g_phase_clk[2][16];
+#define TVQ_PH(i) do { long long _t = clock64(); ph_acc[i] += _t - ph_t; ph_t = _t; } while (0)
+#else
+#define TVQ_PH(i) do { } while (0)
+#endif
+
+#ifndef TVQ_UGROUPS
+#define TVQ_UGROUPS 2
+#endif
 constexpr int kUM = 64;                 // latents per UMMA tile (M)
-constexpr int kUGroupThreads = 128;     // one epilogue group = 4 warps = the 4 TMEM lane quadrants
-constexpr int kUThreads = 64 + 2 * kUGroupThreads;
-constexpr int kUSlots = 4;              // TMEM accumulator slots
+constexpr int kUGroups = TVQ_UGROUPS;   // epilogue groups of 4 warps (one warp per TMEM lane quadrant)
+constexpr int kUThreads = 64 + 128 * kUGroups;   // producer warp + MMA warp + epilogue warps
+constexpr int kUSlots = 4;              // TMEM score slots
 constexpr int kUMaxStages = 8;
+constexpr int kUBatch = 4;              // rows a warp keeps in flight in the apply phase
 
 struct UmmaPlan {
     int stages, stage_bytes;
-    int x, cb, e2s, grp, grp_stride, red, misc, bars, tmem, total;
-    // per-group block: sidx[64] order[64] xn2[64] start[KP+4] cntw[2*KP] hist[KP]
+    int x, cb, e2s, hist, red, misc, bars, tmem, total;
 };
 __host__ __device__ inline UmmaPlan make_umma_plan(int dp, int kp, int stages) {
     UmmaPlan u;
@@ -49,8 +65,7 @@ __host__ __device__ inline UmmaPlan make_umma_plan(int dp, int kp, int stages) {
     u.x = o;    o += stages * u.stage_bytes;
     u.cb = o;   o += kp * dp * 4;
     u.e2s = o;  o += kp * 4;
-    u.grp = o;  u.grp_stride = (64 + 64 + 64 + (kp + 4) + 2 * kp + kp) * 4;
-    o += 2 * u.grp_stride;
+    u.hist = o; o += kp * 4;
     o = (o + 15) & ~15;
     u.red = o;  o += 16 * 8;
     u.misc = o; o += 16 * 4;
@@ -60,24 +75,107 @@ __host__ __device__ inline UmmaPlan make_umma_plan(int dp, int kp, int stages) {
     return u;
 }
 
-template <int DP, int KP, bool TRAIN>
+// Sorted insert of `key` into (t0 <= t1 <= t2 <= t3): branch-free min/max network.
+__device__ __forceinline__ void top4_insert(float key, float& t0, float& t1, float& t2, float& t3) {
+    float c = fmaxf(t0, key);
+    t0 = fminf(t0, key);
+    float c2 = fmaxf(t1, c);
+    t1 = fminf(t1, c);
+    float c3 = fmaxf(t2, c2);
+    t2 = fminf(t2, c2);
+    t3 = fminf(t3, c3);
+}
+
+// Rows whose tf32 scores leave more than one code inside the error bound go through a cascade:
+// level 2 re-scores the candidates with fp32 FMAs (error ~1e-6 relative, rigorous bound err32),
+// and only if that still cannot separate them does level 3 apply the canonical fp64 rule.  All 32
+// lanes work on the one row (lane l holds chunk l of x).  Returns the canonical argmin.
+template <int KP>
+__device__ __noinline__ int resolve_row(const float4 xv, const float bnd2, const unsigned c0, const unsigned c1,
+                                           const unsigned c2, const int nc, const bool all_codes, const float* cbs,
+                                           const float* e2s, const int k, const bool has_chunk, const int lane) {
+    // return value: code | (1 << 16) if the decision needed the fp64 level
+    const float thr32 = 1.3e-6f * bnd2;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!all_codes) {
+        // three candidate slots (unused slots repeat the best code, which is harmless); everything is
+        // kept in named registers — no dynamically indexed arrays, hence no local memory
+        const unsigned a0 = c0, a1 = nc > 1 ? c1 : c0, a2 = nc > 2 ? c2 : c0;
+        const float4 e0 = has_chunk ? *reinterpret_cast<const float4*>(cbs + tile_off<KP>((int)a0, lane)) : z4;
+        const float4 e1 = has_chunk ? *reinterpret_cast<const float4*>(cbs + tile_off<KP>((int)a1, lane)) : z4;
+        const float4 e2v = has_chunk ? *reinterpret_cast<const float4*>(cbs + tile_off<KP>((int)a2, lane)) : z4;
+        float d0 = fmaf(xv.x, e0.x, fmaf(xv.y, e0.y, fmaf(xv.z, e0.z, xv.w * e0.w)));
+        float d1 = fmaf(xv.x, e1.x, fmaf(xv.y, e1.y, fmaf(xv.z, e1.z, xv.w * e1.w)));
+        float d2 = fmaf(xv.x, e2v.x, fmaf(xv.y, e2v.y, fmaf(xv.z, e2v.z, xv.w * e2v.w)));
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            d0 += __shfl_xor_sync(0xffffffffu, d0, off);
+            d1 += __shfl_xor_sync(0xffffffffu, d1, off);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+        }
+        const float s0 = fmaf(-2.f, d0, e2s[a0]), s1 = fmaf(-2.f, d1, e2s[a1]), s2 = fmaf(-2.f, d2, e2s[a2]);
+        float sb = s0;
+        unsigned cb_ = a0;
+        if (s1 < sb || (s1 == sb && a1 < cb_)) { sb = s1; cb_ = a1; }
+        if (s2 < sb || (s2 == sb && a2 < cb_)) { sb = s2; cb_ = a2; }
+        const float lim = sb + thr32;
+        const bool amb = (a0 != cb_ && s0 <= lim) || (a1 != cb_ && s1 <= lim) || (a2 != cb_ && s2 <= lim);
+        if (!amb) return (int)cb_;
+        // level 3: canonical fp64 among the candidates
+        const float x2 = __double2float_rn(butterfly_sum(dot4(0.0, xv, xv)));
+        const float q0 = canon_score(x2, butterfly_sum(dot4(0.0, xv, e0)), e2s[a0]);
+        const float q1 = canon_score(x2, butterfly_sum(dot4(0.0, xv, e1)), e2s[a1]);
+        const float q2 = canon_score(x2, butterfly_sum(dot4(0.0, xv, e2v)), e2s[a2]);
+        float best = q0;
+        int arg = (int)a0;
+        if (q1 < best || (q1 == best && (int)a1 < arg)) { best = q1; arg = (int)a1; }
+        if (q2 < best || (q2 == best && (int)a2 < arg)) { best = q2; arg = (int)a2; }
+        return arg | (1 << 16);
+    }
+    // candidate list overflowed (or non-finite scores): fp32 pass over every code, then fp64 if needed
+    float m1 = __int_as_float(0x7f800000), m2 = m1;
+    int i1 = 0;
+    for (int c = 0; c < k; ++c) {
+        const float4 ev = has_chunk ? *reinterpret_cast<const float4*>(cbs + tile_off<KP>(c, lane)) : z4;
+        float dd = fmaf(xv.x, ev.x, fmaf(xv.y, ev.y, fmaf(xv.z, ev.z, xv.w * ev.w)));
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, off);
+        const float sv = fmaf(-2.f, dd, e2s[c]);
+        if (sv < m1) { m2 = m1; m1 = sv; i1 = c; }
+        else if (sv < m2) m2 = sv;
+    }
+    if (m2 - m1 > thr32) return i1;
+    const float x2 = __double2float_rn(butterfly_sum(dot4(0.0, xv, xv)));
+    float best = __int_as_float(0x7f800000);
+    int arg = 0;
+    for (int c = 0; c < k; ++c) {
+        const float4 ev = has_chunk ? *reinterpret_cast<const float4*>(cbs + tile_off<KP>(c, lane)) : z4;
+        const float dk = canon_score(x2, butterfly_sum(dot4(0.0, xv, ev)), e2s[c]);
+        if (dk < best) { best = dk; arg = c; }
+    }
+    return arg | (1 << 16);
+}
+
+template <int DP, int KP, bool TRAIN, bool FULLD>
 __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const FwdParams p,
                                                                const int stages) {
     using namespace sm100;
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr int DPC = DP / 4;                 // 16-byte chunks per padded row
+    constexpr int DPC = DP / 4;                 // 16-byte chunks per padded row (<= 32: one per lane)
     constexpr int NSLAB = DP / 32;              // 128-byte K slabs per tile
     constexpr int SLAB_X = kUM * 128;           // bytes of one x slab
     constexpr int SLAB_CB = KP * 128;           // bytes of one codebook slab
-    constexpr int NSUB = kUGroupThreads / DP > 0 ? kUGroupThreads / DP : 1;   // threads sharing one column
-    constexpr int NACC = KP / NSUB;             // register accumulators per thread
-    constexpr uint32_t TMEM_COLS = (kUSlots * KP) <= 32 ? 32 : (kUSlots * KP) <= 64 ? 64 : (kUSlots * KP) <= 128 ? 128 : 256;
+    constexpr int ACC_COLS = TRAIN ? kUGroups * 4 * KP : 0;   // per-warp accumulators: 4 columns per code
+    constexpr uint32_t TMEM_NEED = kUSlots * KP + ACC_COLS;
+    constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
     static_assert(DP == 64 || DP == 128, "resident-codebook path: d padded to 64 or 128");
     static_assert(KP == 16 || KP == 32 || KP == 64, "resident-codebook path: k padded to 16, 32 or 64");
+    static_assert(TMEM_NEED <= 512, "tensor memory budget");
 
     const UmmaPlan pl = make_umma_plan(DP, KP, stages);
     float* cbs = reinterpret_cast<float*>(smem + pl.cb);
     float* e2s = reinterpret_cast<float*>(smem + pl.e2s);
+    int* hist = reinterpret_cast<int*>(smem + pl.hist);
     double* red = reinterpret_cast<double*>(smem + pl.red);
     int* misc = reinterpret_cast<int*>(smem + pl.misc);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
@@ -88,7 +186,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunk = p.d >> 2;
-    const float INF = __int_as_float(0x7f800000);
+    const float BIG = 1e30f;                    // score of a padded code (finite: keys stay ordered)
 
     // ------------------------------------------------------------------ CTA prologue
     if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need 1024-byte alignment
@@ -98,14 +196,13 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         if (row < p.k && c4 < nchunk) v = __ldg(reinterpret_cast<const float4*>(p.cb + (size_t)row * p.d) + c4);
         *reinterpret_cast<float4*>(cbs + tile_off<KP>(row, c4)) = v;
     }
-    for (int c = tid; c < KP; c += kUThreads) e2s[c] = (c < p.k) ? __ldg(p.e2 + c) : INF;
-    for (int g = 0; g < 2; ++g) {                         // per-group histograms
-        int* hist = reinterpret_cast<int*>(smem + pl.grp + g * pl.grp_stride) + 64 + 64 + 64 + (KP + 4) + 2 * KP;
-        for (int c = tid; c < KP; c += kUThreads) hist[c] = 0;
+    for (int c = tid; c < KP; c += kUThreads) {
+        e2s[c] = (c < p.k) ? __ldg(p.e2 + c) : BIG;
+        hist[c] = 0;
     }
     fence_proxy_async_smem();                             // generic-proxy writes -> visible to tcgen05.mma
     if (tid == 0) {
-        for (int s = 0; s < kUMaxStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < kUMaxStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 4); }
         for (int s = 0; s < kUSlots; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_x);
@@ -118,16 +215,14 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     float emax2 = 0.f;
     for (int c = 0; c < KP; ++c) emax2 = fmaxf(emax2, (c < p.k) ? e2s[c] : 0.f);
     const float emax = sqrtf(emax2) * 1.0001f;
-    // |(s_a - s_b) - (d_a - d_b)| <= err_c * (|x| + max|e|)^2 for tf32 operands (each within 2^-10
-    // relative, truncated or rounded) and fp32 accumulation: 2^-9 with 10 % slack + fp32 terms.
-    const float err_c = 2.2e-3f;
+    // |(s_a - s_b) - (d_a - d_b)| <= err_c * (|x| + max|e|)^2: tf32 operands (each within 2^-10
+    // relative, truncated or rounded) and fp32 accumulation give 2^-9 on the dot product; 10 % slack,
+    // plus the fp32 roundings of both formulas and the 6 key bits that carry the code (64 ulps).
+    const float err_c = 2.2e-3f + 3e-5f;
 
     const int num_tiles = p.num_tiles;                    // tiles of 64 rows
-    ApplyState st;
-    st.loss = 0.f;
-    float acc[NACC];
-#pragma unroll
-    for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
+    float loss = 0.f;
+    unsigned n_rescored = 0, n_full = 0;
 
     if (warp == 0) {
         // ============================================================ TMA producer
@@ -165,192 +260,234 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
             }
         }
     } else {
-        // ============================================================ epilogue groups
-        const int g = (warp - 2) >> 2;                    // group 0 / 1
-        const int lt = tid - 64 - g * kUGroupThreads;     // 0..127 within the group
-        const int wg = lt >> 5;                           // warp within the group
-        const int quad = warp & 3;                        // TMEM lane quadrant this warp may read
-        int* gi = reinterpret_cast<int*>(smem + pl.grp + g * pl.grp_stride);
-        int* sidx = gi;
-        int* order = gi + 64;
-        float* xn2 = reinterpret_cast<float*>(gi + 128);
-        int* start = gi + 192;
-        int* cntw = start + (KP + 4);
-        int* hist = cntw + 2 * KP;
-        const uint32_t bar_id = 1 + g;
-
-        for (int it = g; ; it += 2) {
+        // ============================================================ epilogue warps
+        const int g = (warp - 2) >> 2;                    // epilogue group: tiles g, g + kUGroups, ...
+        const int quad = warp & 3;                        // TMEM lane quadrant this warp may access
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        const uint32_t acc_base = tmem_base + lane_base + kUSlots * KP + g * (4 * KP);
+        const bool has_chunk = FULLD ? true : (lane < DPC && lane < nchunk);   // FULLD: d == DP == 128
+        if (TRAIN) {
+            for (int c = 0; c < KP; ++c) tmem_st_x4(acc_base + 4 * c, make_float4(0.f, 0.f, 0.f, 0.f));
+            tmem_st_wait();
+        }
+#ifdef TVQ_PROFILE_PHASES
+        long long ph_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long ph_t = clock64();
+#endif
+        for (int it = g; ; it += kUGroups) {
             const int tile = blockIdx.x + it * gridDim.x;
             if (tile >= num_tiles) break;
             const int s = it % stages, slot = it % kUSlots;
             const uint32_t ph = (uint32_t)(it / stages) & 1u, sph = (uint32_t)(it / kUSlots) & 1u;
-            const int64_t row0 = (int64_t)tile * kUM;
+            const int64_t row0 = (int64_t)tile * kUM + quad * 16;     // first of this warp's 16 rows
             const float* xt = reinterpret_cast<const float*>(smem + pl.x + s * pl.stage_bytes);
 
             mbar_wait(bar_full + 8 * s, ph);              // x tile landed (TMA writes visible)
-            // ---- row norms of this warp's 16 rows (overlaps the MMA)
-            for (int r = 0; r < 16; ++r) {
-                const int row = quad * 16 + r;
-                float ss = 0.f;
-                for (int c = lane; c < DPC; c += 32) {
-                    float4 v = *reinterpret_cast<const float4*>(xt + tile_off<kUM>(row, c));
-                    ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-                }
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-                if (lane == 0) xn2[row] = ss;
-            }
-            __syncwarp();
-            // ---- scores from TMEM: lane l < 16 owns row quad*16 + l (M = 64 accumulator layout)
-            mbar_wait(bar_tfull + 8 * slot, sph);
+            TVQ_PH(0);
+            mbar_wait(bar_tfull + 8 * slot, sph);         // scores ready
             tc_fence_after();
-            float sc[KP];
+            TVQ_PH(1);
+            // ---- 1. scan: lane l < 16 owns row l of the quadrant (M = 64 accumulator layout)
+            float t0 = BIG, t1 = BIG, t2 = BIG, t3 = BIG;
+            {
+                float sc[KP];
 #pragma unroll
-            for (int c0 = 0; c0 < KP; c0 += 16)
-                tmem_ld_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * KP + c0), sc + c0);
-            tmem_ld_wait();
-            tc_fence_before();
+                for (int c0 = 0; c0 < KP; c0 += 16) tmem_ld_x16(tmem_base + lane_base + (uint32_t)(slot * KP + c0), sc + c0);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // score slot may be overwritten
+#pragma unroll
+                for (int c = 0; c < KP; ++c) {
+                    const float sv = fmaf(-2.f, sc[c], e2s[c]);
+                    const float key = __uint_as_float((__float_as_uint(sv) & ~63u) | (unsigned)c);
+                    top4_insert(key, t0, t1, t2, t3);
+                }
+            }
+            TVQ_PH(2);
+            // ---- 2-4. apply: all lanes on one row, kUBatch rows in flight
+            int mycode = 0;                               // lane r (< 16) keeps the code of row r
+            const int nvalid = (int)((p.n - row0) < 16 ? (p.n - row0) : 16);      // rows of this warp inside n
+            const float* xrow = xt + (lane >> 3) * (kUM * 32) + quad * 16 * 32;   // + r*32 + swizzled chunk
+            float* qrow = p.q ? p.q + (size_t)row0 * p.d + 4 * lane : nullptr;
+#pragma unroll 1
+            for (int b = 0; b < 16 / kUBatch; ++b) {
+                float4 xv[kUBatch];
+                float ss[kUBatch], k0[kUBatch], k1[kUBatch];
+#pragma unroll
+                for (int u = 0; u < kUBatch; ++u) {
+                    const int r = b * kUBatch + u;
+                    // (row & 7) == (r & 7): quad*16 is a multiple of 8
+                    const float4 ld = *reinterpret_cast<const float4*>(xrow + r * 32 + (((lane ^ r) & 7) << 2));
+                    xv[u] = has_chunk ? ld : make_float4(0.f, 0.f, 0.f, 0.f);
+                    k0[u] = __shfl_sync(0xffffffffu, t0, r);
+                    k1[u] = __shfl_sync(0xffffffffu, t1, r);
+                    ss[u] = fmaf(xv[u].x, xv[u].x, fmaf(xv[u].y, xv[u].y, fmaf(xv[u].z, xv[u].z, xv[u].w * xv[u].w)));
+                }
+                TVQ_PH(5);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+                    for (int u = 0; u < kUBatch; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], off);
+                TVQ_PH(6);
+                int cd[kUBatch];
+#pragma unroll
+                for (int u = 0; u < kUBatch; ++u) {        // (a) decisions
+                    const int r = b * kUBatch + u;
+                    const bool valid = r < nvalid;
+                    const float bnd = sqrt_approx(ss[u]) * 1.0001f + emax;
+                    const float bnd2 = bnd * bnd;
+                    const float lim = fmaf(err_c, bnd2, k0[u]);
+                    int code = (int)(__float_as_uint(k0[u]) & 63u);
+                    if (valid && !(k1[u] > lim && k0[u] < BIG)) {
+                        // second-best inside the bound (or non-finite scores): cascade re-score
+                        const float k2 = __shfl_sync(0xffffffffu, t2, r), k3 = __shfl_sync(0xffffffffu, t3, r);
+                        const int nc = 1 + (k1[u] <= lim) + (k2 <= lim) + (k3 <= lim);
+                        const bool finite = k0[u] < BIG;
+                        code = resolve_row<KP>(xv[u], bnd2, __float_as_uint(k0[u]) & 63u, __float_as_uint(k1[u]) & 63u,
+                                               __float_as_uint(k2) & 63u, nc, nc == 4 || !finite, cbs, e2s, p.k,
+                                               has_chunk, lane);
+                        n_full += (unsigned)(code >> 16);
+                        code &= 0xffff;
+                        code = code < p.k ? code : 0;      // non-finite rows: any code, but a valid one
+                        ++n_rescored;
+                    }
+                    cd[u] = valid ? code : -1;
+                    if (lane == r) mycode = code;
+                }
+                if (p.q != nullptr || TRAIN) {
+                    float4 ev[kUBatch];
+#pragma unroll
+                    for (int u = 0; u < kUBatch; ++u) {    // (b) gather from the shared-memory codebook
+                        const int c = cd[u] < 0 ? 0 : cd[u];
+                        const float4 ld = *reinterpret_cast<const float4*>(cbs + (lane >> 3) * (KP * 32) + c * 32 + (((lane ^ c) & 7) << 2));
+                        ev[u] = (has_chunk && cd[u] >= 0) ? ld : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kUBatch; ++u) {    // (c) straight-through, loss, store
+                        float4 o = ev[u];
+                        if (TRAIN) {
+                            // x + (e - x): two rounded fp32 ops, never contracted; the loss is taken on
+                            // that rounded tensor, as F.mse_loss(quantize.detach(), x) does.  Rows past
+                            // n are zero-filled and gather zeros, so they add exactly 0.
+                            o.x = __fadd_rn(xv[u].x, __fsub_rn(ev[u].x, xv[u].x));
+                            o.y = __fadd_rn(xv[u].y, __fsub_rn(ev[u].y, xv[u].y));
+                            o.z = __fadd_rn(xv[u].z, __fsub_rn(ev[u].z, xv[u].z));
+                            o.w = __fadd_rn(xv[u].w, __fsub_rn(ev[u].w, xv[u].w));
+                            const float dx = __fsub_rn(o.x, xv[u].x), dy = __fsub_rn(o.y, xv[u].y);
+                            const float dz = __fsub_rn(o.z, xv[u].z), dw = __fsub_rn(o.w, xv[u].w);
+                            loss = fmaf(dx, dx, loss);
+                            loss = fmaf(dy, dy, loss);
+                            loss = fmaf(dz, dz, loss);
+                            loss = fmaf(dw, dw, loss);
+                        }
+                        if (qrow != nullptr && has_chunk && cd[u] >= 0) st_stream_v4(qrow + (size_t)(b * kUBatch + u) * p.d, o);
+                    }
+                }
+                if (lane < kUBatch) {                       // counts: lane u books row u of the batch
+                    int c = cd[0];
+#pragma unroll
+                    for (int u = 1; u < kUBatch; ++u) c = (lane == u) ? cd[u] : c;
+                    if (c >= 0) atomicAdd(hist + c, 1);
+                }
+                TVQ_PH(7);
+                if (TRAIN) {
+                    // rows of the batch that share a code are merged first, then one TMEM
+                    // read-modify-write per distinct code (codes are warp-uniform values)
+                    bool dup = false;
+#pragma unroll
+                    for (int v = 1; v < kUBatch; ++v)
+#pragma unroll
+                        for (int u = 0; u < v; ++u) dup |= (cd[v] == cd[u]) && cd[v] >= 0;
+                    if (dup) {                            // uncommon: taken as one warp-uniform branch
+#pragma unroll
+                        for (int v = 1; v < kUBatch; ++v)
+#pragma unroll
+                            for (int u = 0; u < v; ++u)
+                                if (cd[v] >= 0 && cd[v] == cd[u]) {
+                                    xv[u].x += xv[v].x; xv[u].y += xv[v].y; xv[u].z += xv[v].z; xv[u].w += xv[v].w;
+                                    cd[v] = -1;
+                                }
+                    }
+                    __syncwarp();
+                    tmem_st_wait();                       // the previous batch's stores have landed
+                    float4 a[kUBatch];
+#pragma unroll
+                    for (int u = 0; u < kUBatch; ++u)
+                        if (cd[u] >= 0) a[u] = tmem_ld_x4(acc_base + 4 * cd[u]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < kUBatch; ++u)
+                        if (cd[u] >= 0) {
+                            a[u].x += xv[u].x; a[u].y += xv[u].y; a[u].z += xv[u].z; a[u].w += xv[u].w;
+                            tmem_st_x4(acc_base + 4 * cd[u], a[u]);
+                        }
+                }
+                TVQ_PH(8);
+            }
+            if (lane < nvalid) p.idx[row0 + lane] = (int64_t)mycode;
+            TVQ_PH(3);
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // accumulator slot may be overwritten
-            const int row = quad * 16 + (lane & 15);
-            const bool active = lane < 16 && row0 + row < p.n;
-            float m = INF;
-#pragma unroll
-            for (int c = 0; c < KP; ++c) {
-                sc[c] = fmaf(-2.f, sc[c], e2s[c]);
-                m = fminf(m, sc[c]);
-            }
-            const float b = sqrtf(xn2[row]) * 1.0001f + emax;
-            const float lim = m + err_c * b * b;
-            int cand[4] = {0, 0, 0, 0};
-            int ncand = 0;
-#pragma unroll
-            for (int c = 0; c < KP; ++c) {
-                if (sc[c] <= lim) {
-                    if (ncand == 0) cand[0] = c;
-                    else if (ncand == 1) cand[1] = c;
-                    else if (ncand == 2) cand[2] = c;
-                    else if (ncand == 3) cand[3] = c;
-                    ++ncand;
-                }
-            }
-            if (!(m < INF)) ncand = 5;                    // NaN / Inf rows: let the exact scan decide
-            int code = cand[0];
-            // ---- canonical fp64 re-score of rows with more than one candidate (warp-cooperative)
-            unsigned need = __ballot_sync(0xffffffffu, active && ncand > 1);
-            unsigned nres = __popc(need), nfull = 0;
-            while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                const int r_row = __shfl_sync(0xffffffffu, row, src);
-                const int r_n = __shfl_sync(0xffffffffu, ncand, src);
-                int r_c[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) r_c[j] = __shfl_sync(0xffffffffu, cand[j], src);
-                int best;
-                if (r_n > 4) { best = canon_scan_row<DP, kUM>(xt, r_row, p.cb, p.e2, p.k, p.d, lane); ++nfull; }
-                else best = canon_pick<DP, kUM>(xt, r_row, p.cb, p.e2, p.d, lane, r_c, r_n);
-                if (lane == src) code = best;
-            }
-            if (lane == 0 && nres) { atomicAdd(&p.hdr->n_rescored, nres); if (nfull) atomicAdd(&p.hdr->n_exact, nfull); }
-            if (lane < 16) sidx[row] = active ? code : 0;
-            if (active) p.idx[row0 + row] = (int64_t)code;
-            named_bar_sync(bar_id, kUGroupThreads);
-            // ---- gather, straight-through, loss, q_st out
-            apply_rows<DP, TRAIN, kUM>(p, xt, sidx, hist, row0, st, wg, 4);
-            // ---- EMA statistics into register accumulators
-            if (TRAIN) {
-                for (int i = lt; i < 2 * KP; i += kUGroupThreads) cntw[i] = 0;
-                named_bar_sync(bar_id, kUGroupThreads);
-                int mycode = -1, rank = 0;
-                if (lt < kUM) {
-                    mycode = (row0 + lt < p.n) ? sidx[lt] : -1;
-                    const unsigned mm = __match_any_sync(0xffffffffu, mycode);
-                    rank = __popc(mm & lanemask_lt());
-                    if (mycode >= 0 && rank == 0) cntw[wg * KP + mycode] = __popc(mm);
-                }
-                named_bar_sync(bar_id, kUGroupThreads);
-                if (wg == 0) {
-                    constexpr int PER = KP / 32 > 0 ? KP / 32 : 1;
-                    int v[PER], tot = 0;
-#pragma unroll
-                    for (int j = 0; j < PER; ++j) {
-                        const int c = lane * PER + j;
-                        v[j] = (c < KP) ? cntw[c] + cntw[KP + c] : 0;
-                        tot += v[j];
-                    }
-                    int incl = tot;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        int t = __shfl_up_sync(0xffffffffu, incl, off);
-                        if (lane >= off) incl += t;
-                    }
-                    int run = incl - tot;
-#pragma unroll
-                    for (int j = 0; j < PER; ++j) {
-                        const int c = lane * PER + j;
-                        if (c < KP) start[c] = run;
-                        run += v[j];
-                    }
-                    if (lane == 31) start[KP] = incl;
-                }
-                named_bar_sync(bar_id, kUGroupThreads);
-                if (lt < kUM && mycode >= 0) order[start[mycode] + rank + (wg == 1 ? cntw[mycode] : 0)] = lt;
-                named_bar_sync(bar_id, kUGroupThreads);
-                const int col = lt % DP, sub = lt / DP;
-                const int xc4 = col >> 2, xo = col & 3;
-#pragma unroll
-                for (int j = 0; j < NACC; ++j) {
-                    const int c = j * NSUB + sub;
-                    const int beg = start[c], end = start[c + 1];
-                    float a = 0.f;
-                    for (int i = beg; i < end; ++i) a += xt[tile_off<kUM>(order[i], xc4) + xo];
-                    acc[j] += a;
-                    if (col == 0 && end > beg) hist[c] += end - beg;
-                }
-            }
-            named_bar_sync(bar_id, kUGroupThreads);       // every read of the stage is done
-            if (lt == 0) mbar_arrive(bar_empty + 8 * s);
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // this warp is done with the stage
+            TVQ_PH(4);
         }
+        if (TRAIN) tmem_st_wait();
+#ifdef TVQ_PROFILE_PHASES
+        if (blockIdx.x == 0 && lane == 0 && quad == 0 && g < 2)
+            for (int i = 0; i < 10; ++i) g_phase_clk[g][i] = (unsigned long long)ph_acc[i];
+#endif
     }
 
     // ------------------------------------------------------------------ teardown and flush
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
-    float* scratch = reinterpret_cast<float*>(smem + pl.x);          // stage 0 is free now: [KP][DP] sums
+    __syncthreads();                                      // all tiles consumed: the stages are free
+    tc_fence_after();
+    float4* dump = reinterpret_cast<float4*>(smem + pl.x);   // [4 quadrants][KP][32 lanes] float4
     if (TRAIN) {
-        if (warp >= 2 && warp < 6) {
-            const int lt = tid - 64, col = lt % DP, sub = lt / DP;
+        for (int round = 0; round < kUGroups; ++round) {  // one group at a time adds its TMEM accumulators
+            if (warp >= 2 && ((warp - 2) >> 2) == round) {
+                const int quad = warp & 3;
+                const uint32_t acc_base = tmem_base + ((uint32_t)(quad * 32) << 16) + kUSlots * KP + round * (4 * KP);
+                for (int c0 = 0; c0 < KP; c0 += 4) {
+                    float4 v[4];
 #pragma unroll
-            for (int j = 0; j < NACC; ++j) scratch[(j * NSUB + sub) * DP + col] = acc[j];
-        }
-        __syncthreads();
-        if (warp >= 6) {
-            const int lt = tid - 64 - kUGroupThreads, col = lt % DP, sub = lt / DP;
+                    for (int j = 0; j < 4; ++j) v[j] = tmem_ld_x4(acc_base + 4 * (c0 + j));
+                    tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < NACC; ++j) scratch[(j * NSUB + sub) * DP + col] += acc[j];
+                    for (int j = 0; j < 4; ++j) {
+                        float4* cell = dump + (quad * KP + c0 + j) * 32 + lane;
+                        if (round > 0) { const float4 o = *cell; v[j].x += o.x; v[j].y += o.y; v[j].z += o.z; v[j].w += o.w; }
+                        *cell = v[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
         }
-        __syncthreads();
+    }
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (TRAIN) {
         float* esum = p.stats + ((p.k + 3) & ~3);
-        for (int f = tid; f < KP * DPC; f += kUThreads) {
-            const int c = f / DPC, c4 = f % DPC;
-            if (c < p.k && c4 < nchunk) {
-                const float4 v = *reinterpret_cast<const float4*>(scratch + c * DP + 4 * c4);
-                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(esum + (size_t)c * p.d + 4 * c4, v);
+        for (int f = tid; f < KP * 32; f += kUThreads) {
+            const int c = f >> 5, l = f & 31;
+            if (c < p.k && l < nchunk && l < DPC) {
+                float4 a = dump[c * 32 + l];
+#pragma unroll
+                for (int w = 1; w < 4; ++w) {
+                    const float4 b = dump[(w * KP + c) * 32 + l];
+                    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                }
+                if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) red_add_v4(esum + (size_t)c * p.d + 4 * l, a);
             }
         }
     }
-    {
-        const int* h0 = reinterpret_cast<const int*>(smem + pl.grp) + 64 + 64 + 64 + (KP + 4) + 2 * KP;
-        const int* h1 = reinterpret_cast<const int*>(smem + pl.grp + pl.grp_stride) + 64 + 64 + 64 + (KP + 4) + 2 * KP;
-        for (int c = tid; c < p.k; c += kUThreads) {
-            const int v = h0[c] + h1[c];
-            if (v) atomicAdd(p.stats + c, (float)v);
-        }
+    for (int c = tid; c < p.k; c += kUThreads) {
+        const int v = hist[c];
+        if (v) atomicAdd(p.stats + c, (float)v);
     }
+    if (lane == 0 && n_rescored) { atomicAdd(&p.hdr->n_rescored, n_rescored); if (n_full) atomicAdd(&p.hdr->n_exact, n_full); }
     if (TRAIN) {
-        double t = block_sum((double)st.loss, red);
+        double t = block_sum((double)loss, red);
         if (tid == 0) atomicAdd(&p.hdr->loss_sum, t);
     }
     finish_ticket<TRAIN>(p, red, misc);

@@ -1,0 +1,61 @@
+"""Experiment helper (not part of the product): build libtvq with -DTVQ_PROFILE_PHASES, run the
+fused forward at a large N and print CTA 0's per-phase clock totals per epilogue group."""
+import ctypes, os, subprocess, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "t-vq-vae-trajgen_b200", "csrc")
+SO = os.path.join(CSRC, "_prof", "libtvq_prof.so")
+
+VARIANTS = {"base": [], "ng3": ["-DTVQ_UGROUPS=3"], "ng1": ["-DTVQ_UGROUPS=1"]}
+
+def so_path(v):
+    return SO.replace(".so", f"_{v}.so")
+
+def build():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    procs = []
+    for v, flags in VARIANTS.items():
+        procs.append(subprocess.Popen(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                           "-DTVQ_PROFILE_PHASES", *flags, "-shared", "-Xcompiler", "-fPIC", "-o", so_path(v),
+                           os.path.join(CSRC, "tvq_api.cu")], cwd=CSRC))
+    for pr in procs:
+        assert pr.wait() == 0
+
+def run(n=1 << 22, k=32, d=128, train=True, variant='base'):
+    lib = ctypes.CDLL(so_path(variant))
+    print('variant', variant)
+    vp, i64, i, u, f, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_size_t
+    lib.tvq_forward.argtypes = [vp, vp, i64, i, i, u, f, vp, vp, vp, vp, vp, sz, vp]
+    lib.tvq_workspace_bytes.restype = sz
+    lib.tvq_workspace_bytes.argtypes = [i64, i, i]
+    dev = torch.device("cuda:0")
+    x = torch.randn(n, d, device=dev); e = torch.randn(k, d, device=dev)
+    idx = torch.empty(n, dtype=torch.int64, device=dev); q = torch.empty_like(x)
+    stats = torch.empty(((k + 3) & ~3) + k * d, device=dev); sc = torch.empty(8, device=dev)
+    wsb = lib.tvq_workspace_bytes(n, k, d); ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+    flags = (1 if train else 0) | 2
+    for _ in range(3):
+        rc = lib.tvq_forward(x.data_ptr(), e.data_ptr(), n, k, d, flags, 1.0, idx.data_ptr(), q.data_ptr(), stats.data_ptr(),
+                             sc.data_ptr(), ws.data_ptr(), wsb, None)
+        assert rc == 0, rc
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lib.tvq_forward(x.data_ptr(), e.data_ptr(), n, k, d, flags, 1.0, idx.data_ptr(), q.data_ptr(), stats.data_ptr(),
+                    sc.data_ptr(), ws.data_ptr(), wsb, None)
+    e1.record(); torch.cuda.synchronize()
+    out = (ctypes.c_ulonglong * 32)()
+    lib.tvq_debug_phases(out)
+    names = ["wait_full", "wait_tmem", "scan", "apply_rest", "release", "ap_load+shfl", "ap_butterfly", "ap_decide+out", "ap_rmw"]
+    tiles = (n + 63) // 64
+    per_cta = tiles / 148
+    print(f"n={n} k={k} d={d} train={train}: {e0.elapsed_time(e1):.3f} ms, ~{per_cta:.0f} tiles/CTA ({per_cta/2:.0f} per group)")
+    for g in range(2):
+        tot = sum(out[g * 16 + j] for j in range(9))
+        print(f" group {g}: total {tot} clk;", ", ".join(f"{names[j]}={out[g*16+j]/max(1,per_cta/2):.0f}" for j in range(9)), "(clk per tile)")
+
+if __name__ == "__main__":
+    if "--build" in sys.argv:
+        build()
+    else:
+        [run(train=True, variant=v) for v in VARIANTS]
