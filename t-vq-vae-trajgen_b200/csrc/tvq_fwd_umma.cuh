@@ -44,7 +44,7 @@ __device__ unsigned long long g_phase_clk[2][16];
 #endif
 
 #ifndef TVQ_UGROUPS
-#define TVQ_UGROUPS 2
+#define TVQ_UGROUPS 3
 #endif
 constexpr int kUM = 64;                 // latents per UMMA tile (M)
 constexpr int kUGroups = TVQ_UGROUPS;   // epilogue groups of 4 warps (one warp per TMEM lane quadrant)
@@ -55,7 +55,7 @@ constexpr int kUBatch = 4;              // rows a warp keeps in flight in the ap
 
 struct UmmaPlan {
     int stages, stage_bytes;
-    int x, cb, e2s, hist, red, misc, bars, tmem, total;
+    int x, cb, e2s, hist, keys, red, misc, bars, tmem, total;
 };
 __host__ __device__ inline UmmaPlan make_umma_plan(int dp, int kp, int stages) {
     UmmaPlan u;
@@ -67,6 +67,7 @@ __host__ __device__ inline UmmaPlan make_umma_plan(int dp, int kp, int stages) {
     u.e2s = o;  o += kp * 4;
     u.hist = o; o += kp * 4;
     o = (o + 15) & ~15;
+    u.keys = o; o += 4 * kUGroups * 16 * 16;   // per epilogue warp: 16 rows x (4 best keys)
     u.red = o;  o += 16 * 8;
     u.misc = o; o += 16 * 4;
     u.bars = o; o += (2 * kUMaxStages + 2 * kUSlots) * 8;
@@ -156,6 +157,67 @@ __device__ __noinline__ int resolve_row(const float4 xv, const float bnd2, const
     return arg | (1 << 16);
 }
 
+// Everything one epilogue warp needs to finish ONE row (slow, fully checked form).  Used for the
+// rows of the last, partial tile only; the steady state is the batched code in the kernel body.
+struct RowResult {
+    float loss;
+    unsigned counters;   // low 16 bits: re-scored (0/1); high 16 bits: needed fp64 (0/1)
+};
+template <int DP, int KP, bool TRAIN>
+__device__ __noinline__ RowResult row_generic(float* q, int64_t* idx, const int d, const int k, const float* xt,
+                                              const float* cbs, const float* e2s, int* hist, const float4 key, const int trow,
+                                              const int64_t grow, const bool has_chunk, const int lane, const float emax,
+                                              const float err_c, const uint32_t acc_base) {
+    unsigned counters = 0;
+    using namespace sm100;
+    const float BIG = 1e30f;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 xv = has_chunk ? *reinterpret_cast<const float4*>(xt + tile_off<kUM>(trow, lane)) : z4;
+    float ss = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, xv.w * xv.w)));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const float bnd = fmaf(sqrt_approx(ss), 1.0001f, emax);
+    const float bnd2 = bnd * bnd;
+    const float lim = fmaf(err_c, bnd2, key.x);
+    int code = (int)(__float_as_uint(key.x) & 63u);
+    if (!(key.y > lim) || !(key.x < BIG)) {
+        const int nc = 1 + (key.y <= lim) + (key.z <= lim) + (key.w <= lim);
+        const bool finite = key.x < BIG;
+        const int r = resolve_row<KP>(xv, bnd2, __float_as_uint(key.x) & 63u, __float_as_uint(key.y) & 63u,
+                                      __float_as_uint(key.z) & 63u, nc, nc == 4 || !finite, cbs, e2s, k, has_chunk, lane);
+        counters += 1u + ((unsigned)(r >> 16) << 16);
+        code = r & 0xffff;
+        code = code < k ? code : 0;
+    }
+    float loss = 0.f;
+    if (lane == 0) { atomicAdd(hist + code, 1); idx[grow] = (int64_t)code; }
+    if (q != nullptr || TRAIN) {
+        const float4 ev = has_chunk ? *reinterpret_cast<const float4*>(cbs + tile_off<KP>(code, lane)) : z4;
+        float4 o = ev;
+        if (TRAIN) {
+            o.x = __fadd_rn(xv.x, __fsub_rn(ev.x, xv.x));
+            o.y = __fadd_rn(xv.y, __fsub_rn(ev.y, xv.y));
+            o.z = __fadd_rn(xv.z, __fsub_rn(ev.z, xv.z));
+            o.w = __fadd_rn(xv.w, __fsub_rn(ev.w, xv.w));
+            const float dx = __fsub_rn(o.x, xv.x), dy = __fsub_rn(o.y, xv.y), dz = __fsub_rn(o.z, xv.z), dw = __fsub_rn(o.w, xv.w);
+            loss = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+        }
+        if (q != nullptr && has_chunk) st_stream_v4(q + (size_t)grow * d + 4 * lane, o);
+    }
+    if (TRAIN) {
+        __syncwarp();
+        tmem_st_wait();
+        float4 a = tmem_ld_x4(acc_base + 4 * code);
+        tmem_ld_wait();
+        a.x += xv.x; a.y += xv.y; a.z += xv.z; a.w += xv.w;
+        tmem_st_x4(acc_base + 4 * code, a);
+    }
+    RowResult rr;
+    rr.loss = loss;
+    rr.counters = counters;
+    return rr;
+}
+
 template <int DP, int KP, bool TRAIN, bool FULLD>
 __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const FwdParams p,
                                                                const int stages) {
@@ -171,6 +233,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     static_assert(DP == 64 || DP == 128, "resident-codebook path: d padded to 64 or 128");
     static_assert(KP == 16 || KP == 32 || KP == 64, "resident-codebook path: k padded to 16, 32 or 64");
     static_assert(TMEM_NEED <= 512, "tensor memory budget");
+    static_assert(kUBatch == 4, "the batched apply code is written for 4 rows in flight");
 
     const UmmaPlan pl = make_umma_plan(DP, KP, stages);
     float* cbs = reinterpret_cast<float*>(smem + pl.cb);
@@ -222,7 +285,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
 
     const int num_tiles = p.num_tiles;                    // tiles of 64 rows
     float loss = 0.f;
-    unsigned n_rescored = 0, n_full = 0;
+    unsigned counters = 0;                                // low 16 bits: re-scored rows, high: fp64 rows
 
     if (warp == 0) {
         // ============================================================ TMA producer
@@ -266,8 +329,14 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         const uint32_t acc_base = tmem_base + lane_base + kUSlots * KP + g * (4 * KP);
         const bool has_chunk = FULLD ? true : (lane < DPC && lane < nchunk);   // FULLD: d == DP == 128
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* keys = reinterpret_cast<float4*>(smem + pl.keys) + (warp - 2) * 16;   // this warp's 16 rows
+        // per-lane address pieces of the swizzled tiles (tile_off with the lane's chunk folded in)
+        const uint32_t l7s = (uint32_t)(lane & 7) << 4;                 // the lane's 16-byte chunk within a 128-byte row
+        const int alane = has_chunk ? lane : 0;                         // lanes without a chunk read chunk 0 (discarded)
+        const uint32_t cbw = smem_u32(cbs) + (uint32_t)(alane >> 3) * (KP * 128);
         if (TRAIN) {
-            for (int c = 0; c < KP; ++c) tmem_st_x4(acc_base + 4 * c, make_float4(0.f, 0.f, 0.f, 0.f));
+            for (int c = 0; c < KP; ++c) tmem_st_x4(acc_base + 4 * c, z4);
             tmem_st_wait();
         }
 #ifdef TVQ_PROFILE_PHASES
@@ -288,8 +357,8 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
             tc_fence_after();
             TVQ_PH(1);
             // ---- 1. scan: lane l < 16 owns row l of the quadrant (M = 64 accumulator layout)
-            float t0 = BIG, t1 = BIG, t2 = BIG, t3 = BIG;
             {
+                float t0 = BIG, t1 = BIG, t2 = BIG, t3 = BIG;
                 float sc[KP];
 #pragma unroll
                 for (int c0 = 0; c0 < KP; c0 += 16) tmem_ld_x16(tmem_base + lane_base + (uint32_t)(slot * KP + c0), sc + c0);
@@ -303,129 +372,139 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                     const float key = __uint_as_float((__float_as_uint(sv) & ~63u) | (unsigned)c);
                     top4_insert(key, t0, t1, t2, t3);
                 }
+                if (lane < 16) keys[lane] = make_float4(t0, t1, t2, t3);
+                __syncwarp();
             }
             TVQ_PH(2);
-            // ---- 2-4. apply: all lanes on one row, kUBatch rows in flight
-            int mycode = 0;                               // lane r (< 16) keeps the code of row r
+            // ---- 2-4. apply: all lanes on one row, 4 rows in flight
             const int nvalid = (int)((p.n - row0) < 16 ? (p.n - row0) : 16);      // rows of this warp inside n
-            const float* xrow = xt + (lane >> 3) * (kUM * 32) + quad * 16 * 32;   // + r*32 + swizzled chunk
-            float* qrow = p.q ? p.q + (size_t)row0 * p.d + 4 * lane : nullptr;
+            if (nvalid == 16) {
+                // shared-space byte addresses with the lane's chunk and swizzle folded in:
+                //   x row r   : xw + r*128 + ((l7 ^ (r & 7)) << 4)      ((quad*16 + r) & 7 == r & 7)
+                //   code row c: cbw + c*128 + ((l7 ^ (c & 7)) << 4)
+                const uint32_t xw = smem_u32(xt) + (uint32_t)(alane >> 3) * (kUM * 128) + (uint32_t)quad * (16 * 128);
+                float* qp = p.q ? p.q + (size_t)row0 * p.d + 4 * lane : nullptr;
+                const size_t qstep = FULLD ? (size_t)DP : (size_t)p.d;
+                int mycode = 0;                           // lane r (< 16) collects the code of row r
 #pragma unroll 1
-            for (int b = 0; b < 16 / kUBatch; ++b) {
-                float4 xv[kUBatch];
-                float ss[kUBatch], k0[kUBatch], k1[kUBatch];
+                for (int b = 0; b < 4; ++b) {
+                    float4 xv[4], key[4];
+                    float ss[4];
+                    const uint32_t xb = xw + (uint32_t)b * 512u;
+                    const uint32_t bsw = (uint32_t)(b & 1) << 6;           // (r & 7) << 4 = bsw | (u << 4)
 #pragma unroll
-                for (int u = 0; u < kUBatch; ++u) {
-                    const int r = b * kUBatch + u;
-                    // (row & 7) == (r & 7): quad*16 is a multiple of 8
-                    const float4 ld = *reinterpret_cast<const float4*>(xrow + r * 32 + (((lane ^ r) & 7) << 2));
-                    xv[u] = has_chunk ? ld : make_float4(0.f, 0.f, 0.f, 0.f);
-                    k0[u] = __shfl_sync(0xffffffffu, t0, r);
-                    k1[u] = __shfl_sync(0xffffffffu, t1, r);
-                    ss[u] = fmaf(xv[u].x, xv[u].x, fmaf(xv[u].y, xv[u].y, fmaf(xv[u].z, xv[u].z, xv[u].w * xv[u].w)));
-                }
-                TVQ_PH(5);
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-                    for (int u = 0; u < kUBatch; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], off);
-                TVQ_PH(6);
-                int cd[kUBatch];
-#pragma unroll
-                for (int u = 0; u < kUBatch; ++u) {        // (a) decisions
-                    const int r = b * kUBatch + u;
-                    const bool valid = r < nvalid;
-                    const float bnd = sqrt_approx(ss[u]) * 1.0001f + emax;
-                    const float bnd2 = bnd * bnd;
-                    const float lim = fmaf(err_c, bnd2, k0[u]);
-                    int code = (int)(__float_as_uint(k0[u]) & 63u);
-                    if (valid && !(k1[u] > lim && k0[u] < BIG)) {
-                        // second-best inside the bound (or non-finite scores): cascade re-score
-                        const float k2 = __shfl_sync(0xffffffffu, t2, r), k3 = __shfl_sync(0xffffffffu, t3, r);
-                        const int nc = 1 + (k1[u] <= lim) + (k2 <= lim) + (k3 <= lim);
-                        const bool finite = k0[u] < BIG;
-                        code = resolve_row<KP>(xv[u], bnd2, __float_as_uint(k0[u]) & 63u, __float_as_uint(k1[u]) & 63u,
-                                               __float_as_uint(k2) & 63u, nc, nc == 4 || !finite, cbs, e2s, p.k,
-                                               has_chunk, lane);
-                        n_full += (unsigned)(code >> 16);
-                        code &= 0xffff;
-                        code = code < p.k ? code : 0;      // non-finite rows: any code, but a valid one
-                        ++n_rescored;
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 ld = lds_v4(xb + u * 128 + ((l7s ^ (u << 4)) ^ bsw));
+                        xv[u] = has_chunk ? ld : z4;
+                        key[u] = keys[b * 4 + u];
+                        ss[u] = fmaf(xv[u].x, xv[u].x, fmaf(xv[u].y, xv[u].y, fmaf(xv[u].z, xv[u].z, xv[u].w * xv[u].w)));
                     }
-                    cd[u] = valid ? code : -1;
-                    if (lane == r) mycode = code;
-                }
-                if (p.q != nullptr || TRAIN) {
-                    float4 ev[kUBatch];
+                    TVQ_PH(5);
 #pragma unroll
-                    for (int u = 0; u < kUBatch; ++u) {    // (b) gather from the shared-memory codebook
-                        const int c = cd[u] < 0 ? 0 : cd[u];
-                        const float4 ld = *reinterpret_cast<const float4*>(cbs + (lane >> 3) * (KP * 32) + c * 32 + (((lane ^ c) & 7) << 2));
-                        ev[u] = (has_chunk && cd[u] >= 0) ? ld : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    for (int off = 16; off >= 1; off >>= 1)
 #pragma unroll
-                    for (int u = 0; u < kUBatch; ++u) {    // (c) straight-through, loss, store
-                        float4 o = ev[u];
-                        if (TRAIN) {
-                            // x + (e - x): two rounded fp32 ops, never contracted; the loss is taken on
-                            // that rounded tensor, as F.mse_loss(quantize.detach(), x) does.  Rows past
-                            // n are zero-filled and gather zeros, so they add exactly 0.
-                            o.x = __fadd_rn(xv[u].x, __fsub_rn(ev[u].x, xv[u].x));
-                            o.y = __fadd_rn(xv[u].y, __fsub_rn(ev[u].y, xv[u].y));
-                            o.z = __fadd_rn(xv[u].z, __fsub_rn(ev[u].z, xv[u].z));
-                            o.w = __fadd_rn(xv[u].w, __fsub_rn(ev[u].w, xv[u].w));
-                            const float dx = __fsub_rn(o.x, xv[u].x), dy = __fsub_rn(o.y, xv[u].y);
-                            const float dz = __fsub_rn(o.z, xv[u].z), dw = __fsub_rn(o.w, xv[u].w);
-                            loss = fmaf(dx, dx, loss);
-                            loss = fmaf(dy, dy, loss);
-                            loss = fmaf(dz, dz, loss);
-                            loss = fmaf(dw, dw, loss);
+                        for (int u = 0; u < 4; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], off);
+                    TVQ_PH(6);
+                    int cd[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {          // (a) decisions
+                        const float bnd = fmaf(sqrt_approx(ss[u]), 1.0001f, emax);
+                        const float bnd2 = bnd * bnd;
+                        const float lim = fmaf(err_c, bnd2, key[u].x);
+                        int code = (int)(__float_as_uint(key[u].x) & 63u);
+                        if (!(key[u].y > lim)) {
+                            // second best inside the bound (or non-finite scores: the comparison is
+                            // false for NaN): cascade re-score
+                            const int nc = 1 + (key[u].y <= lim) + (key[u].z <= lim) + (key[u].w <= lim);
+                            const bool finite = key[u].x < BIG && bnd2 < BIG;
+                            const int r = resolve_row<KP>(xv[u], bnd2, __float_as_uint(key[u].x) & 63u,
+                                                          __float_as_uint(key[u].y) & 63u, __float_as_uint(key[u].z) & 63u, nc,
+                                                          nc == 4 || !finite, cbs, e2s, p.k, has_chunk, lane);
+                            counters += 1u + ((unsigned)(r >> 16) << 16);
+                            code = r & 0xffff;
+                            code = code < p.k ? code : 0;  // non-finite rows: any code, but a valid one
                         }
-                        if (qrow != nullptr && has_chunk && cd[u] >= 0) st_stream_v4(qrow + (size_t)(b * kUBatch + u) * p.d, o);
+                        cd[u] = code;
                     }
-                }
-                if (lane < kUBatch) {                       // counts: lane u books row u of the batch
-                    int c = cd[0];
+                    if (p.q != nullptr || TRAIN) {
+                        float4 ev[4];
 #pragma unroll
-                    for (int u = 1; u < kUBatch; ++u) c = (lane == u) ? cd[u] : c;
-                    if (c >= 0) atomicAdd(hist + c, 1);
-                }
-                TVQ_PH(7);
-                if (TRAIN) {
-                    // rows of the batch that share a code are merged first, then one TMEM
-                    // read-modify-write per distinct code (codes are warp-uniform values)
-                    bool dup = false;
-#pragma unroll
-                    for (int v = 1; v < kUBatch; ++v)
-#pragma unroll
-                        for (int u = 0; u < v; ++u) dup |= (cd[v] == cd[u]) && cd[v] >= 0;
-                    if (dup) {                            // uncommon: taken as one warp-uniform branch
-#pragma unroll
-                        for (int v = 1; v < kUBatch; ++v)
-#pragma unroll
-                            for (int u = 0; u < v; ++u)
-                                if (cd[v] >= 0 && cd[v] == cd[u]) {
-                                    xv[u].x += xv[v].x; xv[u].y += xv[v].y; xv[u].z += xv[v].z; xv[u].w += xv[v].w;
-                                    cd[v] = -1;
-                                }
-                    }
-                    __syncwarp();
-                    tmem_st_wait();                       // the previous batch's stores have landed
-                    float4 a[kUBatch];
-#pragma unroll
-                    for (int u = 0; u < kUBatch; ++u)
-                        if (cd[u] >= 0) a[u] = tmem_ld_x4(acc_base + 4 * cd[u]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int u = 0; u < kUBatch; ++u)
-                        if (cd[u] >= 0) {
-                            a[u].x += xv[u].x; a[u].y += xv[u].y; a[u].z += xv[u].z; a[u].w += xv[u].w;
-                            tmem_st_x4(acc_base + 4 * cd[u], a[u]);
+                        for (int u = 0; u < 4; ++u) {      // (b) gather from the shared-memory codebook
+                            const uint32_t c = (uint32_t)cd[u];
+                            const float4 ld = lds_v4(cbw + (c << 7) + (((c << 4) ^ l7s) & 0x70u));
+                            ev[u] = has_chunk ? ld : z4;
                         }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {      // (c) straight-through, loss, store
+                            float4 o = ev[u];
+                            if (TRAIN) {
+                                // x + (e - x): two rounded fp32 ops, never contracted; the loss is taken
+                                // on that rounded tensor, as F.mse_loss(quantize.detach(), x) does
+                                o.x = __fadd_rn(xv[u].x, __fsub_rn(ev[u].x, xv[u].x));
+                                o.y = __fadd_rn(xv[u].y, __fsub_rn(ev[u].y, xv[u].y));
+                                o.z = __fadd_rn(xv[u].z, __fsub_rn(ev[u].z, xv[u].z));
+                                o.w = __fadd_rn(xv[u].w, __fsub_rn(ev[u].w, xv[u].w));
+                                const float dx = __fsub_rn(o.x, xv[u].x), dy = __fsub_rn(o.y, xv[u].y);
+                                const float dz = __fsub_rn(o.z, xv[u].z), dw = __fsub_rn(o.w, xv[u].w);
+                                loss = fmaf(dx, dx, loss);
+                                loss = fmaf(dy, dy, loss);
+                                loss = fmaf(dz, dz, loss);
+                                loss = fmaf(dw, dw, loss);
+                            }
+                            if (qp != nullptr && has_chunk) st_stream_v4(qp + u * qstep, o);
+                        }
+                        if (qp != nullptr) qp += 4 * qstep;
+                    }
+                    {   // lane 4b+u remembers the code of row 4b+u (idx store and counts happen once per tile)
+                        const unsigned pk = (unsigned)cd[0] | ((unsigned)cd[1] << 8) | ((unsigned)cd[2] << 16) | ((unsigned)cd[3] << 24);
+                        const int mine = (int)((pk >> ((lane & 3) << 3)) & 0xffu);
+                        mycode = ((lane >> 2) == b) ? mine : mycode;
+                    }
+                    TVQ_PH(7);
+                    if (TRAIN) {
+                        // ONE tensor-memory read-modify-write per row; rows of the batch that share a
+                        // code (a warp-uniform condition) take the sequential form
+                        const bool dup = cd[1] == cd[0] || cd[2] == cd[0] || cd[2] == cd[1] || cd[3] == cd[0] ||
+                                         cd[3] == cd[1] || cd[3] == cd[2];
+                        __syncwarp();
+                        tmem_st_wait();                   // the previous batch's stores have landed
+                        if (!dup) {
+                            float4 a[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) a[u] = tmem_ld_x4(acc_base + 4 * cd[u]);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                a[u].x += xv[u].x; a[u].y += xv[u].y; a[u].z += xv[u].z; a[u].w += xv[u].w;
+                                tmem_st_x4(acc_base + 4 * cd[u], a[u]);
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int u = 0; u < 4; ++u) {
+                                const int c = u == 0 ? cd[0] : u == 1 ? cd[1] : u == 2 ? cd[2] : cd[3];
+                                const float4 xa = u == 0 ? xv[0] : u == 1 ? xv[1] : u == 2 ? xv[2] : xv[3];
+                                float4 a = tmem_ld_x4(acc_base + 4 * c);
+                                tmem_ld_wait();
+                                a.x += xa.x; a.y += xa.y; a.z += xa.z; a.w += xa.w;
+                                tmem_st_x4(acc_base + 4 * c, a);
+                                tmem_st_wait();
+                            }
+                        }
+                    }
+                    TVQ_PH(8);
                 }
-                TVQ_PH(8);
+                if (lane < 16) {                            // idx + counts for the warp's 16 rows
+                    atomicAdd(hist + mycode, 1);
+                    p.idx[row0 + lane] = (int64_t)mycode;
+                }
+            } else {
+                for (int r = 0; r < nvalid; ++r) {        // last, partial tile: one fully checked row at a time
+                    const RowResult rr = row_generic<DP, KP, TRAIN>(p.q, p.idx, p.d, p.k, xt, cbs, e2s, hist, keys[r], quad * 16 + r,
+                                                                    row0 + r, has_chunk, lane, emax, err_c, acc_base);
+                    loss += rr.loss;
+                    counters += rr.counters;
+                }
             }
-            if (lane < nvalid) p.idx[row0 + lane] = (int64_t)mycode;
             TVQ_PH(3);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // this warp is done with the stage
@@ -485,7 +564,10 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         const int v = hist[c];
         if (v) atomicAdd(p.stats + c, (float)v);
     }
-    if (lane == 0 && n_rescored) { atomicAdd(&p.hdr->n_rescored, n_rescored); if (n_full) atomicAdd(&p.hdr->n_exact, n_full); }
+    if (lane == 0 && counters) {
+        atomicAdd(&p.hdr->n_rescored, counters & 0xffffu);
+        if (counters >> 16) atomicAdd(&p.hdr->n_exact, counters >> 16);
+    }
     if (TRAIN) {
         double t = block_sum((double)loss, red);
         if (tid == 0) atomicAdd(&p.hdr->loss_sum, t);

@@ -49,8 +49,13 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 __device__ __forceinline__ float sqrt_approx(float x) {      // MUFU.SQRT, ~2^-22 relative
     float y;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t saddr) {       // 16-byte load from a shared-space byte address
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
