@@ -333,7 +333,9 @@ def our_arm(args):
                "sample": f"5 full steps of the same workload ({LATENTS_PER_STEP} latents each, {s_per * 1e3:.1f} ms/step), "
                          "oracle/vq_oracle.py on torch CPU fp32"}
 
-    launches_per_step = 2 * (2 + 1 + 1)     # per codebook: prep + fused forward, EMA update, backward
+    # per codebook: 1 GPU: fused train step (forward + EMA in one kernel) + backward;
+    # data-parallel: prep + fused forward, [NCCL all-reduce], EMA update, backward
+    launches_per_step = 2 * (1 + 1) if world == 1 else 2 * (2 + 1 + 1)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

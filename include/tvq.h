@@ -58,7 +58,7 @@ TVQ_API const char *tvq_error_string(int code);
 /* 0 if `device` is compute capability 10.x; fills sm_count (may be NULL). */
 TVQ_API int tvq_device_check(int device, int *sm_count);
 
-/* Bytes of scratch the forward needs for (n, k, d): header + per-code constants.
+/* Bytes of scratch for (n, k, d): header + per-code constants + tvq_train_step's statistics.
  * The scratch must be zero-filled ONCE when allocated (it holds a launch ticket). */
 TVQ_API size_t tvq_workspace_bytes(int64_t n, int k, int d);
 
@@ -76,6 +76,20 @@ TVQ_API int tvq_forward(const float *x, const float *codebook, int64_t n, int k,
                 float commitment_weight, int64_t *idx, float *q, float *stats, float *scalars,
                 void *workspace, size_t workspace_bytes, void *stream);
 
+/* One training-mode codebook step in as few launches as the shape allows: everything tvq_forward
+ * does with TVQ_F_TRAIN | TVQ_F_WRITE_Q, then the EMA update of vq.py:227-242 on the statistics of
+ * THIS call (no all-reduce in between: the single-GPU / sync_codebook=False path).  For k <= 32,
+ * d <= 128 it is ONE kernel: the last CTA to finish applies the update.
+ *   embed [k,d] is read as the codebook and updated in place; cluster_size [k], embed_avg [k,d]
+ *   updated in place; embed_prev [k,d] (optional) receives the pre-update codebook for
+ *   tvq_backward; commit_out / weighted_out (optional, 1 float each) receive scalars[0] / [2].
+ *   The statistics live in a private part of `workspace` (zero before and after the call).    */
+TVQ_API int tvq_train_step(const float *x, float *embed, float *cluster_size, float *embed_avg,
+                   float *embed_prev, int64_t n, int k, int d, float commitment_weight,
+                   double decay, double eps, int64_t *idx, float *q, float *scalars,
+                   float *commit_out, float *weighted_out, void *workspace,
+                   size_t workspace_bytes, void *stream);
+
 /* EMA codebook update from (all-reduced) statistics: vq.py:231, :236-242 with helpers :59-64.
  *   cluster_size [k], embed_avg [k,d], embed [k,d] are updated in place; embed_prev [k,d]
  *   (optional, may be NULL) receives the codebook as it was before the update, which is the
@@ -86,11 +100,12 @@ TVQ_API int tvq_ema_update(const float *stats, float *cluster_size, float *embed
                    size_t workspace_bytes, void *stream);
 
 /* Backward of the train forward (autograd through vq.py:357-366):
- *   g_x = g_q + (g_scalars[0] + commitment_weight * g_scalars[2]) * 2/(n*d) * (x - q_st)
- *   with q_st recomputed from x, idx and the codebook the forward used.  g_scalars is the
- *   device gradient w.r.t. the forward's `scalars` ([0] commit loss, [2] weighted loss);
- *   NULL means zero.                                                                          */
-TVQ_API int tvq_backward(const float *g_q, const float *g_scalars, const float *x, const int64_t *idx,
+ *   g_x = g_q + (g_commit + commitment_weight * g_weighted) * 2/(n*d) * (x - q_st)
+ *   with q_st recomputed from x, idx and the codebook the forward used.  g_commit / g_weighted
+ *   are device scalars: the gradients w.r.t. the commit loss (scalars[0]) and the weighted loss
+ *   (scalars[2]); g_q is the gradient w.r.t. q.  Any of the three may be NULL (= zero).      */
+TVQ_API int tvq_backward(const float *g_q, const float *g_commit, const float *g_weighted,
+                 const float *x, const int64_t *idx,
                  const float *codebook, int64_t n, int k, int d, float commitment_weight,
                  float *g_x, void *stream);
 

@@ -169,6 +169,13 @@ extern "C" {
 __attribute__((visibility("default"))) int tvq_debug_phases(unsigned long long* out32) {
     return (int)cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(unsigned long long) * 32);
 }
+__attribute__((visibility("default"))) int tvq_debug_gt(unsigned long long* out4, int reset) {
+    if (reset) {
+        unsigned long long init[4] = {~0ull, 0ull, 0ull, 0ull};
+        return (int)cudaMemcpyToSymbol(g_gt, init, sizeof(init));
+    }
+    return (int)cudaMemcpyFromSymbol(out4, g_gt, sizeof(unsigned long long) * 4);
+}
 #endif
 
 int tvq_abi_version(void) { return 1; }
@@ -194,8 +201,9 @@ int tvq_device_check(int device, int* sm_count) {
 
 size_t tvq_workspace_bytes(int64_t n, int k, int d) {
     (void)n;
-    (void)d;
-    return sizeof(WsHeader) + (((size_t)(k > 0 ? k : 0) + 3) & ~(size_t)3) * sizeof(float) + 64;
+    const size_t kk = k > 0 ? (size_t)k : 0, dd = d > 0 ? (size_t)d : 0;
+    // header | |e|^2 table | private statistics scratch of tvq_train_step
+    return sizeof(WsHeader) + ((kk + 3) & ~(size_t)3) * sizeof(float) + (size_t)TVQ_STATS_LEN(kk, dd) * sizeof(float) + 64;
 }
 
 int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, unsigned flags,
@@ -231,6 +239,9 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
     p.x = x; p.cb = codebook; p.n = n; p.k = k; p.d = d;
     p.idx = idx; p.q = (flags & TVQ_F_WRITE_Q) ? q : nullptr; p.stats = stats; p.scalars = scalars;
     p.hdr = hdr; p.e2 = e2; p.commitment_weight = commitment_weight;
+    p.commit_out = nullptr; p.weighted_out = nullptr; p.fuse_ema = 0;
+    p.cluster_size = nullptr; p.embed_avg = nullptr; p.embed = nullptr; p.embed_prev = nullptr;
+    p.decay = p.one_minus_decay = p.eps = p.k_eps = 0.f;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
     p.exact = (flags & TVQ_F_EXACT) ? 1 : 0;
     p.given_idx = (flags & TVQ_F_GIVEN_IDX) ? 1 : 0;
@@ -251,6 +262,58 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
     SmemPlan pl = make_smem_plan(dp, k, p.stats_mode, p.use_hist, kBN);
     if (pl.total > di->max_smem_optin) return TVQ_ERR_UNSUPPORTED;
     return train ? dispatch_fwd_simt<true>(dp, p, pl, *di, stream) : dispatch_fwd_simt<false>(dp, p, pl, *di, stream);
+}
+
+int tvq_train_step(const float* x, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t n, int k,
+                   int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
+                   float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (k < 1 || d < 4 || d > 256 || (d & 3) || n < 0 || (int64_t)k * d >= (int64_t(1) << 31)) return TVQ_ERR_UNSUPPORTED;
+    if (!embed || !cluster_size || !embed_avg || !scalars || !workspace || (n > 0 && (!x || !idx || !q))) return TVQ_ERR_BAD_ARG;
+    if ((x && !aligned16(x)) || !aligned16(embed) || !aligned16(embed_avg) || (q && !aligned16(q)) || !aligned16(workspace) ||
+        (embed_prev && !aligned16(embed_prev)))
+        return TVQ_ERR_BAD_ARG;
+    if (workspace_bytes < tvq_workspace_bytes(n, k, d)) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    WsHeader* hdr = reinterpret_cast<WsHeader*>(workspace);
+    float* e2 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + sizeof(WsHeader));
+    float* scratch = e2 + (((size_t)k + 3) & ~(size_t)3);     // private statistics: zero on entry, zero on exit
+    const bool umma = n > 0 && k <= 32 && d <= 128 && n < (int64_t(1) << 31) - 64;
+    if (!umma) {
+        // generic composition: zero + |e|^2, CUDA-core forward, EMA kernel (three launches)
+        const int64_t stats_len = TVQ_STATS_LEN(k, d);
+        int64_t work = stats_len / 4 > (int64_t)k * 32 ? stats_len / 4 : (int64_t)k * 32;
+        int blocks = (int)((work + 255) / 256);
+        if (blocks > 4 * di->sm_count) blocks = 4 * di->sm_count;
+        prep_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(embed, k, d, e2, hdr, scratch, stats_len);
+        if ((rc = launch_status()) != TVQ_OK) return rc;
+    }
+    FwdParams p;
+    p.x = x; p.cb = embed; p.n = n; p.k = k; p.d = d;
+    p.idx = idx; p.q = q; p.stats = scratch; p.scalars = scalars;
+    p.hdr = hdr; p.e2 = e2; p.commitment_weight = commitment_weight;
+    p.commit_out = commit_out; p.weighted_out = weighted_out;
+    p.cluster_size = cluster_size; p.embed_avg = embed_avg; p.embed = embed; p.embed_prev = embed_prev;
+    p.decay = (float)decay; p.one_minus_decay = (float)(1.0 - decay); p.eps = (float)eps; p.k_eps = (float)((double)k * eps);
+    p.num_tiles = (int)((n + kBM - 1) / kBM);
+    p.exact = 0; p.given_idx = 0; p.use_hist = k <= 2048;
+    if (umma) {
+        p.fuse_ema = 1;
+        p.use_hist = 1;
+        p.stats_mode = kStatsSmall;
+        return dispatch_fwd_umma<true>(d <= 64 ? 64 : 128, k <= 16 ? 16 : 32, p, *di, stream);
+    }
+    p.fuse_ema = 0;
+    if (n > 0) {
+        const int dp = pad_dim(d);
+        p.stats_mode = ((int64_t)k * dp <= 8192 && k <= 512) ? kStatsSmall : kStatsLarge;
+        SmemPlan pl = make_smem_plan(dp, k, p.stats_mode, p.use_hist, kBN);
+        if (pl.total > di->max_smem_optin) return TVQ_ERR_UNSUPPORTED;
+        if ((rc = dispatch_fwd_simt<true>(dp, p, pl, *di, stream)) != TVQ_OK) return rc;
+    }
+    return tvq_ema_update(scratch, cluster_size, embed_avg, embed, embed_prev, k, d, decay, eps, workspace, workspace_bytes, stream_);
 }
 
 int tvq_ema_update(const float* stats, float* cluster_size, float* embed_avg, float* embed, float* embed_prev,
@@ -278,14 +341,14 @@ int tvq_ema_update(const float* stats, float* cluster_size, float* embed_avg, fl
     return launch_status();
 }
 
-int tvq_backward(const float* g_q, const float* g_scalars, const float* x, const int64_t* idx, const float* codebook,
-                 int64_t n, int k, int d, float commitment_weight, float* g_x, void* stream_) {
+int tvq_backward(const float* g_q, const float* g_commit, const float* g_weighted, const float* x, const int64_t* idx,
+                 const float* codebook, int64_t n, int k, int d, float commitment_weight, float* g_x, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     (void)k;
     if (d < 4 || (d & 3) || n < 0) return TVQ_ERR_UNSUPPORTED;
     if (n == 0) return TVQ_OK;
-    if (!g_q || !x || !idx || !codebook || !g_x) return TVQ_ERR_BAD_ARG;
-    if (!aligned16(g_q) || !aligned16(x) || !aligned16(codebook) || !aligned16(g_x)) return TVQ_ERR_BAD_ARG;
+    if (!x || !idx || !codebook || !g_x) return TVQ_ERR_BAD_ARG;
+    if ((g_q && !aligned16(g_q)) || !aligned16(x) || !aligned16(codebook) || !aligned16(g_x)) return TVQ_ERR_BAD_ARG;
     DeviceInfo* di = nullptr;
     int rc = device_info(&di);
     if (rc != TVQ_OK) return rc;
@@ -293,7 +356,7 @@ int tvq_backward(const float* g_q, const float* g_scalars, const float* x, const
     int64_t work = n * (d / 4);
     int64_t blocks = (work + 255) / 256;
     if (blocks > 8LL * di->sm_count) blocks = 8LL * di->sm_count;
-    backward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g_q, g_scalars, x, idx, codebook, n, d, commitment_weight, scale, g_x);
+    backward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g_q, g_commit, g_weighted, x, idx, codebook, n, d, commitment_weight, scale, g_x);
     return launch_status();
 }
 

@@ -105,19 +105,19 @@ __global__ void __launch_bounds__(256) ema_kernel(const EmaParams p) {
 // ------------------------------------------------------------------------------------------
 // Backward: g_x = g_q + coef * (x - q_st), coef = g_loss * w * 2 / (n*d); q_st = x + (e[idx]-x).
 // 12d + 8 bytes per latent (the code word comes from the L2-resident codebook).
-__global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__ g_q, const float* __restrict__ g_scalars,
-                                                        const float* __restrict__ x, const int64_t* __restrict__ idx,
-                                                        const float* __restrict__ cb, int64_t n, int d, float weight,
-                                                        float scale, float* __restrict__ g_x) {
+__global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__ g_q, const float* __restrict__ g_commit,
+                                                        const float* __restrict__ g_weighted, const float* __restrict__ x,
+                                                        const int64_t* __restrict__ idx, const float* __restrict__ cb, int64_t n,
+                                                        int d, float weight, float scale, float* __restrict__ g_x) {
     const int dq = d >> 2;
     const int64_t total = n * dq;
-    const float coef = g_scalars ? fmaf(weight, __ldg(g_scalars + 2), __ldg(g_scalars)) * scale : 0.f;
+    const float coef = fmaf(weight, g_weighted ? __ldg(g_weighted) : 0.f, g_commit ? __ldg(g_commit) : 0.f) * scale;
     for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = f / dq;
         const int c = (int)(f - row * dq);
         const int64_t code = __ldg(idx + row);
         const float4 xv = ld_stream_v4(x + 4 * f);
-        const float4 gv = ld_stream_v4(g_q + 4 * f);
+        const float4 gv = g_q ? ld_stream_v4(g_q + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 ev = __ldg(reinterpret_cast<const float4*>(cb + (size_t)code * d) + c);
         float4 o;
         o.x = fmaf(coef, __fsub_rn(xv.x, __fadd_rn(xv.x, __fsub_rn(ev.x, xv.x))), gv.x);

@@ -40,6 +40,15 @@ struct FwdParams {
     int use_hist;     // shared-memory count histogram (k <= 2048)
     int exact;        // decide every row with the canonical scan
     int given_idx;    // skip scoring: idx[] already holds the codes (stochastic / dropout branches)
+    float* commit_out;    // optional 1-element copies of scalars[0] / scalars[2] (separate autograd outputs)
+    float* weighted_out;
+    // fused EMA update by the last CTA (tvq_train_step): buffers updated in place, statistics consumed
+    int fuse_ema;
+    float* cluster_size;
+    float* embed_avg;
+    float* embed;         // == cb (written only after every CTA has finished reading it)
+    float* embed_prev;    // optional: receives the pre-update codebook
+    float decay, one_minus_decay, eps, k_eps;
 };
 
 // Shared-memory carve-up, computed identically on host and device.
@@ -276,7 +285,52 @@ __device__ __forceinline__ void finish_ticket(const FwdParams& p, double* red, i
             reinterpret_cast<unsigned*>(p.scalars)[5] = *reinterpret_cast<volatile unsigned*>(&p.hdr->n_exact);
             p.scalars[6] = 0.f;
             p.scalars[7] = 0.f;
+            if (p.commit_out) *p.commit_out = commit;
+            if (p.weighted_out) *p.weighted_out = __fmul_rn(commit, p.commitment_weight);
             p.hdr->ticket = 0;
+            p.hdr->loss_sum = 0.0;             // consumed: the header is clean for the next call
+            p.hdr->n_rescored = 0u;
+            p.hdr->n_exact = 0u;
+        }
+        if (TRAIN && p.fuse_ema) {
+            // EMA codebook update (vq.py:231,236-242) by this last CTA: every other CTA has taken its
+            // ticket, i.e. finished reading the codebook and flushing its statistics.  Same arithmetic
+            // as ema_kernel (tvq_aux.cuh); the statistics scratch is zeroed for the next call.
+            __syncthreads();
+            double part = 0.0;
+            for (int c = tid; c < p.k; c += blockDim.x)
+                part += (double)fmaf(__ldcg(p.stats + c), p.one_minus_decay, __fmul_rn(p.cluster_size[c], p.decay));
+            const double totn = block_sum(part, red);
+            if (tid == 0) red[15] = totn;
+            __syncthreads();
+            const float nsum = __double2float_rn(red[15]);
+            const float denom = __fadd_rn(nsum, p.k_eps);
+            const int kp = (p.k + 3) & ~3;
+            const int dq = p.d >> 2;
+            float4* esum4 = reinterpret_cast<float4*>(p.stats + kp);
+            float4* avg4 = reinterpret_cast<float4*>(p.embed_avg);
+            float4* emb4 = reinterpret_cast<float4*>(p.embed);
+            float4* prev4 = reinterpret_cast<float4*>(p.embed_prev);
+            for (int f = tid; f < p.k * dq; f += blockDim.x) {
+                const int c = f / dq;
+                const float cs = fmaf(__ldcg(p.stats + c), p.one_minus_decay, __fmul_rn(p.cluster_size[c], p.decay));
+                const float sm = __fmul_rn(__fdiv_rn(__fadd_rn(cs, p.eps), denom), nsum);
+                const float4 sv = __ldcg(esum4 + f);
+                float4 a = avg4[f];
+                a.x = fmaf(sv.x, p.one_minus_decay, __fmul_rn(a.x, p.decay));
+                a.y = fmaf(sv.y, p.one_minus_decay, __fmul_rn(a.y, p.decay));
+                a.z = fmaf(sv.z, p.one_minus_decay, __fmul_rn(a.z, p.decay));
+                a.w = fmaf(sv.w, p.one_minus_decay, __fmul_rn(a.w, p.decay));
+                avg4[f] = a;
+                if (prev4) prev4[f] = emb4[f];
+                emb4[f] = make_float4(__fdiv_rn(a.x, sm), __fdiv_rn(a.y, sm), __fdiv_rn(a.z, sm), __fdiv_rn(a.w, sm));
+                esum4[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+            for (int c = tid; c < kp; c += blockDim.x) {
+                if (c < p.k) p.cluster_size[c] = fmaf(__ldcg(p.stats + c), p.one_minus_decay, __fmul_rn(p.cluster_size[c], p.decay));
+                p.stats[c] = 0.f;
+            }
         }
     }
 }

@@ -38,6 +38,8 @@ namespace tvq {
 #ifdef TVQ_PROFILE_PHASES
 // Experiment build only (tools/profile_phases.py): per-phase clock64 totals of CTA 0's epilogue warps.
 __device__ unsigned long long g_phase_clk[2][16];
+__device__ unsigned long long g_gt[4];   // [0] min CTA start (globaltimer ns), [1] max CTA end, [2] max CTA clocks, [3] max main-loop-end clocks
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TVQ_PH(i) do { long long _t = clock64(); ph_acc[i] += _t - ph_t; ph_t = _t; } while (0)
 #else
 #define TVQ_PH(i) do { } while (0)
@@ -250,6 +252,14 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunk = p.d >> 2;
     const float BIG = 1e30f;                    // score of a padded code (finite: keys stay ordered)
+#ifdef TVQ_PROFILE_PHASES
+    long long kt[8];
+    kt[0] = clock64();
+    if (tid == 0) atomicMin(&g_gt[0], gtimer());
+#define TVQ_KT(i) kt[i] = clock64()
+#else
+#define TVQ_KT(i) do { } while (0)
+#endif
 
     // ------------------------------------------------------------------ CTA prologue
     if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need 1024-byte alignment
@@ -259,9 +269,10 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         if (row < p.k && c4 < nchunk) v = __ldg(reinterpret_cast<const float4*>(p.cb + (size_t)row * p.d) + c4);
         *reinterpret_cast<float4*>(cbs + tile_off<KP>(row, c4)) = v;
     }
-    for (int c = tid; c < KP; c += kUThreads) {
-        e2s[c] = (c < p.k) ? __ldg(p.e2 + c) : BIG;
-        hist[c] = 0;
+    for (int c = warp; c < KP; c += kUThreads / 32) {     // canonical |e|^2 (one warp per code), BIG for padding
+        float v = BIG;
+        if (c < p.k) v = __double2float_rn(canon_dot_global(p.cb + (size_t)c * p.d, p.cb + (size_t)c * p.d, nchunk, lane));
+        if (lane == 0) { e2s[c] = v; hist[c] = 0; }
     }
     fence_proxy_async_smem();                             // generic-proxy writes -> visible to tcgen05.mma
     if (tid == 0) {
@@ -275,6 +286,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    TVQ_KT(1);
     float emax2 = 0.f;
     for (int c = 0; c < KP; ++c) emax2 = fmaxf(emax2, (c < p.k) ? e2s[c] : 0.f);
     const float emax = sqrtf(emax2) * 1.0001f;
@@ -513,14 +525,16 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         if (TRAIN) tmem_st_wait();
 #ifdef TVQ_PROFILE_PHASES
         if (blockIdx.x == 0 && lane == 0 && quad == 0 && g < 2)
-            for (int i = 0; i < 10; ++i) g_phase_clk[g][i] = (unsigned long long)ph_acc[i];
+            for (int i = 0; i < 8; ++i) g_phase_clk[g][i] = (unsigned long long)ph_acc[i];
 #endif
     }
 
     // ------------------------------------------------------------------ teardown and flush
+    TVQ_KT(2);
     tc_fence_before();
     __syncthreads();                                      // all tiles consumed: the stages are free
     tc_fence_after();
+    TVQ_KT(3);
     float4* dump = reinterpret_cast<float4*>(smem + pl.x);   // [4 quadrants][KP][32 lanes] float4
     if (TRAIN) {
         for (int round = 0; round < kUGroups; ++round) {  // one group at a time adds its TMEM accumulators
@@ -544,6 +558,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
             __syncthreads();
         }
     }
+    TVQ_KT(4);
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
     if (TRAIN) {
         float* esum = p.stats + ((p.k + 3) & ~3);
@@ -568,11 +583,23 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         atomicAdd(&p.hdr->n_rescored, counters & 0xffffu);
         if (counters >> 16) atomicAdd(&p.hdr->n_exact, counters >> 16);
     }
+    TVQ_KT(5);
     if (TRAIN) {
         double t = block_sum((double)loss, red);
         if (tid == 0) atomicAdd(&p.hdr->loss_sum, t);
     }
+    TVQ_KT(6);
     finish_ticket<TRAIN>(p, red, misc);
+    TVQ_KT(7);
+#ifdef TVQ_PROFILE_PHASES
+    if (blockIdx.x == 0 && (tid == 0 || tid == 64))
+        for (int i = 0; i < 8; ++i) g_phase_clk[tid == 0 ? 0 : 1][8 + i] = (unsigned long long)(kt[i] - kt[0]);
+    if (tid == 0) {
+        atomicMax(&g_gt[1], gtimer());
+        atomicMax(&g_gt[2], (unsigned long long)(kt[7] - kt[0]));
+        atomicMax(&g_gt[3], (unsigned long long)(kt[3] - kt[0]));
+    }
+#endif
 }
 
 }  // namespace tvq

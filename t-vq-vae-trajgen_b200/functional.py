@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["Workspace", "vq_forward_raw", "vq_ema_update", "vq_backward", "vq_gather", "vq_neg_dist",
+__all__ = ["Workspace", "vq_forward_raw", "vq_train_step_raw", "vq_ema_update", "vq_backward", "vq_gather", "vq_neg_dist",
            "vq_reseed", "stats_offset", "stats_len", "VQTrainStep"]
 
 
@@ -97,15 +97,45 @@ def vq_ema_update(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg: to
     _lib.check(rc, "tvq_ema_update")
 
 
-def vq_backward(g_q: torch.Tensor, g_scalars: Optional[torch.Tensor], x: torch.Tensor, idx: torch.Tensor,
-                codebook: torch.Tensor, commitment_weight: float) -> torch.Tensor:
-    """g_x = g_q + (g_scalars[0] + w * g_scalars[2]) * 2/(n d) * (x - q_st)."""
-    _need(g_q, "g_q"); _need(x, "x"); _need(idx, "idx", torch.int64); _need(codebook, "codebook")
+def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: float, embed_prev: Optional[torch.Tensor]):
+    """tvq_train_step on a codebook module's buffers: fused forward + EMA (one kernel for k <= 32, d <= 128).
+
+    Returns (idx, q_st, scalars[8], commit[()], weighted[1]); the module's cluster_size / embed_avg /
+    embed are updated in place, `embed_prev` (optional) receives the codebook the outputs came from.
+    """
+    _need(x, "x")
+    embed = cb._embed_data()
+    n, d = x.shape
+    k = embed.shape[0]
+    idx = torch.empty(n, dtype=torch.int64, device=x.device)
+    q = torch.empty_like(x)
+    scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32, device=x.device)
+    commit = torch.empty((), dtype=torch.float32, device=x.device)
+    weighted = torch.empty(1, dtype=torch.float32, device=x.device)
+    if n == 0:
+        scalars.fill_(float("nan")); commit.fill_(float("nan")); weighted.fill_(float("nan"))
+    rc = _lib.load().tvq_train_step(x.data_ptr() if n else None, embed.data_ptr(), cb.cluster_size.data_ptr(),
+                                    cb.embed_avg.data_ptr(), embed_prev.data_ptr() if embed_prev is not None else None,
+                                    n, k, d, float(commitment_weight), float(cb.decay), float(cb.eps),
+                                    idx.data_ptr() if n else None, q.data_ptr() if n else None, scalars.data_ptr(),
+                                    commit.data_ptr(), weighted.data_ptr(), ws.buf.data_ptr(), ws.nbytes, _stream())
+    _lib.check(rc, "tvq_train_step")
+    return idx, q, scalars, commit, weighted
+
+
+def vq_backward(g_q: Optional[torch.Tensor], g_commit: Optional[torch.Tensor], g_weighted: Optional[torch.Tensor],
+                x: torch.Tensor, idx: torch.Tensor, codebook: torch.Tensor, commitment_weight: float) -> torch.Tensor:
+    """g_x = g_q + (g_commit + w * g_weighted) * 2/(n d) * (x - q_st); any gradient may be None (= 0)."""
+    _need(x, "x"); _need(idx, "idx", torch.int64); _need(codebook, "codebook")
+    for t, name in ((g_q, "g_q"), (g_commit, "g_commit"), (g_weighted, "g_weighted")):
+        if t is not None:
+            _need(t, name)
     n, d = x.shape
     g_x = torch.empty_like(x)
-    rc = _lib.load().tvq_backward(g_q.data_ptr(), g_scalars.data_ptr() if g_scalars is not None else None, x.data_ptr(),
-                                  idx.data_ptr(), codebook.data_ptr(), n, codebook.shape[0], d,
-                                  float(commitment_weight), g_x.data_ptr(), _stream())
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    rc = _lib.load().tvq_backward(ptr(g_q), ptr(g_commit), ptr(g_weighted), x.data_ptr(), idx.data_ptr(),
+                                  codebook.data_ptr(), n, codebook.shape[0], d, float(commitment_weight), g_x.data_ptr(),
+                                  _stream())
     _lib.check(rc, "tvq_backward")
     return g_x
 
@@ -149,34 +179,41 @@ class VQTrainStep(torch.autograd.Function):
     """One training-mode codebook step: assign + ST + commit loss + EMA, differentiable in x.
 
     forward(x[n,d], codebook_module, commitment_weight, given_idx|None)
-        -> (q_st[n,d], idx[n], scalars[8])   scalars[0] = commit loss, [1] = perplexity, [2] = w * commit
-    backward: g_x = g_q + (g_scalars[0] + w g_scalars[2]) * 2/(n d) * (x - q_st)   
-    The EMA update runs inside forward (after the optional all-reduce of the packed statistics,
-    vq.py:229/234); the pre-update codebook is kept for the backward.
+        -> (q_st[n,d], idx[n], scalars[8], commit[()], weighted[1])
+           scalars[1] = perplexity; commit = mean((q_st - x)^2); weighted = commitment_weight * commit
+    backward: g_x = g_q + (g_commit + w g_weighted) * 2/(n d) * (x - q_st)          
+
+    Without data-parallel statistics the whole step is tvq_train_step (one launch where the shape
+    allows).  With `sync_codebook` on an initialised process group the packed statistics are
+    all-reduced between the forward and the EMA kernel (vq.py:229/234).  The pre-update codebook is
+    kept for the backward.
     """
 
     @staticmethod
     def forward(ctx, x, cb, commitment_weight, given_idx):
+        ctx.set_materialize_grads(False)
         ws = cb._workspace(x.device)
-        idx, q, scalars = vq_forward_raw(x, cb._embed_data(), ws, train=True, write_q=True, idx=given_idx,
-                                         commitment_weight=commitment_weight)
-        cb._all_reduce_stats(ws.stats)
         prev = torch.empty_like(cb._embed_data()) if ctx.needs_input_grad[0] else None
-        vq_ema_update(ws.stats, cb.cluster_size, cb.embed_avg, cb._embed_data(), prev, cb.decay, cb.eps, ws)
+        if given_idx is None and not cb._ddp_active():
+            idx, q, scalars, commit, weighted = vq_train_step_raw(x, cb, ws, commitment_weight, prev)
+        else:
+            idx, q, scalars = vq_forward_raw(x, cb._embed_data(), ws, train=True, write_q=True, idx=given_idx,
+                                             commitment_weight=commitment_weight)
+            cb._all_reduce_stats(ws.stats)
+            vq_ema_update(ws.stats, cb.cluster_size, cb.embed_avg, cb._embed_data(), prev, cb.decay, cb.eps, ws)
+            commit, weighted = scalars[0].clone(), scalars[2:3].clone()
         ctx.save_for_backward(x, idx, prev)
         ctx.commitment_weight = float(commitment_weight)
-        ctx.mark_non_differentiable(idx)
-        return q, idx, scalars
+        ctx.mark_non_differentiable(idx, scalars)
+        return q, idx, scalars, commit, weighted
 
     @staticmethod
-    def backward(ctx, g_q, g_idx, g_scalars):
+    def backward(ctx, g_q, g_idx, g_scalars, g_commit, g_weighted):
         x, idx, prev = ctx.saved_tensors
-        if g_q is None:
-            g_q = torch.zeros_like(x)
-        elif not g_q.is_contiguous():
+        if g_q is not None and not g_q.is_contiguous():
             g_q = g_q.contiguous()
-        if g_scalars is None:
+        if g_commit is None and g_weighted is None:
             return g_q, None, None, None
-        if not g_scalars.is_contiguous():
-            g_scalars = g_scalars.contiguous()
-        return vq_backward(g_q, g_scalars, x, idx, prev, ctx.commitment_weight), None, None, None
+        g_commit = g_commit.contiguous() if g_commit is not None else None
+        g_weighted = g_weighted.contiguous() if g_weighted is not None else None
+        return vq_backward(g_q, g_commit, g_weighted, x, idx, prev, ctx.commitment_weight), None, None, None

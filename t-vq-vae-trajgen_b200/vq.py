@@ -92,10 +92,13 @@ class EuclideanCodebook(nn.Module):
             self._ws = TF.Workspace(self.codebook_size, self.dim, device)
         return self._ws
 
+    def _ddp_active(self) -> bool:
+        return bool(self.use_ddp and distributed.is_available() and distributed.is_initialized()
+                    and distributed.get_world_size() > 1)
+
     def _all_reduce_stats(self, stats: torch.Tensor) -> None:
         """The reference's two all_reduce hooks (vq.py:229, :234) as ONE call on the packed buffer."""
-        if self.use_ddp and distributed.is_available() and distributed.is_initialized() \
-                and distributed.get_world_size() > 1:
+        if self._ddp_active():
             distributed.all_reduce(stats)
 
     def _embed_data(self) -> torch.Tensor:
@@ -193,8 +196,7 @@ class EuclideanCodebook(nn.Module):
         commit = weighted = None
         if self.training:
             if straight_through:
-                q, idx, scalars = TF.VQTrainStep.apply(flat, self, commitment_weight, given)
-                commit, weighted = scalars[0], scalars[2:3]
+                q, idx, scalars, commit, weighted = TF.VQTrainStep.apply(flat, self, commitment_weight, given)
             else:
                 idx, _, scalars = TF.vq_forward_raw(flat.detach(), self._embed_data(), ws, train=True, write_q=False,
                                                     idx=given)

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "t-vq-vae-trajgen_b200", "csrc")
 SO = os.path.join(CSRC, "_prof", "libtvq_prof.so")
 
-VARIANTS = {"base": [], "ng3": ["-DTVQ_UGROUPS=3"], "ng1": ["-DTVQ_UGROUPS=1"]}
+VARIANTS = {"base": []}
 
 def so_path(v):
     return SO.replace(".so", f"_{v}.so")
@@ -39,6 +39,8 @@ def run(n=1 << 22, k=32, d=128, train=True, variant='base'):
                              sc.data_ptr(), ws.data_ptr(), wsb, None)
         assert rc == 0, rc
     torch.cuda.synchronize()
+    gt = (ctypes.c_ulonglong * 4)()
+    lib.tvq_debug_gt(gt, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     lib.tvq_forward(x.data_ptr(), e.data_ptr(), n, k, d, flags, 1.0, idx.data_ptr(), q.data_ptr(), stats.data_ptr(),
@@ -46,16 +48,19 @@ def run(n=1 << 22, k=32, d=128, train=True, variant='base'):
     e1.record(); torch.cuda.synchronize()
     out = (ctypes.c_ulonglong * 32)()
     lib.tvq_debug_phases(out)
+    lib.tvq_debug_gt(gt, 0)
+    print(f"  globaltimer: first CTA start -> last CTA end = {(gt[1]-gt[0])/1000:.2f} us; max CTA clocks {gt[2]} ; max clocks to end of main loop {gt[3]}")
     names = ["wait_full", "wait_tmem", "scan", "apply_rest", "release", "ap_load+shfl", "ap_butterfly", "ap_decide+out", "ap_rmw"]
     tiles = (n + 63) // 64
     per_cta = tiles / 148
     print(f"n={n} k={k} d={d} train={train}: {e0.elapsed_time(e1):.3f} ms, ~{per_cta:.0f} tiles/CTA ({per_cta/2:.0f} per group)")
+    print("  kernel timeline (clk from start) thread0:", [int(out[8 + i]) for i in range(8)], " thread64:", [int(out[16 + 8 + i]) for i in range(8)])
     for g in range(2):
-        tot = sum(out[g * 16 + j] for j in range(9))
-        print(f" group {g}: total {tot} clk;", ", ".join(f"{names[j]}={out[g*16+j]/max(1,per_cta/2):.0f}" for j in range(9)), "(clk per tile)")
+        tot = sum(out[g * 16 + j] for j in range(8))
+        print(f" group {g}: total {tot} clk;", ", ".join(f"{names[j]}={out[g*16+j]/max(1,per_cta/2):.0f}" for j in range(8)), "(clk per tile)")
 
 if __name__ == "__main__":
     if "--build" in sys.argv:
         build()
     else:
-        [run(train=True, variant=v) for v in VARIANTS]
+        run(n=18432); run(n=76800); run(n=1<<20)
