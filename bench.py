@@ -170,6 +170,8 @@ def our_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     hbm_gbs, bf16_tf, peak_src = load_peaks()
 
@@ -184,11 +186,20 @@ def our_arm(args):
 
     ones = torch.ones(1, device=dev)
 
+    side_h = torch.cuda.Stream()
+
     def step(xl, xh, gl, gh):
-        """One VQ train step (both codebooks), forward + backward, via the public module API."""
+        """One VQ train step (both codebooks), forward + backward, via the public module API.
+        The LF and HF quantisers are independent, so each runs on its own stream: with data-parallel
+        statistics the all-reduce of one overlaps the kernels of the other."""
+        cur = torch.cuda.current_stream()
+        side_h.wait_stream(cur)
+        with torch.cuda.stream(side_h):
+            qh, ih, lh, ph = vq_h(xh)
+            torch.autograd.grad([qh, lh["loss"]], [xh], [gh, ones])
         ql, il, ll, pl = vq_l(xl)
-        qh, ih, lh, ph = vq_h(xh)
-        torch.autograd.grad([ql, qh, ll["loss"], lh["loss"]], [xl, xh], [gl, gh, ones, ones])
+        torch.autograd.grad([ql, ll["loss"]], [xl], [gl, ones])
+        cur.wait_stream(side_h)
         return ll["loss"], lh["loss"], il, ih
 
     def barrier():
@@ -224,7 +235,7 @@ def our_arm(args):
     # ---- CUDA-graph replay of the same step (launch-bound regime: 8 small kernels per step) -------
     graphs = None
     graph_ms = None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         try:
             graphs = []
             side = torch.cuda.Stream()
@@ -233,19 +244,26 @@ def our_arm(args):
                 for s in sets:
                     step(*s)
             torch.cuda.current_stream().wait_stream(side)
-            clear_grads()
+            barrier()
             for s in sets:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     step(*s)
                 graphs.append(g)
+        except Exception as exc:   # report, never hide
+            print(f"[bench] rank {rank}: CUDA-graph capture failed: {exc}", file=sys.stderr)
+            graphs = None
+        if world > 1:              # every rank must take the same path BEFORE anything is replayed
+            torch.cuda.synchronize()
+            ok = torch.tensor([1 if graphs is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0:
+                graphs = None
+        if graphs is not None:
             for i in range(max(args.warmup, 3)):
                 graphs[i % N_INPUT_SETS].replay()
             graph_ms = timed(lambda i: graphs[i % N_INPUT_SETS].replay(), args.steps)
-        except Exception as exc:   # report, never hide
-            print(f"[bench] CUDA-graph capture failed: {exc}", file=sys.stderr)
-            graphs, graph_ms = None, None
-        clear_grads()
 
     # ---- the timed region that `value` reports, with clocks sampled during it -----------------------
     sampler = ClockSampler(local)
@@ -349,9 +367,15 @@ def our_arm(args):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "sweep": sweep,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work: drop them, drain, and leave without the (hanging) teardown
+        graphs = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def sweep_point(tvq, dev, n, k, d, hbm_gbs, bf16_tf):
