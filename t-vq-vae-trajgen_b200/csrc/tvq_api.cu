@@ -8,6 +8,7 @@
 #include "tvq_aux.cuh"
 #include "tvq_common.cuh"
 #include "tvq_fwd_simt.cuh"
+#include "tvq_fwd_stream.cuh"
 #include "tvq_fwd_umma.cuh"
 
 using namespace tvq;
@@ -161,6 +162,74 @@ int dispatch_fwd_umma(int dp, int kp, const FwdParams& p, const DeviceInfo& di, 
     return TVQ_ERR_UNSUPPORTED;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streamed-codebook tcgen05 path (any k): TMA tensor map over the bf16 codebook copy in the workspace.
+inline int stream_dp(int d) { return d <= 64 ? 64 : d <= 128 ? 128 : 256; }
+// |e|^2 table length: padded to a multiple of 256 (pad = +BIG) so that the streamed path can bulk-copy whole slices
+inline size_t e2_len(int k) { return ((size_t)(k > 0 ? k : 0) + 255) & ~(size_t)255; }
+inline size_t ws_bf16_offset(int k, int d) {
+    const size_t kk = (size_t)k, dd = (size_t)d;
+    size_t o = sizeof(WsHeader) + e2_len(k) * sizeof(float) + (size_t)TVQ_STATS_LEN(kk, dd) * sizeof(float);
+    return (o + 255) & ~(size_t)255;
+}
+
+int make_cb_tensor_map(CUtensorMap* tm, const void* cbh, int k, int dp, int nt) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return TVQ_ERR_DEVICE;
+    cuuint64_t gdim[2] = {(cuuint64_t)dp, (cuuint64_t)k};
+    cuuint64_t gstride[1] = {(cuuint64_t)dp * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)nt};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(cbh), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? TVQ_OK : TVQ_ERR_BAD_ARG;
+}
+
+template <int DP, int NT, bool TRAIN>
+int launch_fwd_stream_impl(FwdParams p, const void* cbh, const DeviceInfo& di, cudaStream_t stream) {
+    auto kern = fwd_stream_kernel<DP, NT, TRAIN>;
+    const StreamPlan fixed = make_stream_plan(DP, NT, 0);
+    int stages = (di.max_smem_optin - fixed.total) / (NT * 128);
+    if (stages > kSMaxStages) stages = kSMaxStages;
+    if (stages < 2) return TVQ_ERR_UNSUPPORTED;
+    const StreamPlan pl = make_stream_plan(DP, NT, stages);
+    static int configured_smem = -1;
+    if (pl.total > configured_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total);
+        if (e != cudaSuccess) return (int)e;
+        configured_smem = pl.total;
+    }
+    CUtensorMap tm;
+    int rc = make_cb_tensor_map(&tm, cbh, p.k, DP, NT);
+    if (rc != TVQ_OK) return rc;
+    p.num_tiles = (int)((p.n + kSM - 1) / kSM);
+    int grid = p.num_tiles < di.sm_count ? p.num_tiles : di.sm_count;
+    kern<<<grid, kSThreads, pl.total, stream>>>(tm, p, stages);
+    return launch_status();
+}
+
+template <bool TRAIN>
+int dispatch_fwd_stream(const FwdParams& p, const void* cbh, const DeviceInfo& di, cudaStream_t s) {
+    switch (stream_dp(p.d)) {
+        case 64: return launch_fwd_stream_impl<64, 256, TRAIN>(p, cbh, di, s);
+        case 128: return launch_fwd_stream_impl<128, 256, TRAIN>(p, cbh, di, s);
+        case 256: return launch_fwd_stream_impl<256, 128, TRAIN>(p, cbh, di, s);
+    }
+    return TVQ_ERR_UNSUPPORTED;
+}
+
+int launch_prep(const float* cb, int k, int d, float* e2, WsHeader* hdr, float* stats, int64_t stats_len, void* cbh, int dp,
+                const DeviceInfo& di, cudaStream_t stream) {
+    int64_t work = stats_len / 4 > (int64_t)k * 32 ? stats_len / 4 : (int64_t)k * 32;
+    if (cbh && (int64_t)k * (dp / 4) > work) work = (int64_t)k * (dp / 4);
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > 4 * di.sm_count) blocks = 4 * di.sm_count;
+    if (blocks < 1) blocks = 1;
+    prep_kernel<<<blocks, 256, 0, stream>>>(cb, k, d, e2, hdr, stats, stats_len, reinterpret_cast<__nv_bfloat16*>(cbh), dp);
+    return launch_status();
+}
+
 }  // namespace
 
 extern "C" {
@@ -202,8 +271,9 @@ int tvq_device_check(int device, int* sm_count) {
 size_t tvq_workspace_bytes(int64_t n, int k, int d) {
     (void)n;
     const size_t kk = k > 0 ? (size_t)k : 0, dd = d > 0 ? (size_t)d : 0;
-    // header | |e|^2 table | private statistics scratch of tvq_train_step
-    return sizeof(WsHeader) + ((kk + 3) & ~(size_t)3) * sizeof(float) + (size_t)TVQ_STATS_LEN(kk, dd) * sizeof(float) + 64;
+    // header | |e|^2 table | private statistics scratch of tvq_train_step | bf16 codebook copy (streamed tcgen05 path)
+    if (kk == 0 || dd == 0) return sizeof(WsHeader) + 256;
+    return ws_bf16_offset((int)kk, (int)dd) + kk * (size_t)stream_dp((int)dd) * 2 + 256;
 }
 
 int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, unsigned flags,
@@ -225,14 +295,13 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
     const bool train = flags & TVQ_F_TRAIN;
     const int64_t stats_len = TVQ_STATS_LEN(k, d);
 
-    {   // per-call preparation: |e|^2, zero statistics / loss
-        int64_t work = stats_len / 4 > (int64_t)k * 32 ? stats_len / 4 : (int64_t)k * 32;
-        int blocks = (int)((work + 255) / 256);
-        if (blocks > 4 * di->sm_count) blocks = 4 * di->sm_count;
-        if (blocks < 1) blocks = 1;
-        prep_kernel<<<blocks, 256, 0, stream>>>(codebook, k, d, e2, hdr, stats, stats_len);
-        if ((rc = launch_status()) != TVQ_OK) return rc;
-    }
+    // Streamed-codebook tcgen05 path: every shape the resident-codebook path does not take.
+    const bool resident = k <= (train ? 32 : 64) && d <= 128;
+    const bool use_stream = !(flags & (TVQ_F_EXACT | TVQ_F_GIVEN_IDX | TVQ_F_NO_UMMA)) && !resident && n > 0 &&
+                            n < (int64_t(1) << 31) - 256;
+    void* cbh = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_bf16_offset(k, d) : nullptr;
+    // per-call preparation: |e|^2, zero statistics / loss (+ bf16 codebook copy)
+    if ((rc = launch_prep(codebook, k, d, e2, hdr, stats, stats_len, cbh, stream_dp(d), *di, stream)) != TVQ_OK) return rc;
     if (n == 0) return TVQ_OK;   // nothing to assign; scalars are left to the caller (reference yields NaN)
 
     FwdParams p;
@@ -254,6 +323,11 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
         p.use_hist = 1;
         p.stats_mode = train ? kStatsSmall : kStatsNone;
         return train ? dispatch_fwd_umma<true>(udp, ukp, p, *di, stream) : dispatch_fwd_umma<false>(udp, ukp, p, *di, stream);
+    }
+    if (use_stream) {
+        p.use_hist = 0;
+        p.stats_mode = train ? kStatsLarge : kStatsNone;
+        return train ? dispatch_fwd_stream<true>(p, cbh, *di, stream) : dispatch_fwd_stream<false>(p, cbh, *di, stream);
     }
     const int dp = pad_dim(d);
     p.use_hist = k <= 2048;
@@ -279,16 +353,13 @@ int tvq_train_step(const float* x, float* embed, float* cluster_size, float* emb
     if (rc != TVQ_OK) return rc;
     WsHeader* hdr = reinterpret_cast<WsHeader*>(workspace);
     float* e2 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + sizeof(WsHeader));
-    float* scratch = e2 + (((size_t)k + 3) & ~(size_t)3);     // private statistics: zero on entry, zero on exit
+    float* scratch = e2 + e2_len(k);                          // private statistics: zero on entry, zero on exit
     const bool umma = n > 0 && k <= 32 && d <= 128 && n < (int64_t(1) << 31) - 64;
+    const bool use_stream = !umma && n > 0 && n < (int64_t(1) << 31) - 256;
+    void* cbh = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_bf16_offset(k, d) : nullptr;
     if (!umma) {
-        // generic composition: zero + |e|^2, CUDA-core forward, EMA kernel (three launches)
-        const int64_t stats_len = TVQ_STATS_LEN(k, d);
-        int64_t work = stats_len / 4 > (int64_t)k * 32 ? stats_len / 4 : (int64_t)k * 32;
-        int blocks = (int)((work + 255) / 256);
-        if (blocks > 4 * di->sm_count) blocks = 4 * di->sm_count;
-        prep_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(embed, k, d, e2, hdr, scratch, stats_len);
-        if ((rc = launch_status()) != TVQ_OK) return rc;
+        // generic composition: zero + |e|^2 (+ bf16 copy), streamed tcgen05 forward, EMA kernel (three launches)
+        if ((rc = launch_prep(embed, k, d, e2, hdr, scratch, TVQ_STATS_LEN(k, d), cbh, stream_dp(d), *di, stream)) != TVQ_OK) return rc;
     }
     FwdParams p;
     p.x = x; p.cb = embed; p.n = n; p.k = k; p.d = d;
@@ -306,7 +377,11 @@ int tvq_train_step(const float* x, float* embed, float* cluster_size, float* emb
         return dispatch_fwd_umma<true>(d <= 64 ? 64 : 128, k <= 16 ? 16 : 32, p, *di, stream);
     }
     p.fuse_ema = 0;
-    if (n > 0) {
+    if (use_stream) {
+        p.use_hist = 0;
+        p.stats_mode = kStatsLarge;
+        if ((rc = dispatch_fwd_stream<true>(p, cbh, *di, stream)) != TVQ_OK) return rc;
+    } else if (n > 0) {
         const int dp = pad_dim(d);
         p.stats_mode = ((int64_t)k * dp <= 8192 && k <= 512) ? kStatsSmall : kStatsLarge;
         SmemPlan pl = make_smem_plan(dp, k, p.stats_mode, p.use_hist, kBN);

@@ -2,15 +2,19 @@
 // update, backward, de-tokenising gather, dense distance matrix and dead-code re-seed.
 // All of them are HBM- or latency-bound elementwise / gather work (no tensor cores).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "tvq_common.cuh"
 
 namespace tvq {
 
 // ------------------------------------------------------------------------------------------
 // Per-call preparation: canonical |e_k|^2 (one warp per code), zero the statistics buffer and
-// the loss / diagnostic fields of the workspace header.
+// the loss / diagnostic fields of the workspace header; optionally the bf16 copy of the codebook
+// ([k, dp] row-major, zero padded to dp columns) that the streamed tcgen05 path feeds to TMA.
 __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ cb, int k, int d, float* __restrict__ e2,
-                                                   WsHeader* hdr, float* __restrict__ stats, int64_t stats_len) {
+                                                   WsHeader* hdr, float* __restrict__ stats, int64_t stats_len,
+                                                   __nv_bfloat16* __restrict__ cbh, int dp) {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -19,11 +23,29 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ cb,
         double s = canon_dot_global(er, er, d >> 2, lane);
         if (lane == 0) e2[c] = __double2float_rn(s);
     }
+    for (int c = k + gwarp * 32 + lane; c < ((k + 255) & ~255); c += nwarps * 32) e2[c] = 1e30f;   // pad: never the minimum
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
-    float4* s4 = reinterpret_cast<float4*>(stats);
-    for (int64_t i = gtid; i < (stats_len >> 2); i += gsz) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t i = (stats_len & ~int64_t(3)) + gtid; i < stats_len; i += gsz) stats[i] = 0.f;
+    if (stats != nullptr) {
+        float4* s4 = reinterpret_cast<float4*>(stats);
+        for (int64_t i = gtid; i < (stats_len >> 2); i += gsz) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t i = (stats_len & ~int64_t(3)) + gtid; i < stats_len; i += gsz) stats[i] = 0.f;
+    }
+    if (cbh != nullptr) {
+        const int dq = dp >> 2, nchunk = d >> 2;
+        const int64_t total = (int64_t)k * dq;
+        for (int64_t f = gtid; f < total; f += gsz) {
+            const int64_t row = f / dq;
+            const int c4 = (int)(f - row * dq);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c4 < nchunk) v = __ldg(reinterpret_cast<const float4*>(cb + (size_t)row * d) + c4);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&lo);
+            o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(cbh + (size_t)row * dp + 4 * c4) = o;
+        }
+    }
     if (gtid == 0) {
         hdr->loss_sum = 0.0;
         hdr->n_rescored = 0u;

@@ -1,0 +1,701 @@
+// tvq_fwd_stream.cuh — fused VQ forward with tcgen05 scoring and a STREAMED codebook: any k, d <= 256.
+// This is the path of BASELINE configs[2] (k = 512 ... 16384, d = 64 ... 256, millions of latents),
+// where the distance computation is a real GEMM (2*k*d FLOP per latent) and, from k ~ 1000 up,
+// the tensor pipe — not HBM — is the roofline.
+//
+// Scoring runs in bf16 on the tensor cores (fp32 accumulate in tensor memory); the bf16 scores only
+// NOMINATE candidates.  The decision itself is the canonical fp32/fp64 rule shared by every path
+// (oracle/vq_canon.c): a code can be the canonical arg-min only if its bf16
+// score lies within a rigorous error bound of the best bf16 score, so those codes (1.2 ... 1.8 per
+// row on Gaussian data) are re-scored in fp32 and, if still inseparable, in fp64.  Indices are
+// therefore bit-identical to the CUDA-core path and to the C oracle.
+//
+// One persistent CTA per SM, 10 warps, warp-specialised; a row tile is 128 latents (UMMA M = 128:
+// TMEM lane = latent), a code tile is NT codes (one tcgen05.mma N), d is cut into 64-column slabs:
+//   warp 0      producer: TMA (cp.async.bulk.tensor, SWIZZLE_128B) of bf16 code slabs [NT x 64]
+//               into a ring of shared-memory stages; also stages the |e|^2 slice of each code tile
+//   warp 1      MMA issuer: per code tile d/16 tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32, M = 128,
+//               N = NT) into one of 512/NT tensor-memory score slots; tcgen05.commit
+//   warps 2-5   scan + apply, one warp per TMEM lane quadrant, ONE THREAD PER LATENT: tcgen05.ld of 32
+//               scores at a time, score = |e|^2 - 2 x.e (packed FFMA2), 3-input-min tree, running
+//               minimum m and threshold m + bound; a 32-score chunk is looked at again only if its
+//               minimum beats the threshold (rare after the first chunks), and then its candidates go
+//               to a small per-latent list in shared memory.  After the last code tile the warp
+//               resolves its 32 latents (cascade above), gathers the code words, writes idx / q
+//               (straight-through) / loss partial and adds the EMA statistics (red.global.v4).
+//   warps 6-9   converters: x rows fp32 (global, L2-prefetched two tiles ahead) -> bf16 A operand in
+//               UMMA K-major SWIZZLE_128B layout, double buffered; also |x| -> the row's error bound.
+// Algorithmic cost per latent: 8d + 8 bytes of HBM (x is re-read once from L2 by the apply phase),
+// 2*k*d tensor FLOP.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "tvq_common.cuh"
+#include "tvq_fwd_simt.cuh"
+#include "tvq_sm100.cuh"
+
+namespace tvq {
+
+constexpr int kSM = 128;                 // latents per row tile
+constexpr int kSThreads = 320;           // 10 warps
+constexpr int kSCand = 16;               // candidate slots per latent
+constexpr int kSESlots = 8;              // |e|^2 slices in flight
+constexpr int kSBrowRing = 4;            // row-bound buffers (converter runs up to 2 tiles ahead of the scan)
+constexpr int kSMaxStages = 8;
+
+struct StreamPlan {
+    int stages, stage_bytes, a_bytes;
+    int a, b, e2s, brow, cs, cc, drop, red, misc, bars, tmem, total;
+};
+__host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages) {
+    StreamPlan u;
+    u.stages = stages;
+    u.stage_bytes = nt * 128;            // NT codes x 64 bf16
+    u.a_bytes = kSM * dp * 2;
+    int o = 0;
+    u.a = o;     o += 2 * u.a_bytes;
+    u.b = o;     o += stages * u.stage_bytes;
+    u.e2s = o;   o += kSESlots * nt * 4;
+    u.brow = o;  o += kSBrowRing * kSM * 4;
+    u.cs = o;    o += kSCand * kSM * 4;
+    u.cc = o;    o += kSCand * kSM * 4;
+    u.drop = o;  o += kSM * 4;
+    u.red = o;   o += 32 * 8;
+    u.misc = o;  o += 16 * 4;
+    u.bars = o;  o += (2 * kSMaxStages + 4 + 8 + 2 * kSESlots + 2 * kSBrowRing) * 8;
+    u.tmem = o;  o += 16;
+    u.total = o;
+    return u;
+}
+
+namespace sm100 {
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    // kind::f16: c_format [4,6) = 1 (fp32), a_format [7,10) = 1 (bf16), b_format [10,13) = 1 (bf16), K-major both
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32-bit, 32 consecutive columns per thread.
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// 1-D bulk copy global -> shared (multiple of 16 bytes), completion (bytes) on an mbarrier.
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+// (d0, d1) = (a0, a1) * (b0, b1) + (c0, c1) in one FFMA2
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    uint64_t a, b, c, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float m;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
+    return m;
+}
+__device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+}  // namespace sm100
+
+// Append (score, code) to a latent's candidate list (slots are kSM words apart so that the 32
+// latents of a warp never collide on a bank).  A full list is first compacted against the current
+// threshold (which only ever decreases); if it is still full the WORST entry is dropped and the
+// smallest dropped score remembered: at the end of the scan the list is complete iff that score
+// lies above the final threshold (otherwise the latent takes the exhaustive scan).
+__device__ __noinline__ int cand_append(const float s, const int code, int cnt, const float thr, float* ls, int* lc, float* dropp) {
+    if (cnt == kSCand) {
+        int kept = 0;
+        for (int i = 0; i < kSCand; ++i) {
+            const float v = ls[i * kSM];
+            const int c = lc[i * kSM];
+            if (v <= thr) { ls[kept * kSM] = v; lc[kept * kSM] = c; ++kept; }
+        }
+        cnt = kept;
+        if (cnt == kSCand) {
+            int imax = 0;
+            float vmax = ls[0];
+            for (int i = 1; i < kSCand; ++i) {
+                const float v = ls[i * kSM];
+                if (v > vmax) { vmax = v; imax = i; }
+            }
+            if (s >= vmax) { *dropp = fminf(*dropp, s); return cnt; }
+            *dropp = fminf(*dropp, vmax);
+            ls[imax * kSM] = s;
+            lc[imax * kSM] = code;
+            return cnt;
+        }
+    }
+    ls[cnt * kSM] = s;
+    lc[cnt * kSM] = code;
+    return cnt + 1;
+}
+
+// One chunk of 32 scores of ONE latent (this thread's TMEM lane).
+__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const float4* e2c, const int code0, const float brow,
+                                           float& m, int& cnt, float* ls, int* lc, float* dropp) {
+    using namespace sm100;
+    float s[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 e = e2c[i];     // the same address for every lane: shared-memory broadcast
+        fma2(s[4 * i], s[4 * i + 1], __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), -2.f, -2.f, e.x, e.y);
+        fma2(s[4 * i + 2], s[4 * i + 3], __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]), -2.f, -2.f, e.z, e.w);
+    }
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = fminf(fmin3(s[4 * i], s[4 * i + 1], s[4 * i + 2]), s[4 * i + 3]);
+    const float cmin = fmin3(fmin3(g[0], g[1], g[2]), fmin3(g[3], g[4], g[5]), fminf(g[6], g[7]));
+    m = fminf(m, cmin);
+    const float thr = m + brow;
+    if (cmin <= thr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (g[i] <= thr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (s[4 * i + j] <= thr) cnt = cand_append(s[4 * i + j], code0 + 4 * i + j, cnt, thr, ls, lc, dropp);
+            }
+        }
+    }
+}
+
+// fp32 dot of the lane's x chunks with code word `code`, partial (before the butterfly)
+template <int NV>
+__device__ __forceinline__ float dot32_part(const float4 x0, const float4 x1, const float* cb, const int code, const int d,
+                                            const bool h0, const bool h1, const int lane) {
+    const float4* er = reinterpret_cast<const float4*>(cb + (size_t)code * d);
+    float dd = 0.f;
+    if (h0) { const float4 e = __ldg(er + lane); dd = fmaf(x0.x, e.x, fmaf(x0.y, e.y, fmaf(x0.z, e.z, x0.w * e.w))); }
+    if (NV > 1 && h1) { const float4 e = __ldg(er + lane + 32); dd = fmaf(x1.x, e.x, fmaf(x1.y, e.y, fmaf(x1.z, e.z, fmaf(x1.w, e.w, dd)))); }
+    return dd;
+}
+
+// General (rare) resolution of one latent: from its candidate list (nc > 4) or from ALL codes
+// (nc <= 0: the list overflowed or held non-finite scores).  fp32 re-score four codes at a time, then
+// the canonical fp64 rule over the same set if the fp32 scores cannot separate the two best.
+// All 32 lanes work on the one latent; lane l holds the 16-byte chunks l (x0) and l + 32 (x1) of x.
+// Returns the canonical arg-min, | 1 << 30 if the fp64 level was needed.
+template <int NV>
+__device__ __noinline__ int resolve_stream(const float4 x0, const float4 x1, const int nc, const int* lc, const float* cb,
+                                           const float* e2g, const int k, const int d, const float emax, const int lane) {
+    const int nchunk = d >> 2;
+    const bool h0 = lane < nchunk, h1 = NV > 1 && lane + 32 < nchunk;
+    const float INF = __int_as_float(0x7f800000);
+    float ss = fmaf(x0.x, x0.x, fmaf(x0.y, x0.y, fmaf(x0.z, x0.z, x0.w * x0.w)));
+    if (NV > 1) ss = fmaf(x1.x, x1.x, fmaf(x1.y, x1.y, fmaf(x1.z, x1.z, fmaf(x1.w, x1.w, ss))));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const float bnd = fmaf(sqrtf(ss), 1.0001f, emax);
+    const float thr32 = 1.6e-6f * bnd * bnd;
+    const int count = nc > 0 ? nc : k;
+    float m1 = INF, m2 = INF;
+    int i1 = 0;
+    for (int j0 = 0; j0 < count; j0 += 4) {
+        int code[4];
+        float dd[4], e2v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int j = j0 + t < count ? j0 + t : count - 1;
+            int c = nc > 0 ? lc[j * kSM] : j;
+            c = (c >= 0 && c < k) ? c : 0;
+            code[t] = c;
+            dd[t] = dot32_part<NV>(x0, x1, cb, c, d, h0, h1, lane);
+            e2v[t] = __ldg(e2g + c);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) dd[t] += __shfl_xor_sync(0xffffffffu, dd[t], off);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (j0 + t >= count) break;
+            const float sv = fmaf(-2.f, dd[t], e2v[t]);
+            if (sv < m1) { m2 = m1; m1 = sv; i1 = code[t]; }
+            else if (sv < m2) m2 = sv;
+        }
+    }
+    if (m2 - m1 > thr32) return i1;                       // NaN compares false: falls through to fp64
+    double pp = 0.0;
+    if (h0) pp = dot4(pp, x0, x0);
+    if (h1) pp = dot4(pp, x1, x1);
+    const float x2 = __double2float_rn(butterfly_sum(pp));
+    float best = INF;
+    int arg = 0x7fffffff;
+    for (int j = 0; j < count; ++j) {
+        int code = nc > 0 ? lc[j * kSM] : j;
+        code = (code >= 0 && code < k) ? code : 0;
+        const float4* er = reinterpret_cast<const float4*>(cb + (size_t)code * d);
+        double sd = 0.0;
+        if (h0) sd = dot4(sd, x0, __ldg(er + lane));
+        if (h1) sd = dot4(sd, x1, __ldg(er + lane + 32));
+        const float dk = canon_score(x2, butterfly_sum(sd), __ldg(e2g + code));
+        if (dk < best || (dk == best && code < arg)) { best = dk; arg = code; }
+    }
+    if (arg == 0x7fffffff) arg = 0;                       // non-finite row: any valid code
+    return arg | (1 << 30);
+}
+
+template <int DP, int NT, bool TRAIN>
+__global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_cb, const FwdParams p,
+                                                                 const int stages) {
+    using namespace sm100;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int KSLABS = DP / 64;             // 64-column (128-byte) bf16 slabs per row
+    constexpr int SLOTS = 512 / NT;             // tensor-memory score slots
+    constexpr int NCHUNK32 = NT / 32;           // 32-score chunks per code tile
+    constexpr int F = DP / 4;                   // 16-byte fp32 chunks per padded row
+    constexpr int NV = DP > 128 ? 2 : 1;        // 16-byte chunks per lane in the warp-per-latent phases
+    constexpr int A_SLAB = kSM * 128;           // bytes of one A slab (128 rows x 128 bytes)
+    static_assert(DP == 64 || DP == 128 || DP == 256, "d padded to 64, 128 or 256");
+    static_assert(NT == 128 || NT == 256, "code tile of 128 or 256");
+
+    const StreamPlan pl = make_stream_plan(DP, NT, stages);
+    float* e2s = reinterpret_cast<float*>(smem + pl.e2s);
+    float* brow_ring = reinterpret_cast<float*>(smem + pl.brow);
+    float* cand_s = reinterpret_cast<float*>(smem + pl.cs);
+    int* cand_c = reinterpret_cast<int*>(smem + pl.cc);
+    double* red = reinterpret_cast<double*>(smem + pl.red);
+    int* misc = reinterpret_cast<int*>(smem + pl.misc);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.tmem);
+    const uint32_t bar0 = smem_u32(smem + pl.bars);
+    const uint32_t bar_bfull = bar0, bar_bempty = bar_bfull + 8 * kSMaxStages;
+    const uint32_t bar_afull = bar_bempty + 8 * kSMaxStages, bar_aempty = bar_afull + 16;
+    const uint32_t bar_tfull = bar_aempty + 16, bar_tempty = bar_tfull + 32;
+    const uint32_t bar_efull = bar_tempty + 32, bar_eempty = bar_efull + 8 * kSESlots;
+    const uint32_t bar_rfull = bar_eempty + 8 * kSESlots, bar_rempty = bar_rfull + 8 * kSBrowRing;
+    const uint32_t a_base = smem_u32(smem + pl.a), b_base = smem_u32(smem + pl.b);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunk = p.d >> 2;
+    const int n_ct = (p.k + NT - 1) / NT;                 // code tiles
+    const int num_tiles = p.num_tiles;                    // row tiles of 128 latents
+
+    // ------------------------------------------------------------------ CTA prologue
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    if (tid == 0) {
+        for (int s = 0; s < kSMaxStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
+        for (int s = 0; s < kSESlots; ++s) { mbar_init(bar_efull + 8 * s, 1); mbar_init(bar_eempty + 8 * s, 4); }
+        for (int s = 0; s < kSBrowRing; ++s) { mbar_init(bar_rfull + 8 * s, 4); mbar_init(bar_rempty + 8 * s, 4); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_cb);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    // max |e| (error-bound constant): every CTA scans the |e|^2 table (k floats, L2 resident)
+    float emax2 = 0.f;
+    for (int c = tid; c < p.k; c += kSThreads) emax2 = fmaxf(emax2, __ldg(p.e2 + c));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) emax2 = fmaxf(emax2, __shfl_xor_sync(0xffffffffu, emax2, off));
+    float* wmax = reinterpret_cast<float*>(red);
+    if (lane == 0) wmax[warp] = emax2;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    emax2 = 0.f;
+    for (int w = 0; w < kSThreads / 32; ++w) emax2 = fmaxf(emax2, wmax[w]);
+    const float emax = sqrtf(emax2) * 1.0001f;
+    __syncthreads();                                      // wmax (aliases red) is free again
+
+    double loss_d = 0.0;
+    unsigned n_resc = 0, n_f64 = 0;
+
+    if (warp == 0) {
+        // ============================================================ producer: code slabs (TMA) + |e|^2 slices
+        // (the |e|^2 table in the workspace is padded with BIG to a multiple of 256, so every slice is a
+        //  plain NT*4-byte bulk copy and codes >= k can never be nominated)
+        if (lane == 0) {
+            int ib = 0, et = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int ct = 0; ct < n_ct; ++ct, ++et) {
+                    const int es = et % kSESlots;
+                    mbar_wait(bar_eempty + 8 * es, (((uint32_t)(et / kSESlots)) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(bar_efull + 8 * es, (uint32_t)(NT * 4));
+                    bulk_load_1d(smem_u32(e2s + es * NT), p.e2 + (size_t)ct * NT, (uint32_t)(NT * 4), bar_efull + 8 * es);
+                    for (int j = 0; j < KSLABS; ++j, ++ib) {
+                        const int s = ib % stages;
+                        mbar_wait(bar_bempty + 8 * s, (((uint32_t)(ib / stages)) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(bar_bfull + 8 * s, (uint32_t)(NT * 128));
+                        tma_load_2d(b_base + s * pl.stage_bytes, &tmap_cb, bar_bfull + 8 * s, j * 64, ct * NT);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================================================ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kSM, NT);
+            int ib = 0, tt = 0, it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int ab = it & 1;
+                mbar_wait(bar_afull + 8 * ab, ((uint32_t)(it >> 1)) & 1u);
+                tc_fence_after();
+                const uint32_t a0 = a_base + ab * pl.a_bytes;
+                for (int ct = 0; ct < n_ct; ++ct, ++tt) {
+                    const int slot = tt % SLOTS;
+                    mbar_wait(bar_tempty + 8 * slot, (((uint32_t)(tt / SLOTS)) & 1u) ^ 1u);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int j = 0; j < KSLABS; ++j, ++ib) {
+                        const int s = ib % stages;
+                        mbar_wait(bar_bfull + 8 * s, ((uint32_t)(ib / stages)) & 1u);
+                        tc_fence_after();
+                        const uint32_t b0 = b_base + s * pl.stage_bytes;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
+                                      umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
+                        umma_commit(bar_bempty + 8 * s);       // stage free once these MMAs have read it
+                    }
+                    umma_commit(bar_tfull + 8 * slot);         // scores of this code tile complete
+                }
+                umma_commit(bar_aempty + 8 * ab);              // A buffer free once every MMA of the row tile is done
+            }
+        }
+    } else if (warp >= 6) {
+        // ============================================================ converters: x fp32 -> bf16 A operand, |x| -> bound
+        const int cw = warp - 6;
+        const int rowbase = cw * 32;                          // this warp's 32 latents of the tile
+        constexpr int U = 8;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const int64_t row0 = (int64_t)tile * kSM;
+            if (cw == 0 && lane == 0) {                       // L2 prefetch of the tile two iterations ahead
+                const int64_t t2 = (int64_t)tile + 2 * (int64_t)gridDim.x;
+                if (t2 < num_tiles) {
+                    const int64_t r2 = t2 * kSM;
+                    const int64_t rows = (p.n - r2) < kSM ? (p.n - r2) : kSM;
+                    prefetch_l2_bulk(p.x + (size_t)r2 * p.d, (uint32_t)(rows * p.d * 4));
+                }
+            }
+            const int rs = it & (kSBrowRing - 1);
+            mbar_wait(bar_aempty + 8 * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+            mbar_wait(bar_rempty + 8 * rs, (((uint32_t)(it / kSBrowRing)) & 1u) ^ 1u);
+            const uint32_t a0 = a_base + ab * pl.a_bytes;
+            float* brow = brow_ring + rs * kSM;
+#pragma unroll 1
+            for (int i0 = 0; i0 < F; i0 += U) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int f = (i0 + u) * 32 + lane;
+                    const int row = rowbase + f / F, c4 = f % F;
+                    const int64_t grow = row0 + row;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (grow < p.n && c4 < nchunk) v[u] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)grow * p.d) + c4);
+                }
+                float ssq[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int f = (i0 + u) * 32 + lane;
+                    const int row = rowbase + f / F, c4 = f % F;
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y);
+                    const __nv_bfloat162 hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+                    // element column 4*c4: slab c4/16, 16-byte chunk (c4 % 16) / 2 (XOR row & 7), half c4 & 1
+                    const uint32_t addr = a0 + (uint32_t)(c4 >> 4) * A_SLAB + (uint32_t)row * 128u +
+                                          ((((uint32_t)(c4 & 15) >> 1) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)(c4 & 1) << 3);
+                    sts_v2(addr, *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                    ssq[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
+                }
+                // row norms -> bound of |(s_a - s_b) - (d_a - d_b)| for this latent
+                if constexpr (F == 64) {
+#pragma unroll
+                    for (int u = 0; u < U; u += 2) {
+                        float t = ssq[u] + ssq[u + 1];
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                        if (lane == 0) {
+                            const float xn = sqrtf(t) * 1.0001f, sum = xn + emax;
+                            brow[rowbase + (i0 + u) / 2] = fmaf(0.0172f * xn, emax, 2e-6f * sum * sum);
+                        }
+                    }
+                } else if constexpr (F == 32) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        float t = ssq[u];
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                        if (lane == 0) {
+                            const float xn = sqrtf(t) * 1.0001f, sum = xn + emax;
+                            brow[rowbase + i0 + u] = fmaf(0.0172f * xn, emax, 2e-6f * sum * sum);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        float t = ssq[u];
+#pragma unroll
+                        for (int off = 8; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                        if ((lane & 15) == 0) {
+                            const float xn = sqrtf(t) * 1.0001f, sum = xn + emax;
+                            brow[rowbase + 2 * (i0 + u) + (lane >> 4)] = fmaf(0.0172f * xn, emax, 2e-6f * sum * sum);
+                        }
+                    }
+                }
+            }
+            fence_proxy_async_smem();                         // generic-proxy stores -> visible to tcgen05.mma
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar_afull + 8 * ab); mbar_arrive(bar_rfull + 8 * rs); }
+        }
+    } else {
+        // ============================================================ scan + apply warps (one thread per latent)
+        const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int trow = quad * 32 + lane;                    // this thread's latent within the tile
+        float* ls = cand_s + trow;
+        int* lc = cand_c + trow;
+        float* dropp = reinterpret_cast<float*>(smem + pl.drop) + trow;
+        float* esum = p.stats + ((p.k + 3) & ~3);
+        const bool h0 = lane < nchunk, h1 = NV > 1 && lane + 32 < nchunk;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float INF = __int_as_float(0x7f800000);
+        constexpr int R = NV > 1 ? 2 : 4;                     // latents in flight in the apply phase
+        int et = 0, it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int rs = it & (kSBrowRing - 1);
+            mbar_wait(bar_rfull + 8 * rs, ((uint32_t)(it / kSBrowRing)) & 1u);     // the row bounds are written
+            const float brow = brow_ring[rs * kSM + trow];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);
+            float m = INF;
+            int cnt = 0;
+            *dropp = INF;
+            // ---- scan: all code tiles of this row tile
+            for (int ct = 0; ct < n_ct; ++ct, ++et) {
+                const int slot = et % SLOTS, es = et % kSESlots;
+                mbar_wait(bar_efull + 8 * es, ((uint32_t)(et / kSESlots)) & 1u);
+                mbar_wait(bar_tfull + 8 * slot, ((uint32_t)(et / SLOTS)) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + (uint32_t)(slot * NT);
+                const float4* e2c = reinterpret_cast<const float4*>(e2s + es * NT);
+                const int code0 = ct * NT;
+                uint32_t ra[32], rb[32];
+                tmem_ld_x32(taddr, ra);
+#pragma unroll 1
+                for (int c = 0; c < NCHUNK32; c += 2) {
+                    tmem_ld_wait();
+                    tmem_ld_x32(taddr + (uint32_t)(c + 1) * 32u, rb);
+                    scan_chunk(ra, e2c + c * 8, code0 + c * 32, brow, m, cnt, ls, lc, dropp);
+                    tmem_ld_wait();
+                    if (c + 2 < NCHUNK32) tmem_ld_x32(taddr + (uint32_t)(c + 2) * 32u, ra);
+                    scan_chunk(rb, e2c + (c + 1) * 8, code0 + (c + 1) * 32, brow, m, cnt, ls, lc, dropp);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar_tempty + 8 * slot); mbar_arrive(bar_eempty + 8 * es); }
+            }
+            // ---- final candidate set of this thread's latent: scores within the bound of the minimum
+            int ncand = -1;
+            {
+                const float thr = m + brow;
+                int kept = 0;
+                for (int i = 0; i < cnt; ++i) {
+                    const float v = ls[i * kSM];
+                    if (v <= thr) { lc[kept * kSM] = lc[i * kSM]; ++kept; }
+                }
+                if (kept > 0 && *dropp > thr) ncand = kept;   // else: non-finite scores or a truly overflowed list
+            }
+            __syncwarp();
+            // ---- resolve + apply: all 32 lanes on one latent, R latents in flight, ONE round trip to L2:
+            //      x rows, the first candidate's code word and (for ambiguous latents) candidates 2-4 are
+            //      all requested before anything is used
+            const int64_t wrow0 = (int64_t)tile * kSM + quad * 32;
+            int mycode = 0;
+            float loss = 0.f;
+#pragma unroll 1
+            for (int b = 0; b < 32 / R; ++b) {
+                if (wrow0 + R * b >= p.n) break;              // warp-uniform
+                float4 xa[R], xb[R], ea[R][4], eb[R][4];
+                float e2v[R][4];
+                int nc[R], cc[R][4];
+                bool valid[R];
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    const int64_t grow = wrow0 + R * b + u;
+                    valid[u] = grow < p.n;
+                    nc[u] = __shfl_sync(0xffffffffu, ncand, R * b + u);
+                    const int* lcr = cand_c + quad * 32 + R * b + u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        int c = lcr[(j < nc[u] ? j : 0) * kSM];
+                        cc[u][j] = (c >= 0 && c < p.k) ? c : 0;
+                    }
+                    const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)(valid[u] ? grow : 0) * p.d);
+                    xa[u] = (valid[u] && h0) ? __ldg(xr + lane) : z4;
+                    xb[u] = (valid[u] && h1) ? __ldg(xr + lane + 32) : z4;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        ea[u][j] = z4; eb[u][j] = z4; e2v[u][j] = 0.f;
+                        if (j == 0 || (j < nc[u] && nc[u] <= 4)) {
+                            const float4* er = reinterpret_cast<const float4*>(p.cb + (size_t)cc[u][j] * p.d);
+                            if (h0) ea[u][j] = __ldg(er + lane);
+                            if (h1) eb[u][j] = __ldg(er + lane + 32);
+                            if (nc[u] >= 2) e2v[u][j] = __ldg(p.e2 + cc[u][j]);
+                        }
+                    }
+                }
+                int cd[R];
+                float4 wa[R], wb[R];
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    int sel = 0;
+                    cd[u] = cc[u][0];
+                    if (valid[u] && nc[u] >= 2 && nc[u] <= 4) {
+                        // fp32 re-score of the (<= 4) candidates, all lanes on this latent
+                        n_resc += 1u;
+                        float dd[4];
+                        float ss = fmaf(xa[u].x, xa[u].x, fmaf(xa[u].y, xa[u].y, fmaf(xa[u].z, xa[u].z, xa[u].w * xa[u].w)));
+                        if (NV > 1) ss = fmaf(xb[u].x, xb[u].x, fmaf(xb[u].y, xb[u].y, fmaf(xb[u].z, xb[u].z, fmaf(xb[u].w, xb[u].w, ss))));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            dd[j] = fmaf(xa[u].x, ea[u][j].x, fmaf(xa[u].y, ea[u][j].y, fmaf(xa[u].z, ea[u][j].z, xa[u].w * ea[u][j].w)));
+                            if (NV > 1) dd[j] = fmaf(xb[u].x, eb[u][j].x, fmaf(xb[u].y, eb[u][j].y, fmaf(xb[u].z, eb[u][j].z, fmaf(xb[u].w, eb[u][j].w, dd[j]))));
+                        }
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            ss += __shfl_xor_sync(0xffffffffu, ss, off);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], off);
+                        }
+                        const float bnd = fmaf(sqrtf(ss), 1.0001f, emax);
+                        const float thr32 = 1.6e-6f * bnd * bnd;
+                        float m1 = INF, m2 = INF;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float sv = j < nc[u] ? fmaf(-2.f, dd[j], e2v[u][j]) : INF;
+                            if (sv < m1) { m2 = m1; m1 = sv; sel = j; }
+                            else if (sv < m2) m2 = sv;
+                        }
+                        if (!(m2 - m1 > thr32)) {
+                            // canonical fp64 rule among the candidates (code words already in registers)
+                            n_f64 += 1u;
+                            double pp = 0.0;
+                            if (h0) pp = dot4(pp, xa[u], xa[u]);
+                            if (h1) pp = dot4(pp, xb[u], xb[u]);
+                            const float x2 = __double2float_rn(butterfly_sum(pp));
+                            float best = INF;
+                            int arg = 0x7fffffff;
+                            sel = 0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (j < nc[u]) {
+                                    double sd = 0.0;
+                                    if (h0) sd = dot4(sd, xa[u], ea[u][j]);
+                                    if (h1) sd = dot4(sd, xb[u], eb[u][j]);
+                                    const float dk = canon_score(x2, butterfly_sum(sd), e2v[u][j]);
+                                    if (dk < best || (dk == best && cc[u][j] < arg)) { best = dk; arg = cc[u][j]; sel = j; }
+                                }
+                            }
+                        }
+                        cd[u] = sel == 0 ? cc[u][0] : sel == 1 ? cc[u][1] : sel == 2 ? cc[u][2] : cc[u][3];
+                    }
+                    wa[u] = sel == 0 ? ea[u][0] : sel == 1 ? ea[u][1] : sel == 2 ? ea[u][2] : ea[u][3];
+                    wb[u] = sel == 0 ? eb[u][0] : sel == 1 ? eb[u][1] : sel == 2 ? eb[u][2] : eb[u][3];
+                    if (valid[u] && (nc[u] < 1 || nc[u] > 4)) {
+                        // rare: long candidate list or exhaustive scan, then a second trip for the code word
+                        const int r = resolve_stream<NV>(xa[u], xb[u], nc[u], cand_c + quad * 32 + R * b + u, p.cb, p.e2, p.k, p.d,
+                                                         emax, lane);
+                        n_resc += 1u;
+                        n_f64 += (unsigned)(r >> 30);
+                        int code = r & 0x3fffffff;
+                        code = code < p.k ? code : 0;
+                        cd[u] = code;
+                        const float4* er = reinterpret_cast<const float4*>(p.cb + (size_t)code * p.d);
+                        wa[u] = h0 ? __ldg(er + lane) : z4;
+                        wb[u] = h1 ? __ldg(er + lane + 32) : z4;
+                    }
+                }
+                if (p.q != nullptr || TRAIN) {
+#pragma unroll
+                    for (int u = 0; u < R; ++u) {
+                        if (!valid[u]) continue;
+                        const int64_t grow = wrow0 + R * b + u;
+                        float4 oa = wa[u], ob = wb[u];
+                        if (TRAIN) {
+                            // x + (e - x): two rounded fp32 ops, never contracted; the loss is taken on
+                            // that rounded tensor, as F.mse_loss(quantize.detach(), x) does
+                            oa.x = __fadd_rn(xa[u].x, __fsub_rn(wa[u].x, xa[u].x));
+                            oa.y = __fadd_rn(xa[u].y, __fsub_rn(wa[u].y, xa[u].y));
+                            oa.z = __fadd_rn(xa[u].z, __fsub_rn(wa[u].z, xa[u].z));
+                            oa.w = __fadd_rn(xa[u].w, __fsub_rn(wa[u].w, xa[u].w));
+                            const float dx = __fsub_rn(oa.x, xa[u].x), dy = __fsub_rn(oa.y, xa[u].y);
+                            const float dz = __fsub_rn(oa.z, xa[u].z), dw = __fsub_rn(oa.w, xa[u].w);
+                            loss = fmaf(dx, dx, loss); loss = fmaf(dy, dy, loss);
+                            loss = fmaf(dz, dz, loss); loss = fmaf(dw, dw, loss);
+                            if (NV > 1) {
+                                ob.x = __fadd_rn(xb[u].x, __fsub_rn(wb[u].x, xb[u].x));
+                                ob.y = __fadd_rn(xb[u].y, __fsub_rn(wb[u].y, xb[u].y));
+                                ob.z = __fadd_rn(xb[u].z, __fsub_rn(wb[u].z, xb[u].z));
+                                ob.w = __fadd_rn(xb[u].w, __fsub_rn(wb[u].w, xb[u].w));
+                                const float ex = __fsub_rn(ob.x, xb[u].x), ey = __fsub_rn(ob.y, xb[u].y);
+                                const float ez = __fsub_rn(ob.z, xb[u].z), ew = __fsub_rn(ob.w, xb[u].w);
+                                loss = fmaf(ex, ex, loss); loss = fmaf(ey, ey, loss);
+                                loss = fmaf(ez, ez, loss); loss = fmaf(ew, ew, loss);
+                            }
+                            float* es_row = esum + (size_t)cd[u] * p.d;
+                            if (h0) red_add_v4(es_row + 4 * lane, xa[u]);
+                            if (h1) red_add_v4(es_row + 4 * (lane + 32), xb[u]);
+                        }
+                        if (p.q != nullptr) {
+                            float* qr = p.q + (size_t)grow * p.d;
+                            if (h0) st_stream_v4(qr + 4 * lane, oa);
+                            if (h1) st_stream_v4(qr + 4 * (lane + 32), ob);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < R; ++u) mycode = (lane == R * b + u) ? cd[u] : mycode;
+            }
+            if (wrow0 + lane < p.n) {
+                p.idx[wrow0 + lane] = (int64_t)mycode;
+                atomicAdd(p.stats + mycode, 1.0f);            // counts (exact integers in fp32)
+            }
+            loss_d += (double)loss;
+            __syncwarp();                                     // candidate lists are reused by the next row tile
+        }
+    }
+
+    // ------------------------------------------------------------------ teardown
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (lane == 0 && n_resc) {
+        atomicAdd(&p.hdr->n_rescored, n_resc);
+        if (n_f64) atomicAdd(&p.hdr->n_exact, n_f64);
+    }
+    if (TRAIN) {
+        const double t = block_sum(loss_d, red);
+        if (tid == 0) atomicAdd(&p.hdr->loss_sum, t);
+    }
+    finish_ticket<TRAIN>(p, red, misc);
+}
+
+}  // namespace tvq

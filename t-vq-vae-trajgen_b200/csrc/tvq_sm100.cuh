@@ -30,15 +30,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "r"(bar), "r"(parity), "r"(1000000u)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must become an error (trap -> sticky CUDA error), never a hung GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait: a protocol bug must become an error (trap -> sticky CUDA error) within seconds,
+// never a hung GPU.  The bound is wall time (4 s), far above any legitimate wait of these kernels.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-        if (spin > (1u << 22)) __trap();
+    const uint64_t t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (globaltimer_ns() - t0 > 4000000000ull) __trap();
     }
 }
 
