@@ -234,6 +234,11 @@ int launch_prep(const float* cb, int k, int d, float* e2, WsHeader* hdr, float* 
 
 extern "C" {
 
+#ifdef TVQ_STREAM_PROF
+__attribute__((visibility("default"))) int tvq_debug_stream_prof(unsigned long long* out64) {
+    return (int)cudaMemcpyFromSymbol(out64, g_sprof, sizeof(unsigned long long) * 128);
+}
+#endif
 #ifdef TVQ_PROFILE_PHASES
 __attribute__((visibility("default"))) int tvq_debug_phases(unsigned long long* out32) {
     return (int)cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(unsigned long long) * 32);

@@ -10,20 +10,21 @@
 // row on Gaussian data) are re-scored in fp32 and, if still inseparable, in fp64.  Indices are
 // therefore bit-identical to the CUDA-core path and to the C oracle.
 //
-// One persistent CTA per SM, 10 warps, warp-specialised; a row tile is 128 latents (UMMA M = 128:
+// One persistent CTA per SM, 14 warps, warp-specialised; a row tile is 128 latents (UMMA M = 128:
 // TMEM lane = latent), a code tile is NT codes (one tcgen05.mma N), d is cut into 64-column slabs:
 //   warp 0      producer: TMA (cp.async.bulk.tensor, SWIZZLE_128B) of bf16 code slabs [NT x 64]
 //               into a ring of shared-memory stages; also stages the |e|^2 slice of each code tile
 //   warp 1      MMA issuer: per code tile d/16 tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32, M = 128,
 //               N = NT) into one of 512/NT tensor-memory score slots; tcgen05.commit
-//   warps 2-5   scan + apply, one warp per TMEM lane quadrant, ONE THREAD PER LATENT: tcgen05.ld of 32
-//               scores at a time, score = |e|^2 - 2 x.e (packed FFMA2), 3-input-min tree, running
-//               minimum m and threshold m + bound; a 32-score chunk is looked at again only if its
-//               minimum beats the threshold (rare after the first chunks), and then its candidates go
-//               to a small per-latent list in shared memory.  After the last code tile the warp
-//               resolves its 32 latents (cascade above), gathers the code words, writes idx / q
+//   warps 2-9   scan + apply, TWO warps per TMEM lane quadrant (each takes half of the columns of every
+//               code tile), ONE THREAD PER LATENT: tcgen05.ld of 32 scores at a time, score =
+//               |e|^2 - 2 x.e (packed FFMA2), 3-input-min tree, running minimum m and threshold
+//               m + bound; a 32-score chunk is looked at again only if its minimum beats the threshold
+//               (rare after the first chunks), and then its candidates go to a small per-latent list in
+//               shared memory.  After the last code tile the two warps of a quadrant merge their minima,
+//               and each resolves 16 latents (cascade above), gathers the code words, writes idx / q
 //               (straight-through) / loss partial and adds the EMA statistics (red.global.v4).
-//   warps 6-9   converters: x rows fp32 (global, L2-prefetched two tiles ahead) -> bf16 A operand in
+//   warps 10-13 converters: x rows fp32 (global, L2-prefetched two tiles ahead) -> bf16 A operand in
 //               UMMA K-major SWIZZLE_128B layout, double buffered; also |x| -> the row's error bound.
 // Algorithmic cost per latent: 8d + 8 bytes of HBM (x is re-read once from L2 by the apply phase),
 // 2*k*d tensor FLOP.
@@ -37,16 +38,35 @@
 
 namespace tvq {
 
+#ifdef TVQ_STREAM_PROF
+// Experiment build only (tools/profile_stream.py): CTA 0's per-role wait / work clock totals.
+__device__ unsigned long long g_sprof[128];
+#define SP_DECL long long sp[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long sp_t = clock64(); (void)sp_t
+#define SP_WAIT(i, bar, par) do { long long _t = clock64(); mbar_wait(bar, par); sp[i] += clock64() - _t; } while (0)
+#define SP_LAP(i) do { long long _t = clock64(); sp[i] += _t - sp_t; sp_t = _t; } while (0)
+#define SP_RESET() do { sp_t = clock64(); } while (0)
+#define SP_DUMP(base) do { if (blockIdx.x == 0) for (int _i = 0; _i < 8; ++_i) g_sprof[(base) + _i] = (unsigned long long)sp[_i]; } while (0)
+#else
+#define SP_DECL do { } while (0)
+#define SP_WAIT(i, bar, par) mbar_wait(bar, par)
+#define SP_LAP(i) do { } while (0)
+#define SP_RESET() do { } while (0)
+#define SP_DUMP(base) do { } while (0)
+#endif
+
 constexpr int kSM = 128;                 // latents per row tile
-constexpr int kSThreads = 320;           // 10 warps
-constexpr int kSCand = 16;               // candidate slots per latent
+constexpr int kSThreads = 448;           // 14 warps
+constexpr int kSScanWarps = 8;           // two per TMEM lane quadrant
+constexpr int kSCand = 8;                // candidate slots per latent and scan half
 constexpr int kSESlots = 8;              // |e|^2 slices in flight
 constexpr int kSBrowRing = 4;            // row-bound buffers (converter runs up to 2 tiles ahead of the scan)
 constexpr int kSMaxStages = 8;
+constexpr int kSOvf = 32;                // spill entries per quadrant and row tile (beyond that: exhaustive scan)
+constexpr int kSScratch = 2 * kSCand + kSOvf;   // merged candidate list of one latent (general resolution path)
 
 struct StreamPlan {
     int stages, stage_bytes, a_bytes;
-    int a, b, e2s, brow, cs, cc, drop, red, misc, bars, tmem, total;
+    int a, b, e2s, brow, cs, cc, drop, mfin, ncnt, ovf, scratch, red, misc, bars, tmem, total;
 };
 __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages) {
     StreamPlan u;
@@ -58,9 +78,13 @@ __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stage
     u.b = o;     o += stages * u.stage_bytes;
     u.e2s = o;   o += kSESlots * nt * 4;
     u.brow = o;  o += kSBrowRing * kSM * 4;
-    u.cs = o;    o += kSCand * kSM * 4;
-    u.cc = o;    o += kSCand * kSM * 4;
-    u.drop = o;  o += kSM * 4;
+    u.cs = o;    o += 2 * kSCand * kSM * 4;
+    u.cc = o;    o += 2 * kSCand * kSM * 4;
+    u.drop = o;  o += 2 * kSM * 4;
+    u.mfin = o;  o += 2 * kSM * 4;
+    u.ncnt = o;  o += 2 * kSM * 4;
+    u.ovf = o;   o += 2 * 4 * kSOvf * 12;       // [row-tile parity][quadrant]: rows | scores | codes
+    u.scratch = o; o += kSScratch * 8 * 4;   // per scan warp
     u.red = o;   o += 32 * 8;
     u.misc = o;  o += 16 * 4;
     u.bars = o;  o += (2 * kSMaxStages + 4 + 8 + 2 * kSESlots + 2 * kSBrowRing) * 8;
@@ -122,42 +146,47 @@ __device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) {
 }
 }  // namespace sm100
 
-// Append (score, code) to a latent's candidate list (slots are kSM words apart so that the 32
-// latents of a warp never collide on a bank).  A full list is first compacted against the current
-// threshold (which only ever decreases); if it is still full the WORST entry is dropped and the
-// smallest dropped score remembered: at the end of the scan the list is complete iff that score
-// lies above the final threshold (otherwise the latent takes the exhaustive scan).
-__device__ __noinline__ int cand_append(const float s, const int code, int cnt, const float thr, float* ls, int* lc, float* dropp) {
-    if (cnt == kSCand) {
-        int kept = 0;
-        for (int i = 0; i < kSCand; ++i) {
-            const float v = ls[i * kSM];
-            const int c = lc[i * kSM];
-            if (v <= thr) { ls[kept * kSM] = v; lc[kept * kSM] = c; ++kept; }
-        }
-        cnt = kept;
-        if (cnt == kSCand) {
-            int imax = 0;
-            float vmax = ls[0];
-            for (int i = 1; i < kSCand; ++i) {
-                const float v = ls[i * kSM];
-                if (v > vmax) { vmax = v; imax = i; }
-            }
-            if (s >= vmax) { *dropp = fminf(*dropp, s); return cnt; }
-            *dropp = fminf(*dropp, vmax);
-            ls[imax * kSM] = s;
-            lc[imax * kSM] = code;
-            return cnt;
-        }
+// Spill buffer of one TMEM lane quadrant for the current row tile (shared memory).
+struct OvfBuf {
+    int* n;        // entries used (may run past kSOvf: then entries were lost)
+    int* row;      // [kSOvf] latent (row within the tile)
+    float* s;      // [kSOvf] bf16 score
+    int* c;        // [kSOvf] code
+};
+
+// Candidate list of one latent and one scan half: kSCand slots, kSM words apart so that the 32 latents
+// of a warp never collide on a bank.  Called when the list is full: compact it against the current
+// threshold (which only ever decreases); if it is still full move the WORST entry to the quadrant's
+// spill buffer.  Only if that is full too is an entry really lost; the smallest lost score is
+// remembered, and the latent takes the exhaustive scan iff it lies inside the final threshold.
+// Returns the new count (< kSCand), | 0x100 if an entry was spilled.
+__device__ __noinline__ int cand_compact(const float thr, float* ls, int* lc, float* dropp, const OvfBuf ob, const int trow) {
+    int kept = 0;
+    for (int i = 0; i < kSCand; ++i) {
+        const float v = ls[i * kSM];
+        const int c = lc[i * kSM];
+        if (v <= thr) { ls[kept * kSM] = v; lc[kept * kSM] = c; ++kept; }
     }
-    ls[cnt * kSM] = s;
-    lc[cnt * kSM] = code;
-    return cnt + 1;
+    if (kept == kSCand) {
+        int imax = 0;
+        float vmax = ls[0];
+        for (int i = 1; i < kSCand; ++i) {
+            const float v = ls[i * kSM];
+            if (v > vmax) { vmax = v; imax = i; }
+        }
+        const int pos = atomicAdd(ob.n, 1);
+        if (pos < kSOvf) { ob.row[pos] = trow; ob.s[pos] = vmax; ob.c[pos] = lc[imax * kSM]; }
+        else *dropp = fminf(*dropp, vmax);
+        ls[imax * kSM] = ls[(kSCand - 1) * kSM];
+        lc[imax * kSM] = lc[(kSCand - 1) * kSM];
+        kept = (kSCand - 1) | 0x100;
+    }
+    return kept;
 }
 
 // One chunk of 32 scores of ONE latent (this thread's TMEM lane).
 __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const float4* e2c, const int code0, const float brow,
-                                           float& m, int& cnt, float* ls, int* lc, float* dropp) {
+                                           float& m, int& cnt, float* ls, int* lc, float* dropp, const OvfBuf& ob, const int trow) {
     using namespace sm100;
     float s[32];
 #pragma unroll
@@ -177,8 +206,14 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const float4
         for (int i = 0; i < 8; ++i) {
             if (g[i] <= thr) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (s[4 * i + j] <= thr) cnt = cand_append(s[4 * i + j], code0 + 4 * i + j, cnt, thr, ls, lc, dropp);
+                for (int j = 0; j < 4; ++j) {
+                    if (s[4 * i + j] <= thr) {
+                        if ((cnt & 0xff) == kSCand) cnt = cand_compact(thr, ls, lc, dropp, ob, trow) | (cnt & 0x100);
+                        ls[(cnt & 0xff) * kSM] = s[4 * i + j];
+                        lc[(cnt & 0xff) * kSM] = code0 + 4 * i + j;
+                        ++cnt;
+                    }
+                }
             }
         }
     }
@@ -195,13 +230,13 @@ __device__ __forceinline__ float dot32_part(const float4 x0, const float4 x1, co
     return dd;
 }
 
-// General (rare) resolution of one latent: from its candidate list (nc > 4) or from ALL codes
-// (nc <= 0: the list overflowed or held non-finite scores).  fp32 re-score four codes at a time, then
-// the canonical fp64 rule over the same set if the fp32 scores cannot separate the two best.
-// All 32 lanes work on the one latent; lane l holds the 16-byte chunks l (x0) and l + 32 (x1) of x.
+// General (rare) resolution of one latent: from a merged candidate list in shared memory (nc > 0) or
+// from ALL codes (nc <= 0: entries were lost or the scores were non-finite).  fp32 re-score four codes
+// at a time, then the canonical fp64 rule over the same set if the fp32 scores cannot separate the two
+// best.  All 32 lanes work on the one latent; lane l holds the 16-byte chunks l (x0) and l + 32 (x1) of x.
 // Returns the canonical arg-min, | 1 << 30 if the fp64 level was needed.
 template <int NV>
-__device__ __noinline__ int resolve_stream(const float4 x0, const float4 x1, const int nc, const int* lc, const float* cb,
+__device__ __noinline__ int resolve_stream(const float4 x0, const float4 x1, const int nc, const int* list, const float* cb,
                                            const float* e2g, const int k, const int d, const float emax, const int lane) {
     const int nchunk = d >> 2;
     const bool h0 = lane < nchunk, h1 = NV > 1 && lane + 32 < nchunk;
@@ -221,7 +256,7 @@ __device__ __noinline__ int resolve_stream(const float4 x0, const float4 x1, con
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int j = j0 + t < count ? j0 + t : count - 1;
-            int c = nc > 0 ? lc[j * kSM] : j;
+            int c = nc > 0 ? list[j] : j;
             c = (c >= 0 && c < k) ? c : 0;
             code[t] = c;
             dd[t] = dot32_part<NV>(x0, x1, cb, c, d, h0, h1, lane);
@@ -247,7 +282,7 @@ __device__ __noinline__ int resolve_stream(const float4 x0, const float4 x1, con
     float best = INF;
     int arg = 0x7fffffff;
     for (int j = 0; j < count; ++j) {
-        int code = nc > 0 ? lc[j * kSM] : j;
+        int code = nc > 0 ? list[j] : j;
         code = (code >= 0 && code < k) ? code : 0;
         const float4* er = reinterpret_cast<const float4*>(cb + (size_t)code * d);
         double sd = 0.0;
@@ -260,6 +295,25 @@ __device__ __noinline__ int resolve_stream(const float4 x0, const float4 x1, con
     return arg | (1 << 30);
 }
 
+// Merge the candidates of one latent into `list` (this warp's scratch): half 0's n0 entries, half 1's n1,
+// and the quadrant's spilled entries of this latent that lie inside the final threshold.  Warp-cooperative.
+__device__ __forceinline__ int gather_cands(int* list, const int n0, const int n1, const int* lc_row, const OvfBuf ob,
+                                            const int lrow, const float thr, const int lane) {
+    if (lane < n0) list[lane] = lc_row[lane * kSM];
+    if (lane < n1) list[n0 + lane] = lc_row[(kSCand + lane) * kSM];
+    int cnt = n0 + n1;
+    const int on = min(*ob.n, kSOvf);
+    for (int base = 0; base < on; base += 32) {
+        const int e = base + lane;
+        const bool match = e < on && ob.row[e] == lrow && ob.s[e] <= thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, match);
+        if (match) list[cnt + __popc(bal & lanemask_lt())] = ob.c[e];
+        cnt += __popc(bal);
+    }
+    __syncwarp();
+    return cnt;
+}
+
 template <int DP, int NT, bool TRAIN>
 __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_cb, const FwdParams p,
                                                                  const int stages) {
@@ -267,7 +321,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int KSLABS = DP / 64;             // 64-column (128-byte) bf16 slabs per row
     constexpr int SLOTS = 512 / NT;             // tensor-memory score slots
-    constexpr int NCHUNK32 = NT / 32;           // 32-score chunks per code tile
+    constexpr int NCH = NT / 64;                // 32-score chunks per code tile AND scan half
     constexpr int F = DP / 4;                   // 16-byte fp32 chunks per padded row
     constexpr int NV = DP > 128 ? 2 : 1;        // 16-byte chunks per lane in the warp-per-latent phases
     constexpr int A_SLAB = kSM * 128;           // bytes of one A slab (128 rows x 128 bytes)
@@ -277,8 +331,13 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     const StreamPlan pl = make_stream_plan(DP, NT, stages);
     float* e2s = reinterpret_cast<float*>(smem + pl.e2s);
     float* brow_ring = reinterpret_cast<float*>(smem + pl.brow);
-    float* cand_s = reinterpret_cast<float*>(smem + pl.cs);
+    float* cand_s = reinterpret_cast<float*>(smem + pl.cs);     // [half][slot][latent]
     int* cand_c = reinterpret_cast<int*>(smem + pl.cc);
+    float* drop = reinterpret_cast<float*>(smem + pl.drop);     // [half][latent]
+    float* mfin = reinterpret_cast<float*>(smem + pl.mfin);     // [half][latent] minimum seen by each scan half
+    int* ncnt = reinterpret_cast<int*>(smem + pl.ncnt);         // [half][latent] final candidates per half (-1: incomplete)
+    int* ovf_base = reinterpret_cast<int*>(smem + pl.ovf);      // [parity][quadrant][rows | scores | codes][kSOvf]
+    int* scratch_base = reinterpret_cast<int*>(smem + pl.scratch);
     double* red = reinterpret_cast<double*>(smem + pl.red);
     int* misc = reinterpret_cast<int*>(smem + pl.misc);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.tmem);
@@ -300,11 +359,12 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     if (tid == 0) {
         for (int s = 0; s < kSMaxStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }
-        for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
-        for (int s = 0; s < kSESlots; ++s) { mbar_init(bar_efull + 8 * s, 1); mbar_init(bar_eempty + 8 * s, 4); }
-        for (int s = 0; s < kSBrowRing; ++s) { mbar_init(bar_rfull + 8 * s, 4); mbar_init(bar_rempty + 8 * s, 4); }
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, kSScanWarps); }
+        for (int s = 0; s < kSESlots; ++s) { mbar_init(bar_efull + 8 * s, 1); mbar_init(bar_eempty + 8 * s, kSScanWarps); }
+        for (int s = 0; s < kSBrowRing; ++s) { mbar_init(bar_rfull + 8 * s, 4); mbar_init(bar_rempty + 8 * s, kSScanWarps); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_cb);
+        for (int i = 4; i < 12; ++i) misc[i] = 0;           // spill counters [parity][quadrant]
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     // max |e| (error-bound constant): every CTA scans the |e|^2 table (k floats, L2 resident)
@@ -331,40 +391,44 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
         // (the |e|^2 table in the workspace is padded with BIG to a multiple of 256, so every slice is a
         //  plain NT*4-byte bulk copy and codes >= k can never be nominated)
         if (lane == 0) {
+            SP_DECL;
             int ib = 0, et = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int ct = 0; ct < n_ct; ++ct, ++et) {
                     const int es = et % kSESlots;
-                    mbar_wait(bar_eempty + 8 * es, (((uint32_t)(et / kSESlots)) & 1u) ^ 1u);
+                    SP_WAIT(0, bar_eempty + 8 * es, (((uint32_t)(et / kSESlots)) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(bar_efull + 8 * es, (uint32_t)(NT * 4));
                     bulk_load_1d(smem_u32(e2s + es * NT), p.e2 + (size_t)ct * NT, (uint32_t)(NT * 4), bar_efull + 8 * es);
                     for (int j = 0; j < KSLABS; ++j, ++ib) {
                         const int s = ib % stages;
-                        mbar_wait(bar_bempty + 8 * s, (((uint32_t)(ib / stages)) & 1u) ^ 1u);
+                        SP_WAIT(1, bar_bempty + 8 * s, (((uint32_t)(ib / stages)) & 1u) ^ 1u);
                         mbar_arrive_expect_tx(bar_bfull + 8 * s, (uint32_t)(NT * 128));
                         tma_load_2d(b_base + s * pl.stage_bytes, &tmap_cb, bar_bfull + 8 * s, j * 64, ct * NT);
                     }
                 }
             }
+            SP_LAP(7);
+            SP_DUMP(0);
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(kSM, NT);
+            SP_DECL;
             int ib = 0, tt = 0, it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int ab = it & 1;
-                mbar_wait(bar_afull + 8 * ab, ((uint32_t)(it >> 1)) & 1u);
+                SP_WAIT(0, bar_afull + 8 * ab, ((uint32_t)(it >> 1)) & 1u);
                 tc_fence_after();
                 const uint32_t a0 = a_base + ab * pl.a_bytes;
                 for (int ct = 0; ct < n_ct; ++ct, ++tt) {
                     const int slot = tt % SLOTS;
-                    mbar_wait(bar_tempty + 8 * slot, (((uint32_t)(tt / SLOTS)) & 1u) ^ 1u);
+                    SP_WAIT(1, bar_tempty + 8 * slot, (((uint32_t)(tt / SLOTS)) & 1u) ^ 1u);
                     tc_fence_after();
 #pragma unroll 1
                     for (int j = 0; j < KSLABS; ++j, ++ib) {
                         const int s = ib % stages;
-                        mbar_wait(bar_bfull + 8 * s, ((uint32_t)(ib / stages)) & 1u);
+                        SP_WAIT(2, bar_bfull + 8 * s, ((uint32_t)(ib / stages)) & 1u);
                         tc_fence_after();
                         const uint32_t b0 = b_base + s * pl.stage_bytes;
 #pragma unroll
@@ -377,12 +441,15 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 }
                 umma_commit(bar_aempty + 8 * ab);              // A buffer free once every MMA of the row tile is done
             }
+            SP_LAP(7);
+            SP_DUMP(8);
         }
-    } else if (warp >= 6) {
+    } else if (warp >= 2 + kSScanWarps) {
         // ============================================================ converters: x fp32 -> bf16 A operand, |x| -> bound
-        const int cw = warp - 6;
+        const int cw = warp - (2 + kSScanWarps);
         const int rowbase = cw * 32;                          // this warp's 32 latents of the tile
         constexpr int U = 8;
+        SP_DECL;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
@@ -396,8 +463,9 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 }
             }
             const int rs = it & (kSBrowRing - 1);
-            mbar_wait(bar_aempty + 8 * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
-            mbar_wait(bar_rempty + 8 * rs, (((uint32_t)(it / kSBrowRing)) & 1u) ^ 1u);
+            SP_WAIT(0, bar_aempty + 8 * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+            SP_WAIT(1, bar_rempty + 8 * rs, (((uint32_t)(it / kSBrowRing)) & 1u) ^ 1u);
+            SP_RESET();
             const uint32_t a0 = a_base + ab * pl.a_bytes;
             float* brow = brow_ring + rs * kSM;
 #pragma unroll 1
@@ -463,74 +531,92 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
             fence_proxy_async_smem();                         // generic-proxy stores -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_afull + 8 * ab); mbar_arrive(bar_rfull + 8 * rs); }
+            SP_LAP(2);
         }
+        if (cw == 0 && lane == 0) SP_DUMP(24);
     } else {
         // ============================================================ scan + apply warps (one thread per latent)
         const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int half = (warp - 2) >> 2;                     // which half of every code tile's columns this warp scans
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (NT / 2));
         const int trow = quad * 32 + lane;                    // this thread's latent within the tile
-        float* ls = cand_s + trow;
-        int* lc = cand_c + trow;
-        float* dropp = reinterpret_cast<float*>(smem + pl.drop) + trow;
+        float* ls = cand_s + half * (kSCand * kSM) + trow;
+        int* lc = cand_c + half * (kSCand * kSM) + trow;
+        float* dropp = drop + half * kSM + trow;
+        float* thrfin = mfin;                                 // reused after the merge: final threshold per latent (half 0 slot)
+        int* scratch = scratch_base + (warp - 2) * kSScratch;
         float* esum = p.stats + ((p.k + 3) & ~3);
         const bool h0 = lane < nchunk, h1 = NV > 1 && lane + 32 < nchunk;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float INF = __int_as_float(0x7f800000);
         constexpr int R = NV > 1 ? 2 : 4;                     // latents in flight in the apply phase
+        SP_DECL;
         int et = 0, it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int rs = it & (kSBrowRing - 1);
-            mbar_wait(bar_rfull + 8 * rs, ((uint32_t)(it / kSBrowRing)) & 1u);     // the row bounds are written
+            SP_WAIT(0, bar_rfull + 8 * rs, ((uint32_t)(it / kSBrowRing)) & 1u);     // the row bounds are written
             const float brow = brow_ring[rs * kSM + trow];
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);
             float m = INF;
-            int cnt = 0;
+            int cnt = 0;                                      // low 8 bits: list entries; 0x100: an entry was spilled
             *dropp = INF;
-            // ---- scan: all code tiles of this row tile
+            OvfBuf ob;
+            {
+                int* ob0 = ovf_base + ((it & 1) * 4 + quad) * (3 * kSOvf);
+                ob.n = misc + 4 + (it & 1) * 4 + quad;
+                ob.row = ob0;
+                ob.s = reinterpret_cast<float*>(ob0 + kSOvf);
+                ob.c = ob0 + 2 * kSOvf;
+            }
+            // ---- scan: this warp's half of the columns of every code tile
             for (int ct = 0; ct < n_ct; ++ct, ++et) {
                 const int slot = et % SLOTS, es = et % kSESlots;
-                mbar_wait(bar_efull + 8 * es, ((uint32_t)(et / kSESlots)) & 1u);
-                mbar_wait(bar_tfull + 8 * slot, ((uint32_t)(et / SLOTS)) & 1u);
+                SP_WAIT(1, bar_efull + 8 * es, ((uint32_t)(et / kSESlots)) & 1u);
+                SP_WAIT(2, bar_tfull + 8 * slot, ((uint32_t)(et / SLOTS)) & 1u);
                 tc_fence_after();
+                SP_RESET();
                 const uint32_t taddr = lane_addr + (uint32_t)(slot * NT);
-                const float4* e2c = reinterpret_cast<const float4*>(e2s + es * NT);
-                const int code0 = ct * NT;
-                uint32_t ra[32], rb[32];
-                tmem_ld_x32(taddr, ra);
+                const float4* e2c = reinterpret_cast<const float4*>(e2s + es * NT + half * (NT / 2));
+                const int code0 = ct * NT + half * (NT / 2);
 #pragma unroll 1
-                for (int c = 0; c < NCHUNK32; c += 2) {
+                for (int c = 0; c < NCH; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_x32(taddr + (uint32_t)c * 32u, r);
                     tmem_ld_wait();
-                    tmem_ld_x32(taddr + (uint32_t)(c + 1) * 32u, rb);
-                    scan_chunk(ra, e2c + c * 8, code0 + c * 32, brow, m, cnt, ls, lc, dropp);
-                    tmem_ld_wait();
-                    if (c + 2 < NCHUNK32) tmem_ld_x32(taddr + (uint32_t)(c + 2) * 32u, ra);
-                    scan_chunk(rb, e2c + (c + 1) * 8, code0 + (c + 1) * 32, brow, m, cnt, ls, lc, dropp);
+                    scan_chunk(r, e2c + c * 8, code0 + c * 32, brow, m, cnt, ls, lc, dropp, ob, trow);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(bar_tempty + 8 * slot); mbar_arrive(bar_eempty + 8 * es); }
+                SP_LAP(3);
             }
-            // ---- final candidate set of this thread's latent: scores within the bound of the minimum
-            int ncand = -1;
+            SP_RESET();
+            // ---- merge the two halves of the quadrant: common minimum, then each half filters its own list
+            mfin[half * kSM + trow] = m;
+            named_bar_sync(1 + quad, 64);
+            const float thr_fin = fminf(m, mfin[(half ^ 1) * kSM + trow]) + brow;
             {
-                const float thr = m + brow;
+                const int nl = cnt & 0xff;
                 int kept = 0;
-                for (int i = 0; i < cnt; ++i) {
+                for (int i = 0; i < nl; ++i) {
                     const float v = ls[i * kSM];
-                    if (v <= thr) { lc[kept * kSM] = lc[i * kSM]; ++kept; }
+                    if (v <= thr_fin) { lc[kept * kSM] = lc[i * kSM]; ++kept; }
                 }
-                if (kept > 0 && *dropp > thr) ncand = kept;   // else: non-finite scores or a truly overflowed list
+                // a half is incomplete if it LOST a score inside the final threshold (or saw non-finite scores)
+                ncnt[half * kSM + trow] = (*dropp > thr_fin) ? (kept | (cnt & 0x100)) : -1;
             }
-            __syncwarp();
+            named_bar_sync(1 + quad, 64);
+            if (half == 0) thrfin[trow] = thr_fin;            // (both halves have read mfin)
             // ---- resolve + apply: all 32 lanes on one latent, R latents in flight, ONE round trip to L2:
             //      x rows, the first candidate's code word and (for ambiguous latents) candidates 2-4 are
-            //      all requested before anything is used
-            const int64_t wrow0 = (int64_t)tile * kSM + quad * 32;
+            //      all requested before anything is used.  This warp takes 16 latents of its quadrant.
+            const int lrow0 = quad * 32 + half * 16;          // first latent (within the tile) of this warp
+            const int64_t wrow0 = (int64_t)tile * kSM + lrow0;
             int mycode = 0;
             float loss = 0.f;
 #pragma unroll 1
-            for (int b = 0; b < 32 / R; ++b) {
+            for (int b = 0; b < 16 / R; ++b) {
                 if (wrow0 + R * b >= p.n) break;              // warp-uniform
                 float4 xa[R], xb[R], ea[R][4], eb[R][4];
                 float e2v[R][4];
@@ -538,13 +624,18 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 bool valid[R];
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
+                    const int lrow = lrow0 + R * b + u;
                     const int64_t grow = wrow0 + R * b + u;
                     valid[u] = grow < p.n;
-                    nc[u] = __shfl_sync(0xffffffffu, ncand, R * b + u);
-                    const int* lcr = cand_c + quad * 32 + R * b + u;
+                    const int n0r = ncnt[lrow], n1r = ncnt[kSM + lrow];
+                    const int n0 = n0r & 0xff, n1 = n1r & 0xff;
+                    // -1: exhaustive scan; 100: general path over lists + spill buffer; else the merged count
+                    nc[u] = (n0r < 0 || n1r < 0 || n0 + n1 == 0) ? -1 : ((n0r | n1r) & 0x100) ? 100 : n0 + n1;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        int c = lcr[(j < nc[u] ? j : 0) * kSM];
+                        // candidate j of the merged list: half 0's entries first, then half 1's
+                        const int jj = j < nc[u] ? j : 0;
+                        const int c = jj < n0 ? cand_c[jj * kSM + lrow] : cand_c[(kSCand + ((jj - n0) & (kSCand - 1))) * kSM + lrow];
                         cc[u][j] = (c >= 0 && c < p.k) ? c : 0;
                     }
                     const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)(valid[u] ? grow : 0) * p.d);
@@ -620,8 +711,12 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                     wb[u] = sel == 0 ? eb[u][0] : sel == 1 ? eb[u][1] : sel == 2 ? eb[u][2] : eb[u][3];
                     if (valid[u] && (nc[u] < 1 || nc[u] > 4)) {
                         // rare: long candidate list or exhaustive scan, then a second trip for the code word
-                        const int r = resolve_stream<NV>(xa[u], xb[u], nc[u], cand_c + quad * 32 + R * b + u, p.cb, p.e2, p.k, p.d,
-                                                         emax, lane);
+                        const int lrow = lrow0 + R * b + u;
+                        int ncg = nc[u];
+                        if (ncg > 0) ncg = gather_cands(scratch, ncnt[lrow] & 0xff, ncnt[kSM + lrow] & 0xff, cand_c + lrow, ob, lrow,
+                                                        thrfin[lrow], lane);
+                        const int r = resolve_stream<NV>(xa[u], xb[u], ncg, scratch, p.cb, p.e2, p.k, p.d, emax, lane);
+                        __syncwarp();
                         n_resc += 1u;
                         n_f64 += (unsigned)(r >> 30);
                         int code = r & 0x3fffffff;
@@ -673,13 +768,17 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
 #pragma unroll
                 for (int u = 0; u < R; ++u) mycode = (lane == R * b + u) ? cd[u] : mycode;
             }
-            if (wrow0 + lane < p.n) {
+            if (lane < 16 && wrow0 + lane < p.n) {
                 p.idx[wrow0 + lane] = (int64_t)mycode;
                 atomicAdd(p.stats + mycode, 1.0f);            // counts (exact integers in fp32)
             }
             loss_d += (double)loss;
-            __syncwarp();                                     // candidate lists are reused by the next row tile
+            if (half == 0 && lane == 0) misc[4 + ((it + 1) & 1) * 4 + quad] = 0;   // spill buffer of the next row tile
+            named_bar_sync(1 + quad, 64);                     // the quadrant's lists are reused by the next row tile
+            SP_LAP(5);
         }
+        if (warp == 2 && lane == 0) SP_DUMP(16);
+        if (lane == 0) SP_DUMP(64 + 8 * (warp - 2));
     }
 
     // ------------------------------------------------------------------ teardown

@@ -44,8 +44,11 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const uint64_t t0 = globaltimer_ns();
-    while (!mbar_try_wait(bar, parity)) {
-        if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+    for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+        // try_wait itself parks the thread for a while; the extra sleep keeps a long wait (a converter
+        // waiting for a whole row tile) from competing for issue slots with the working warps
+        if (spin > 4) __nanosleep(spin > 64 ? 256 : 32);
+        if ((spin & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
     }
 }
 

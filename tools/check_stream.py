@@ -39,6 +39,22 @@ for (n, k, d) in shapes:
         ok &= good
         print(f"n={n} k={k} d={d} train={train}: idx_mismatch={bad} q_eq={qeq} counts_eq={ceq} esum_rel={es:.2e} loss_rel={ls:.2e} "
               f"ppl_rel={pp:.2e} canon={cok} rescored={resc} {'OK' if good else 'FAIL'}", flush=True)
+# near-ties / duplicated codes: candidate lists overflow -> spill buffer -> exhaustive scan; first index must win
+for (n, k, d, dup, noise) in [(3000, 640, 64, 20, 0.0), (2000, 1024, 128, 6, 0.0), (4000, 2048, 128, 12, 1e-3), (1500, 512, 256, 40, 0.0)]:
+    torch.manual_seed(n + k)
+    k = (k // dup) * dup
+    base = torch.randn(k // dup, d)
+    e = (base.repeat_interleave(dup, 0) + noise * torch.randn(k, d)).to(DEV)
+    x = torch.randn(n, d).to(DEV)
+    ws = tvq.Workspace(k, d, torch.device(DEV))
+    idx_u, q_u, sc_u = tvq.vq_forward_raw(x, e, ws, train=True)
+    idx_s, q_s, sc_s = tvq.vq_forward_raw(x, e, ws, train=True, flags=tvq._lib.F_NO_UMMA)
+    torch.cuda.synchronize()
+    bad = int((idx_u != idx_s).sum())
+    cok = np.array_equal(idx_u.cpu().numpy(), C.assign(x.cpu().numpy(), e.cpu().numpy()))
+    good = bad == 0 and cok and torch.equal(q_u, q_s)
+    ok &= good
+    print(f"dup n={n} k={k} d={d} dup={dup} noise={noise}: idx_mismatch={bad} canon={cok} rescored={sc_u.view(torch.int32)[4:6].tolist()} {'OK' if good else 'FAIL'}", flush=True)
 print("PARITY", "OK" if ok else "FAIL", flush=True)
 if not ok or (len(sys.argv) > 1 and sys.argv[1] == "quick"):
     sys.exit(0 if ok else 1)
