@@ -232,12 +232,16 @@ def our_arm(args):
     eager_ms = timed(eager, args.steps)
     clear_grads()
 
-    # ---- CUDA-graph replay of the same step (launch-bound regime: 8 small kernels per step) -------
-    graphs = None
+    # ---- CUDA-graph replay of the same step (launch-bound regime: 4 small kernels per step).  ONE graph holds
+    #      several consecutive training steps (rotating over the resident input batches, EMA state carried from
+    #      step to step inside the graph), so the host launch gap is paid once per replay, not once per step.
+    graph = None
     graph_ms = None
+    steps_per_replay = max(dv for dv in (8, 7, 6, 5, 4, 3, 2, 1) if args.steps % dv == 0)   # EXACTLY args.steps are timed
+    n_replays = args.steps // steps_per_replay
+    timed_steps = args.steps
     if not args.no_graph:
         try:
-            graphs = []
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -245,39 +249,39 @@ def our_arm(args):
                     step(*s)
             torch.cuda.current_stream().wait_stream(side)
             barrier()
-            for s in sets:
-                g = torch.cuda.CUDAGraph()
-                # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    step(*s)
-                graphs.append(g)
+            graph = torch.cuda.CUDAGraph()
+            # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                for j in range(steps_per_replay):
+                    step(*sets[j % N_INPUT_SETS])
         except Exception as exc:   # report, never hide
             print(f"[bench] rank {rank}: CUDA-graph capture failed: {exc}", file=sys.stderr)
-            graphs = None
+            graph = None
         if world > 1:              # every rank must take the same path BEFORE anything is replayed
             torch.cuda.synchronize()
-            ok = torch.tensor([1 if graphs is not None else 0], device=dev)
+            ok = torch.tensor([1 if graph is not None else 0], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok) == 0:
-                graphs = None
-        if graphs is not None:
+                graph = None
+        if graph is not None:
             for i in range(max(args.warmup, 3)):
-                graphs[i % N_INPUT_SETS].replay()
-            graph_ms = timed(lambda i: graphs[i % N_INPUT_SETS].replay(), args.steps)
+                graph.replay()
+            graph_ms = timed(lambda i: graph.replay(), n_replays)
 
     # ---- the timed region that `value` reports, with clocks sampled during it -----------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    if graphs is not None:
-        main_ms = timed(lambda i: graphs[i % N_INPUT_SETS].replay(), args.steps)
-        mode = "cuda_graph_replay"
+    if graph is not None:
+        main_ms = timed(lambda i: graph.replay(), n_replays)
+        mode = f"cuda_graph_replay ({steps_per_replay} steps per replay)"
     else:
+        timed_steps = args.steps
         main_ms = timed(eager, args.steps)
         mode = "eager"
     clocks = sampler.stop() if rank == 0 else None
     clear_grads()
-    value = world * LATENTS_PER_STEP * args.steps / (main_ms * 1e-3)
+    value = world * LATENTS_PER_STEP * timed_steps / (main_ms * 1e-3)
 
     # ---- e2e: pinned host inputs -> H2D -> step -> D2H of the step's result -------------------------
     host_sets = [(s[0].detach().cpu().pin_memory(), s[1].detach().cpu().pin_memory()) for s in sets]
@@ -304,7 +308,8 @@ def our_arm(args):
     e2e_ms = timed(e2e_step, args.steps)
     e2e_value = world * LATENTS_PER_STEP * args.steps / (e2e_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (the HF fused forward), timed alone with CUDA events --------
+    # ---- roofline of the dominant kernel: the HF fused train step (forward + EMA, ONE launch — the kernel the
+    #      timed region runs for the HF codebook), timed alone with CUDA events on the launching stream --------
     cb = vq_h._codebook
     ws = cb._workspace(dev)
     flats = [s[1].detach().reshape(-1, DIM) for s in sets]
@@ -313,13 +318,14 @@ def our_arm(args):
     idx = torch.empty(n_hf, dtype=torch.int64, device=dev)
     q = torch.empty_like(flats[0])
     scal = torch.empty(8, device=dev)
+    emb, csz, eavg = cb.embed.detach().clone(), cb.cluster_size.detach().clone(), cb.embed_avg.detach().clone()
     st = torch.cuda.current_stream().cuda_stream
 
     def fwd_kernel(i):
         x = flats[i % N_INPUT_SETS]
-        rc = lib.tvq_forward(x.data_ptr(), cb.embed.data_ptr(), n_hf, K_CODES, DIM, tvq._lib.F_TRAIN | tvq._lib.F_WRITE_Q,
-                             1.0, idx.data_ptr(), q.data_ptr(), ws.stats.data_ptr(), scal.data_ptr(), ws.buf.data_ptr(),
-                             ws.nbytes, st)
+        rc = lib.tvq_train_step(x.data_ptr(), emb.data_ptr(), csz.data_ptr(), eavg.data_ptr(), None, n_hf, K_CODES, DIM, 1.0,
+                                0.8, 1e-5, idx.data_ptr(), q.data_ptr(), scal.data_ptr(), None, None, ws.buf.data_ptr(),
+                                ws.nbytes, st)
         assert rc == 0
     for i in range(5):
         fwd_kernel(i)
@@ -327,17 +333,24 @@ def our_arm(args):
     k_ms = timed(fwd_kernel, reps) / reps
     alg_bytes = n_hf * (8 * DIM + 8)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:   # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("fwd_umma_train_hf_n76800")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                "traffic": None, "peak_source": peak_src,
-                "kernel": "tvq_forward (prep + fused forward) on the HF codebook, N=76800",
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "fwd_umma_kernel<128,32,train> via tvq_train_step (fused forward + EMA, one launch) on the HF "
+                          "codebook, N=76800, eager launches back to back",
                 "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": k_ms * 1e3,
-                "note": "76 800 latents = 12 us of HBM time: launch/tail-latency regime (SURVEY 7.3-4); see `sweep` "
-                        "for the large-N fractions"}
+                "note": "76 800 latents = 12 us of HBM time: launch/tail-latency regime (SURVEY 7.3-4); `sweep` holds the "
+                        "large-N points (BASELINE configs[2]) where the fraction is meaningful"}
 
     # ---- large-N sweep points (BASELINE configs[2]) ---------------------------------------------------
     sweep = []
     if rank == 0 and not args.no_sweep:
-        for (n, k, d) in ((1 << 22, 32, 128), (1 << 22, 512, 64), (1 << 20, 4096, 128)):
+        for (n, k, d) in ((1 << 22, 32, 128), (1 << 22, 512, 64), (1 << 21, 1024, 128), (1 << 20, 4096, 128),
+                          (1 << 20, 4096, 256), (1 << 19, 16384, 256)):
             try:
                 sweep.append(sweep_point(tvq, dev, n, k, d, hbm_gbs, bf16_tf))
             except Exception as exc:
@@ -356,21 +369,21 @@ def our_arm(args):
     launches_per_step = 2 * (1 + 1) if world == 1 else 2 * (2 + 1 + 1)
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": main_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": timed_steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": main_ms / timed_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": dict(workload_config(world), timed_mode=mode),
             "trajectories_per_sec": value / (TOK_LF + TOK_HF),
-            "eager_ms_per_step": eager_ms / args.steps, "graph_ms_per_step": (graph_ms / args.steps) if graph_ms else None,
+            "eager_ms_per_step": eager_ms / args.steps, "graph_ms_per_step": (graph_ms / timed_steps) if graph_ms else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "what": "pinned host x (LF+HF) -> H2D -> VectorQuantize fwd+bwd (eager, public API) -> D2H of loss + indices"},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches_per_step * timed_steps,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "sweep": sweep,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        # captured graphs hold NCCL work: drop them, drain, and leave without the (hanging) teardown
-        graphs = None
+        # the captured graph holds NCCL work: drop it, drain, and leave without the (hanging) teardown
+        graph = None
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()
@@ -399,8 +412,12 @@ def sweep_point(tvq, dev, n, k, d, hbm_gbs, bf16_tf):
     by = n * (8 * d + 8) / (ms * 1e-3) / 1e9
     fl = 2.0 * n * k * d / (ms * 1e-3) / 1e12
     hb, tc = by / hbm_gbs, fl / bf16_tf
+    # the bound is the SLOWER of the two rooflines for this shape; frac = that roofline's time / ours
+    t_hbm, t_tc = n * (8 * d + 8) / (hbm_gbs * 1e9), 2.0 * n * k * d / (bf16_tf * 1e12)
     return {"n": n, "k": k, "d": d, "mode": "train_forward", "ms": ms, "latents_per_sec": n / (ms * 1e-3),
-            "hbm_gbs": by, "tflops": fl, "bound": "hbm" if hb >= tc else "tensor", "frac": max(hb, tc)}
+            "hbm_gbs": by, "tflops": fl, "bound": "hbm" if t_hbm >= t_tc else "tensor", "frac": max(hb, tc),
+            "path": "tcgen05 tf32, resident codebook" if k <= 32 and d <= 128 else "tcgen05 bf16 nomination, streamed codebook",
+            "peak": "measured copy GB/s / measured cuBLAS bf16 TFLOP/s (MEASURED_PEAKS.json)"}
 
 
 def main():

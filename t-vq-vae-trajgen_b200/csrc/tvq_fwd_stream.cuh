@@ -10,13 +10,13 @@
 // row on Gaussian data) are re-scored in fp32 and, if still inseparable, in fp64.  Indices are
 // therefore bit-identical to the CUDA-core path and to the C oracle.
 //
-// One persistent CTA per SM, 14 warps, warp-specialised; a row tile is 128 latents (UMMA M = 128:
+// One persistent CTA per SM, 12 warps, warp-specialised; a row tile is 128 latents (UMMA M = 128:
 // TMEM lane = latent), a code tile is NT codes (one tcgen05.mma N), d is cut into 64-column slabs:
 //   warp 0      producer: TMA (cp.async.bulk.tensor, SWIZZLE_128B) of bf16 code slabs [NT x 64]
 //               into a ring of shared-memory stages; also stages the |e|^2 slice of each code tile
 //   warp 1      MMA issuer: per code tile d/16 tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32, M = 128,
 //               N = NT) into one of 512/NT tensor-memory score slots; tcgen05.commit
-//   warps 2-9   scan + apply, TWO warps per TMEM lane quadrant (each takes half of the columns of every
+//   warps 4-11  scan + apply, TWO warps per TMEM lane quadrant (each takes half of the columns of every
 //               code tile), ONE THREAD PER LATENT: tcgen05.ld of 32 scores at a time, score =
 //               |e|^2 - 2 x.e (packed FFMA2), 3-input-min tree, running minimum m and threshold
 //               m + bound; a 32-score chunk is looked at again only if its minimum beats the threshold
@@ -24,7 +24,7 @@
 //               shared memory.  After the last code tile the two warps of a quadrant merge their minima,
 //               and each resolves 16 latents (cascade above), gathers the code words, writes idx / q
 //               (straight-through) / loss partial and adds the EMA statistics (red.global.v4).
-//   warps 10-13 converters: x rows fp32 (global, L2-prefetched two tiles ahead) -> bf16 A operand in
+//   warps 2-3   converters: x rows fp32 (global, L2-prefetched two tiles ahead) -> bf16 A operand in
 //               UMMA K-major SWIZZLE_128B layout, double buffered; also |x| -> the row's error bound.
 // Algorithmic cost per latent: 8d + 8 bytes of HBM (x is re-read once from L2 by the apply phase),
 // 2*k*d tensor FLOP.
@@ -43,19 +43,22 @@ namespace tvq {
 __device__ unsigned long long g_sprof[128];
 #define SP_DECL long long sp[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long sp_t = clock64(); (void)sp_t
 #define SP_WAIT(i, bar, par) do { long long _t = clock64(); mbar_wait(bar, par); sp[i] += clock64() - _t; } while (0)
+#define SP_WAITL(i, bar, par) do { long long _t = clock64(); mbar_wait_long(bar, par); sp[i] += clock64() - _t; } while (0)
 #define SP_LAP(i) do { long long _t = clock64(); sp[i] += _t - sp_t; sp_t = _t; } while (0)
 #define SP_RESET() do { sp_t = clock64(); } while (0)
 #define SP_DUMP(base) do { if (blockIdx.x == 0) for (int _i = 0; _i < 8; ++_i) g_sprof[(base) + _i] = (unsigned long long)sp[_i]; } while (0)
 #else
 #define SP_DECL do { } while (0)
 #define SP_WAIT(i, bar, par) mbar_wait(bar, par)
+#define SP_WAITL(i, bar, par) mbar_wait_long(bar, par)
 #define SP_LAP(i) do { } while (0)
 #define SP_RESET() do { } while (0)
 #define SP_DUMP(base) do { } while (0)
 #endif
 
 constexpr int kSM = 128;                 // latents per row tile
-constexpr int kSThreads = 448;           // 14 warps
+constexpr int kSThreads = 384;           // 12 warps: 168 registers per thread (the scan and apply phases need them)
+constexpr int kSCvtWarps = 2;            // converter warps (64 latents each)
 constexpr int kSScanWarps = 8;           // two per TMEM lane quadrant
 constexpr int kSCand = 8;                // candidate slots per latent and scan half
 constexpr int kSESlots = 8;              // |e|^2 slices in flight
@@ -80,7 +83,7 @@ __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stage
     u.brow = o;  o += kSBrowRing * kSM * 4;
     u.cs = o;    o += 2 * kSCand * kSM * 4;
     u.cc = o;    o += 2 * kSCand * kSM * 4;
-    u.drop = o;  o += 2 * kSM * 4;
+    u.drop = o;  o += 4 * kSM * 4;           // [half][spillmin | dropmin][latent]
     u.mfin = o;  o += 2 * kSM * 4;
     u.ncnt = o;  o += 2 * kSM * 4;
     u.ovf = o;   o += 2 * 4 * kSOvf * 12;       // [row-tile parity][quadrant]: rows | scores | codes
@@ -141,6 +144,8 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     asm("min.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
     return m;
 }
+template <int REGS> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 __device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
 }
@@ -154,13 +159,18 @@ struct OvfBuf {
     int* c;        // [kSOvf] code
 };
 
+// Scan state of one latent in one scan half (registers of the owning thread).
+struct ScanState {
+    float m;          // running minimum of the bf16 scores
+    int cnt;          // entries in the candidate list
+};
+
 // Candidate list of one latent and one scan half: kSCand slots, kSM words apart so that the 32 latents
 // of a warp never collide on a bank.  Called when the list is full: compact it against the current
 // threshold (which only ever decreases); if it is still full move the WORST entry to the quadrant's
-// spill buffer.  Only if that is full too is an entry really lost; the smallest lost score is
-// remembered, and the latent takes the exhaustive scan iff it lies inside the final threshold.
-// Returns the new count (< kSCand), | 0x100 if an entry was spilled.
-__device__ __noinline__ int cand_compact(const float thr, float* ls, int* lc, float* dropp, const OvfBuf ob, const int trow) {
+// spill buffer.  Only if that is full too is an entry really lost.  sd[0] / sd[kSM]: smallest spilled / lost
+// score of this latent and half (shared memory).  Returns the new count (<= kSCand - 1).
+__device__ __noinline__ int cand_compact(const float thr, float* ls, int* lc, float* sd, const OvfBuf ob, const int trow) {
     int kept = 0;
     for (int i = 0; i < kSCand; ++i) {
         const float v = ls[i * kSM];
@@ -175,18 +185,18 @@ __device__ __noinline__ int cand_compact(const float thr, float* ls, int* lc, fl
             if (v > vmax) { vmax = v; imax = i; }
         }
         const int pos = atomicAdd(ob.n, 1);
-        if (pos < kSOvf) { ob.row[pos] = trow; ob.s[pos] = vmax; ob.c[pos] = lc[imax * kSM]; }
-        else *dropp = fminf(*dropp, vmax);
+        if (pos < kSOvf) { ob.row[pos] = trow; ob.s[pos] = vmax; ob.c[pos] = lc[imax * kSM]; sd[0] = fminf(sd[0], vmax); }
+        else sd[kSM] = fminf(sd[kSM], vmax);
         ls[imax * kSM] = ls[(kSCand - 1) * kSM];
         lc[imax * kSM] = lc[(kSCand - 1) * kSM];
-        kept = (kSCand - 1) | 0x100;
+        kept = kSCand - 1;
     }
     return kept;
 }
 
 // One chunk of 32 scores of ONE latent (this thread's TMEM lane).
 __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const float4* e2c, const int code0, const float brow,
-                                           float& m, int& cnt, float* ls, int* lc, float* dropp, const OvfBuf& ob, const int trow) {
+                                           ScanState& st, float* ls, int* lc, float* sd, const OvfBuf& ob, const int trow) {
     using namespace sm100;
     float s[32];
 #pragma unroll
@@ -199,8 +209,8 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const float4
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = fminf(fmin3(s[4 * i], s[4 * i + 1], s[4 * i + 2]), s[4 * i + 3]);
     const float cmin = fmin3(fmin3(g[0], g[1], g[2]), fmin3(g[3], g[4], g[5]), fminf(g[6], g[7]));
-    m = fminf(m, cmin);
-    const float thr = m + brow;
+    st.m = fminf(st.m, cmin);
+    const float thr = st.m + brow;
     if (cmin <= thr) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -208,14 +218,49 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const float4
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (s[4 * i + j] <= thr) {
-                        if ((cnt & 0xff) == kSCand) cnt = cand_compact(thr, ls, lc, dropp, ob, trow) | (cnt & 0x100);
-                        ls[(cnt & 0xff) * kSM] = s[4 * i + j];
-                        lc[(cnt & 0xff) * kSM] = code0 + 4 * i + j;
-                        ++cnt;
+                        if (st.cnt == kSCand) st.cnt = cand_compact(thr, ls, lc, sd, ob, trow);
+                        ls[st.cnt * kSM] = s[4 * i + j];
+                        lc[st.cnt * kSM] = code0 + 4 * i + j;
+                        ++st.cnt;
                     }
                 }
             }
         }
+    }
+}
+
+// Straight-through output, commitment-loss partial, EMA statistics and q store of ONE latent
+// (all 32 lanes; lane l holds 16-byte chunks l and l + 32 of x and of the chosen code word).
+template <int NV, bool TRAIN>
+__device__ __forceinline__ void apply_row(const FwdParams& p, float* esum, const float4 xa, const float4 xb, const float4 wa,
+                                          const float4 wb, const int code, const int64_t grow, const bool h0, const bool h1,
+                                          const int lane, float& loss) {
+    float4 oa = wa, ob = wb;
+    if (TRAIN) {
+        // x + (e - x): two rounded fp32 ops, never contracted; the loss is taken on that rounded tensor,
+        // as F.mse_loss(quantize.detach(), x) does
+        oa.x = __fadd_rn(xa.x, __fsub_rn(wa.x, xa.x));
+        oa.y = __fadd_rn(xa.y, __fsub_rn(wa.y, xa.y));
+        oa.z = __fadd_rn(xa.z, __fsub_rn(wa.z, xa.z));
+        oa.w = __fadd_rn(xa.w, __fsub_rn(wa.w, xa.w));
+        const float dx = __fsub_rn(oa.x, xa.x), dy = __fsub_rn(oa.y, xa.y), dz = __fsub_rn(oa.z, xa.z), dw = __fsub_rn(oa.w, xa.w);
+        loss = fmaf(dx, dx, loss); loss = fmaf(dy, dy, loss); loss = fmaf(dz, dz, loss); loss = fmaf(dw, dw, loss);
+        if (NV > 1) {
+            ob.x = __fadd_rn(xb.x, __fsub_rn(wb.x, xb.x));
+            ob.y = __fadd_rn(xb.y, __fsub_rn(wb.y, xb.y));
+            ob.z = __fadd_rn(xb.z, __fsub_rn(wb.z, xb.z));
+            ob.w = __fadd_rn(xb.w, __fsub_rn(wb.w, xb.w));
+            const float ex = __fsub_rn(ob.x, xb.x), ey = __fsub_rn(ob.y, xb.y), ez = __fsub_rn(ob.z, xb.z), ew = __fsub_rn(ob.w, xb.w);
+            loss = fmaf(ex, ex, loss); loss = fmaf(ey, ey, loss); loss = fmaf(ez, ez, loss); loss = fmaf(ew, ew, loss);
+        }
+        float* es_row = esum + (size_t)code * p.d;
+        if (h0) red_add_v4(es_row + 4 * lane, xa);
+        if (h1) red_add_v4(es_row + 4 * (lane + 32), xb);
+    }
+    if (p.q != nullptr) {
+        float* qr = p.q + (size_t)grow * p.d;
+        if (h0) st_stream_v4(qr + 4 * lane, oa);
+        if (h1) st_stream_v4(qr + 4 * (lane + 32), ob);
     }
 }
 
@@ -333,7 +378,6 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     float* brow_ring = reinterpret_cast<float*>(smem + pl.brow);
     float* cand_s = reinterpret_cast<float*>(smem + pl.cs);     // [half][slot][latent]
     int* cand_c = reinterpret_cast<int*>(smem + pl.cc);
-    float* drop = reinterpret_cast<float*>(smem + pl.drop);     // [half][latent]
     float* mfin = reinterpret_cast<float*>(smem + pl.mfin);     // [half][latent] minimum seen by each scan half
     int* ncnt = reinterpret_cast<int*>(smem + pl.ncnt);         // [half][latent] final candidates per half (-1: incomplete)
     int* ovf_base = reinterpret_cast<int*>(smem + pl.ovf);      // [parity][quadrant][rows | scores | codes][kSOvf]
@@ -358,10 +402,10 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     if (tid == 0) {
         for (int s = 0; s < kSMaxStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, kSCvtWarps); mbar_init(bar_aempty + 8 * s, 1); }
         for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, kSScanWarps); }
         for (int s = 0; s < kSESlots; ++s) { mbar_init(bar_efull + 8 * s, 1); mbar_init(bar_eempty + 8 * s, kSScanWarps); }
-        for (int s = 0; s < kSBrowRing; ++s) { mbar_init(bar_rfull + 8 * s, 4); mbar_init(bar_rempty + 8 * s, kSScanWarps); }
+        for (int s = 0; s < kSBrowRing; ++s) { mbar_init(bar_rfull + 8 * s, kSCvtWarps); mbar_init(bar_rempty + 8 * s, kSScanWarps); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_cb);
         for (int i = 4; i < 12; ++i) misc[i] = 0;           // spill counters [parity][quadrant]
@@ -444,10 +488,9 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
             SP_LAP(7);
             SP_DUMP(8);
         }
-    } else if (warp >= 2 + kSScanWarps) {
+    } else if (warp < 2 + kSCvtWarps) {
         // ============================================================ converters: x fp32 -> bf16 A operand, |x| -> bound
-        const int cw = warp - (2 + kSScanWarps);
-        const int rowbase = cw * 32;                          // this warp's 32 latents of the tile
+        const int cw = warp - 2;
         constexpr int U = 8;
         SP_DECL;
         int it = 0;
@@ -463,11 +506,14 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 }
             }
             const int rs = it & (kSBrowRing - 1);
-            SP_WAIT(0, bar_aempty + 8 * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+            SP_WAITL(0, bar_aempty + 8 * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
             SP_WAIT(1, bar_rempty + 8 * rs, (((uint32_t)(it / kSBrowRing)) & 1u) ^ 1u);
             SP_RESET();
             const uint32_t a0 = a_base + ab * pl.a_bytes;
             float* brow = brow_ring + rs * kSM;
+#pragma unroll 1
+            for (int blk = 0; blk < 128 / (32 * kSCvtWarps); ++blk) {
+            const int rowbase = (cw * (128 / (32 * kSCvtWarps)) + blk) * 32;   // 32 latents of the tile
 #pragma unroll 1
             for (int i0 = 0; i0 < F; i0 += U) {
                 float4 v[U];
@@ -528,6 +574,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                     }
                 }
             }
+            }
             fence_proxy_async_smem();                         // generic-proxy stores -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_afull + 8 * ab); mbar_arrive(bar_rfull + 8 * rs); }
@@ -537,14 +584,14 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     } else {
         // ============================================================ scan + apply warps (one thread per latent)
         const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;                     // which half of every code tile's columns this warp scans
+        const int half = (warp - 4) >> 2;                     // which half of every code tile's columns this warp scans
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (NT / 2));
         const int trow = quad * 32 + lane;                    // this thread's latent within the tile
         float* ls = cand_s + half * (kSCand * kSM) + trow;
         int* lc = cand_c + half * (kSCand * kSM) + trow;
-        float* dropp = drop + half * kSM + trow;
+        float* sd = reinterpret_cast<float*>(smem + pl.drop) + half * (2 * kSM) + trow;   // [0]: spillmin, [kSM]: dropmin
         float* thrfin = mfin;                                 // reused after the merge: final threshold per latent (half 0 slot)
-        int* scratch = scratch_base + (warp - 2) * kSScratch;
+        int* scratch = scratch_base + (warp - 4) * kSScratch;
         float* esum = p.stats + ((p.k + 3) & ~3);
         const bool h0 = lane < nchunk, h1 = NV > 1 && lane + 32 < nchunk;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -558,9 +605,9 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
             const float brow = brow_ring[rs * kSM + trow];
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);
-            float m = INF;
-            int cnt = 0;                                      // low 8 bits: list entries; 0x100: an entry was spilled
-            *dropp = INF;
+            ScanState st;
+            st.m = INF; st.cnt = 0;
+            sd[0] = INF; sd[kSM] = INF;
             OvfBuf ob;
             {
                 int* ob0 = ovf_base + ((it & 1) * 4 + quad) * (3 * kSOvf);
@@ -579,12 +626,16 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 const uint32_t taddr = lane_addr + (uint32_t)(slot * NT);
                 const float4* e2c = reinterpret_cast<const float4*>(e2s + es * NT + half * (NT / 2));
                 const int code0 = ct * NT + half * (NT / 2);
+                uint32_t ra[32], rb[32];
+                tmem_ld_x32(taddr, ra);
 #pragma unroll 1
-                for (int c = 0; c < NCH; ++c) {
-                    uint32_t r[32];
-                    tmem_ld_x32(taddr + (uint32_t)c * 32u, r);
+                for (int c = 0; c < NCH; c += 2) {          // the next chunk's tcgen05.ld is in flight while this one is scanned
                     tmem_ld_wait();
-                    scan_chunk(r, e2c + c * 8, code0 + c * 32, brow, m, cnt, ls, lc, dropp, ob, trow);
+                    tmem_ld_x32(taddr + (uint32_t)(c + 1) * 32u, rb);
+                    scan_chunk(ra, e2c + c * 8, code0 + c * 32, brow, st, ls, lc, sd, ob, trow);
+                    tmem_ld_wait();
+                    if (c + 2 < NCH) tmem_ld_x32(taddr + (uint32_t)(c + 2) * 32u, ra);
+                    scan_chunk(rb, e2c + (c + 1) * 8, code0 + (c + 1) * 32, brow, st, ls, lc, sd, ob, trow);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -593,21 +644,23 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
             }
             SP_RESET();
             // ---- merge the two halves of the quadrant: common minimum, then each half filters its own list
-            mfin[half * kSM + trow] = m;
+            mfin[half * kSM + trow] = st.m;
             named_bar_sync(1 + quad, 64);
-            const float thr_fin = fminf(m, mfin[(half ^ 1) * kSM + trow]) + brow;
+            const float thr_fin = fminf(st.m, mfin[(half ^ 1) * kSM + trow]) + brow;
             {
-                const int nl = cnt & 0xff;
                 int kept = 0;
-                for (int i = 0; i < nl; ++i) {
+                for (int i = 0; i < st.cnt; ++i) {
                     const float v = ls[i * kSM];
                     if (v <= thr_fin) { lc[kept * kSM] = lc[i * kSM]; ++kept; }
                 }
-                // a half is incomplete if it LOST a score inside the final threshold (or saw non-finite scores)
-                ncnt[half * kSM + trow] = (*dropp > thr_fin) ? (kept | (cnt & 0x100)) : -1;
+                // -1: a score inside the final threshold was LOST (or the scores were non-finite): exhaustive scan;
+                // 0x100: the spill buffer holds candidates of this latent
+                ncnt[half * kSM + trow] = (sd[kSM] > thr_fin) ? (kept | (sd[0] <= thr_fin ? 0x100 : 0)) : -1;
             }
             named_bar_sync(1 + quad, 64);
             if (half == 0) thrfin[trow] = thr_fin;            // (both halves have read mfin)
+            named_bar_sync(1 + quad, 64);
+            SP_LAP(4);
             // ---- resolve + apply: all 32 lanes on one latent, R latents in flight, ONE round trip to L2:
             //      x rows, the first candidate's code word and (for ambiguous latents) candidates 2-4 are
             //      all requested before anything is used.  This warp takes 16 latents of its quadrant.
@@ -615,6 +668,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
             const int64_t wrow0 = (int64_t)tile * kSM + lrow0;
             int mycode = 0;
             float loss = 0.f;
+            unsigned gen_mask = 0;                            // latents left to the general path (second pass)
 #pragma unroll 1
             for (int b = 0; b < 16 / R; ++b) {
                 if (wrow0 + R * b >= p.n) break;              // warp-uniform
@@ -629,8 +683,9 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                     valid[u] = grow < p.n;
                     const int n0r = ncnt[lrow], n1r = ncnt[kSM + lrow];
                     const int n0 = n0r & 0xff, n1 = n1r & 0xff;
-                    // -1: exhaustive scan; 100: general path over lists + spill buffer; else the merged count
-                    nc[u] = (n0r < 0 || n1r < 0 || n0 + n1 == 0) ? -1 : ((n0r | n1r) & 0x100) ? 100 : n0 + n1;
+                    // 1..4: the merged count, resolved right here; anything else: general path
+                    nc[u] = (n0r < 0 || n1r < 0 || ((n0r | n1r) & 0x100) || n0 + n1 == 0 || n0 + n1 > 4) ? 0 : n0 + n1;
+                    if (valid[u] && nc[u] == 0) gen_mask |= 1u << (R * b + u);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         // candidate j of the merged list: half 0's entries first, then half 1's
@@ -644,7 +699,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         ea[u][j] = z4; eb[u][j] = z4; e2v[u][j] = 0.f;
-                        if (j == 0 || (j < nc[u] && nc[u] <= 4)) {
+                        if (j < nc[u]) {
                             const float4* er = reinterpret_cast<const float4*>(p.cb + (size_t)cc[u][j] * p.d);
                             if (h0) ea[u][j] = __ldg(er + lane);
                             if (h1) eb[u][j] = __ldg(er + lane + 32);
@@ -652,13 +707,10 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                         }
                     }
                 }
-                int cd[R];
-                float4 wa[R], wb[R];
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
                     int sel = 0;
-                    cd[u] = cc[u][0];
-                    if (valid[u] && nc[u] >= 2 && nc[u] <= 4) {
+                    if (valid[u] && nc[u] >= 2) {
                         // fp32 re-score of the (<= 4) candidates, all lanes on this latent
                         n_resc += 1u;
                         float dd[4];
@@ -705,68 +757,46 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                                 }
                             }
                         }
-                        cd[u] = sel == 0 ? cc[u][0] : sel == 1 ? cc[u][1] : sel == 2 ? cc[u][2] : cc[u][3];
                     }
-                    wa[u] = sel == 0 ? ea[u][0] : sel == 1 ? ea[u][1] : sel == 2 ? ea[u][2] : ea[u][3];
-                    wb[u] = sel == 0 ? eb[u][0] : sel == 1 ? eb[u][1] : sel == 2 ? eb[u][2] : eb[u][3];
-                    if (valid[u] && (nc[u] < 1 || nc[u] > 4)) {
-                        // rare: long candidate list or exhaustive scan, then a second trip for the code word
-                        const int lrow = lrow0 + R * b + u;
-                        int ncg = nc[u];
-                        if (ncg > 0) ncg = gather_cands(scratch, ncnt[lrow] & 0xff, ncnt[kSM + lrow] & 0xff, cand_c + lrow, ob, lrow,
-                                                        thrfin[lrow], lane);
-                        const int r = resolve_stream<NV>(xa[u], xb[u], ncg, scratch, p.cb, p.e2, p.k, p.d, emax, lane);
-                        __syncwarp();
-                        n_resc += 1u;
-                        n_f64 += (unsigned)(r >> 30);
-                        int code = r & 0x3fffffff;
-                        code = code < p.k ? code : 0;
-                        cd[u] = code;
-                        const float4* er = reinterpret_cast<const float4*>(p.cb + (size_t)code * p.d);
-                        wa[u] = h0 ? __ldg(er + lane) : z4;
-                        wb[u] = h1 ? __ldg(er + lane + 32) : z4;
+                    if (valid[u] && nc[u] >= 1) {
+                        const int code = sel == 0 ? cc[u][0] : sel == 1 ? cc[u][1] : sel == 2 ? cc[u][2] : cc[u][3];
+                        const float4 wa = sel == 0 ? ea[u][0] : sel == 1 ? ea[u][1] : sel == 2 ? ea[u][2] : ea[u][3];
+                        const float4 wb = sel == 0 ? eb[u][0] : sel == 1 ? eb[u][1] : sel == 2 ? eb[u][2] : eb[u][3];
+                        if (p.q != nullptr || TRAIN)
+                            apply_row<NV, TRAIN>(p, esum, xa[u], xb[u], wa, wb, code, wrow0 + R * b + u, h0, h1, lane, loss);
+                        mycode = (lane == R * b + u) ? code : mycode;
                     }
                 }
+            }
+            // ---- second pass (rare): long merged lists, spilled candidates, exhaustive scans — one latent at a time
+#pragma unroll 1
+            while (gen_mask) {
+                const int r = __ffs(gen_mask) - 1;
+                gen_mask &= gen_mask - 1;
+                const int lrow = lrow0 + r;
+                const int64_t grow = wrow0 + r;
+                const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)grow * p.d);
+                const float4 xa = h0 ? __ldg(xr + lane) : z4;
+                const float4 xb = h1 ? __ldg(xr + lane + 32) : z4;
+                const int n0r = ncnt[lrow], n1r = ncnt[kSM + lrow];
+                int ncg = -1;
+                if (n0r >= 0 && n1r >= 0) {
+                    ncg = gather_cands(scratch, n0r & 0xff, n1r & 0xff, cand_c + lrow, ob, lrow, thrfin[lrow], lane);
+                    if (ncg == 0) ncg = -1;
+                }
+                const int rr = resolve_stream<NV>(xa, xb, ncg, scratch, p.cb, p.e2, p.k, p.d, emax, lane);
+                __syncwarp();
+                n_resc += 1u;
+                n_f64 += (unsigned)(rr >> 30);
+                int code = rr & 0x3fffffff;
+                code = code < p.k ? code : 0;
                 if (p.q != nullptr || TRAIN) {
-#pragma unroll
-                    for (int u = 0; u < R; ++u) {
-                        if (!valid[u]) continue;
-                        const int64_t grow = wrow0 + R * b + u;
-                        float4 oa = wa[u], ob = wb[u];
-                        if (TRAIN) {
-                            // x + (e - x): two rounded fp32 ops, never contracted; the loss is taken on
-                            // that rounded tensor, as F.mse_loss(quantize.detach(), x) does
-                            oa.x = __fadd_rn(xa[u].x, __fsub_rn(wa[u].x, xa[u].x));
-                            oa.y = __fadd_rn(xa[u].y, __fsub_rn(wa[u].y, xa[u].y));
-                            oa.z = __fadd_rn(xa[u].z, __fsub_rn(wa[u].z, xa[u].z));
-                            oa.w = __fadd_rn(xa[u].w, __fsub_rn(wa[u].w, xa[u].w));
-                            const float dx = __fsub_rn(oa.x, xa[u].x), dy = __fsub_rn(oa.y, xa[u].y);
-                            const float dz = __fsub_rn(oa.z, xa[u].z), dw = __fsub_rn(oa.w, xa[u].w);
-                            loss = fmaf(dx, dx, loss); loss = fmaf(dy, dy, loss);
-                            loss = fmaf(dz, dz, loss); loss = fmaf(dw, dw, loss);
-                            if (NV > 1) {
-                                ob.x = __fadd_rn(xb[u].x, __fsub_rn(wb[u].x, xb[u].x));
-                                ob.y = __fadd_rn(xb[u].y, __fsub_rn(wb[u].y, xb[u].y));
-                                ob.z = __fadd_rn(xb[u].z, __fsub_rn(wb[u].z, xb[u].z));
-                                ob.w = __fadd_rn(xb[u].w, __fsub_rn(wb[u].w, xb[u].w));
-                                const float ex = __fsub_rn(ob.x, xb[u].x), ey = __fsub_rn(ob.y, xb[u].y);
-                                const float ez = __fsub_rn(ob.z, xb[u].z), ew = __fsub_rn(ob.w, xb[u].w);
-                                loss = fmaf(ex, ex, loss); loss = fmaf(ey, ey, loss);
-                                loss = fmaf(ez, ez, loss); loss = fmaf(ew, ew, loss);
-                            }
-                            float* es_row = esum + (size_t)cd[u] * p.d;
-                            if (h0) red_add_v4(es_row + 4 * lane, xa[u]);
-                            if (h1) red_add_v4(es_row + 4 * (lane + 32), xb[u]);
-                        }
-                        if (p.q != nullptr) {
-                            float* qr = p.q + (size_t)grow * p.d;
-                            if (h0) st_stream_v4(qr + 4 * lane, oa);
-                            if (h1) st_stream_v4(qr + 4 * (lane + 32), ob);
-                        }
-                    }
+                    const float4* er = reinterpret_cast<const float4*>(p.cb + (size_t)code * p.d);
+                    const float4 wa = h0 ? __ldg(er + lane) : z4;
+                    const float4 wb = h1 ? __ldg(er + lane + 32) : z4;
+                    apply_row<NV, TRAIN>(p, esum, xa, xb, wa, wb, code, grow, h0, h1, lane, loss);
                 }
-#pragma unroll
-                for (int u = 0; u < R; ++u) mycode = (lane == R * b + u) ? cd[u] : mycode;
+                mycode = (lane == r) ? code : mycode;
             }
             if (lane < 16 && wrow0 + lane < p.n) {
                 p.idx[wrow0 + lane] = (int64_t)mycode;
@@ -777,8 +807,8 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
             named_bar_sync(1 + quad, 64);                     // the quadrant's lists are reused by the next row tile
             SP_LAP(5);
         }
-        if (warp == 2 && lane == 0) SP_DUMP(16);
-        if (lane == 0) SP_DUMP(64 + 8 * (warp - 2));
+        if (warp == 4 && lane == 0) SP_DUMP(16);
+        if (lane == 0) SP_DUMP(64 + 8 * (warp - 4));
     }
 
     // ------------------------------------------------------------------ teardown

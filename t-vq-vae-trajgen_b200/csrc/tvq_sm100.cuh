@@ -43,12 +43,28 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // never a hung GPU.  The bound is wall time (4 s), far above any legitimate wait of these kernels.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = globaltimer_ns();
+    uint64_t t0 = 0;
     for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
-        // try_wait itself parks the thread for a while; the extra sleep keeps a long wait (a converter
-        // waiting for a whole row tile) from competing for issue slots with the working warps
-        if (spin > 4) __nanosleep(spin > 64 ? 256 : 32);
-        if ((spin & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+        // (try_wait parks the thread until the barrier moves or a hardware time limit expires)
+        if (spin > 8) __nanosleep(64);
+        if ((spin & 0x3fffu) == 0) {
+            const uint64_t t = globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+// The same for waits known to last a whole row tile (converters): poll rarely, leave the issue slots to the others.
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = 0;
+    for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+        __nanosleep(1000);
+        if ((spin & 0xfffu) == 0) {
+            const uint64_t t = globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull) __trap();
+        }
     }
 }
 

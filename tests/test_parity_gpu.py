@@ -407,10 +407,12 @@ def test_full_size_properties(tvq, n, k, d):
     idx_e, _, _ = tvq.vq_forward_raw(x, e, ws, train=False, write_q=False)
     assert torch.equal(idx_e, idx)
     rescored = int(sc.view(torch.int32)[4])
-    # fp32 nomination (k > 64): a handful of rows; tf32 nomination (k <= 64): the rigorous 2^-9 bound
-    # sends ~10 % of Gaussian rows to the re-score
-    limit = 0.25 * n if k <= 64 else 0.02 * n
-    assert rescored < limit, f"{rescored} of {n} rows needed the fp64 re-score"
+    # tf32 nomination (resident codebook, k <= 64): the rigorous 2^-9 bound sends ~10 % of Gaussian rows to
+    # the re-score; bf16 nomination (streamed codebook): 25-45 % get the fp32 re-score of 2-4 candidates
+    #  and only a handful need fp64
+    limit = 0.25 * n if k <= 64 else 0.6 * n
+    assert rescored < limit, f"{rescored} of {n} rows were re-scored"
+    assert int(sc.view(torch.int32)[5]) < 0.01 * n, "too many rows needed the fp64 level"
 
 
 # ----------------------------------------------- tcgen05 path vs CUDA-core path (same canonical rule)
@@ -440,3 +442,57 @@ def test_umma_path_equals_simt_path(tvq, n, k, d, train):
         close(sc_u[0], sc_s[0], what="commit")
     if n <= 5000:
         assert np.array_equal(idx_u.cpu().numpy(), C.assign(x.cpu().numpy(), e.cpu().numpy()))
+
+
+# ------------------------------------ streamed-codebook tcgen05 path vs CUDA-core path (same canonical rule)
+
+STREAM_CASES = [(128, 64, 64), (130, 100, 128), (1000, 256, 64), (777, 33, 64), (5000, 100, 100), (600, 16, 256),
+                (3000, 512, 64), (2049, 1000, 128), (1500, 70, 256), (4096, 2500, 32), (20000, 4096, 128), (9000, 777, 252),
+                (300000, 512, 64), (70000, 16384, 256)]
+
+
+@pytest.mark.parametrize("n,k,d", STREAM_CASES)
+@pytest.mark.parametrize("train", [True, False])
+def test_stream_path_equals_simt_path(tvq, n, k, d, train):
+    """Every shape outside the resident-codebook path runs the streamed-codebook tcgen05 kernel (bf16
+    nomination on the tensor cores, candidate lists, canonical fp32/fp64 resolution).  Forcing the
+    CUDA-core path must give identical indices, q and counts, and the same sums; up to 20 000 rows the
+    indices are also compared with the C oracle bit for bit."""
+    torch.manual_seed(n + k + d)
+    x = (torch.randn(n, d) * 1.3 + 0.2).to(DEV)
+    e = torch.randn(k, d).to(DEV)
+    ws = tvq.Workspace(k, d, torch.device(DEV))
+    off = tvq.stats_offset(k)
+    idx_u, q_u, sc_u = tvq.vq_forward_raw(x, e, ws, train=train)
+    st_u = ws.stats.clone()
+    idx_s, q_s, sc_s = tvq.vq_forward_raw(x, e, ws, train=train, flags=tvq._lib.F_NO_UMMA)
+    st_s = ws.stats.clone()
+    torch.cuda.synchronize()
+    assert torch.equal(idx_u, idx_s)
+    assert torch.equal(q_u, q_s)
+    assert torch.equal(st_u[:k], st_s[:k])
+    close(sc_u[1], sc_s[1], what="perplexity")
+    if train:
+        close(st_u[off:], st_s[off:], what="embed_sum")
+        close(sc_u[0], sc_s[0], what="commit")
+    if n <= 20000:
+        assert np.array_equal(idx_u.cpu().numpy(), C.assign(x.cpu().numpy(), e.cpu().numpy()))
+
+
+@pytest.mark.parametrize("n,k,d,dup,noise", [(3000, 640, 64, 20, 0.0), (2000, 1020, 128, 6, 0.0), (4000, 2040, 128, 12, 1e-3),
+                                             (1500, 480, 256, 40, 0.0)])
+def test_stream_path_duplicated_codes(tvq, n, k, d, dup, noise):
+    """Duplicated / nearly duplicated code words: every latent has dozens of codes inside the bf16 error
+    bound, so the candidate lists overflow into the spill buffer and, beyond it, into the exhaustive scan.
+    The first index among equal distances must still win, exactly as torch.argmax does."""
+    torch.manual_seed(n + k)
+    base = torch.randn(k // dup, d)
+    e = (base.repeat_interleave(dup, 0) + noise * torch.randn(k, d)).to(DEV)
+    x = torch.randn(n, d).to(DEV)
+    ws = tvq.Workspace(k, d, torch.device(DEV))
+    idx_u, q_u, sc_u = tvq.vq_forward_raw(x, e, ws, train=True)
+    idx_s, q_s, _ = tvq.vq_forward_raw(x, e, ws, train=True, flags=tvq._lib.F_NO_UMMA)
+    assert torch.equal(idx_u, idx_s) and torch.equal(q_u, q_s)
+    assert np.array_equal(idx_u.cpu().numpy(), C.assign(x.cpu().numpy(), e.cpu().numpy()))
+    if noise == 0.0:
+        assert bool((idx_u % dup == 0).all()), "exact duplicates: the first copy must be chosen"

@@ -46,7 +46,7 @@ def run(n, k, d, train):
     show("mma", 8, ["wait_a_full", "wait_t_empty", "wait_b_full", "", "", "", "", "total"])
     show("scan w2", 16, ["wait_rows", "wait_e2", "wait_t_full", "scan", "merge", "apply", "", ""])
     show("convert", 24, ["wait_a_empty", "wait_r_empty", "work", "", "", "", "", ""])
-    for w in range(8):
+    for w in range(0):
         show(f"scan w{w+2}", 64 + 8 * w, ["wait_rows", "wait_e2", "wait_t_full", "scan", "merge", "apply", "", ""])
 
 if __name__ == "__main__":
