@@ -58,11 +58,17 @@ TVQ_API const char *tvq_error_string(int code);
 /* 0 if `device` is compute capability 10.x; fills sm_count (may be NULL). */
 TVQ_API int tvq_device_check(int device, int *sm_count);
 
-/* Bytes of scratch for (n, k, d): header + per-code constants + tvq_train_step's statistics.
+/* Bytes of scratch for (n, k, d): header + per-code constants (|e|^2 padded to a multiple of 256)
+ * + tvq_train_step's statistics + the bf16 copy of the codebook that the streamed-codebook tcgen05
+ * path feeds to TMA (k x roundup(d, 64..256) x 2 bytes, rewritten by every call).
  * The scratch must be zero-filled ONCE when allocated (it holds a launch ticket). */
 TVQ_API size_t tvq_workspace_bytes(int64_t n, int k, int d);
 
 /* Distance + assignment (+ gather / straight-through / loss / EMA statistics).
+ *   Kernel selection: k <= 32 (train) / <= 64 (eval) and d <= 128: codebook resident in shared memory,
+ *   tcgen05 tf32 scoring; every other shape: codebook streamed by TMA, tcgen05 bf16 scoring; the
+ *   TVQ_F_EXACT / TVQ_F_NO_UMMA / TVQ_F_GIVEN_IDX flags select the CUDA-core kernel.  All three decide
+ *   by the same canonical fp32/fp64 rule, so the indices do not depend on the path.
  *   Replaces EuclideanCodebook.forward vq.py:210-234 and the ST + commit-loss lines
  *   VectorQuantize.forward vq.py:357-366, for temperature 0.
  *   idx      out [n]
