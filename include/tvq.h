@@ -105,6 +105,22 @@ TVQ_API int tvq_ema_update(const float *stats, float *cluster_size, float *embed
                    float *embed_prev, int k, int d, double decay, double eps, void *workspace,
                    size_t workspace_bytes, void *stream);
 
+/* Data-parallel EMA update in ONE kernel (no NCCL call): one-shot all-reduce of the packed statistics
+ * over NVLink peer memory fused with the EMA update — the reference's two all_reduce hooks
+ * (vq.py:229, :234) plus vq.py:231, :236-242.
+ *   peer_bufs  DEVICE array of `world` pointers: peer_bufs[r] is rank r's exchange buffer of
+ *              tvq_exchange_bytes(k, d, world) bytes, allocated symmetrically, mapped by every rank
+ *              (e.g. torch.distributed._symmetric_memory) and zero-filled ONCE before the first call.
+ *   Every rank must call it the same number of times (the step counter lives in the buffer, so the
+ *   launch can be replayed from a CUDA graph).  Slots are added in rank order on every rank, so the
+ *   replicas stay bit-identical.  Statistics of at most 65 536 floats (TVQ_ERR_UNSUPPORTED beyond:
+ *   use an all-reduce + tvq_ema_update).  stats (this rank's, from tvq_forward) must be padded to a
+ *   multiple of 4 floats (TVQ_STATS_LEN rounded up).                                              */
+TVQ_API size_t tvq_exchange_bytes(int k, int d, int world);
+TVQ_API int tvq_ema_update_dp(const float *stats, void *const *peer_bufs, int rank, int world,
+                      float *cluster_size, float *embed_avg, float *embed, float *embed_prev, int k,
+                      int d, double decay, double eps, void *stream);
+
 /* Backward of the train forward (autograd through vq.py:357-366):
  *   g_x = g_q + (g_commit + commitment_weight * g_weighted) * 2/(n*d) * (x - q_st)
  *   with q_st recomputed from x, idx and the codebook the forward used.  g_commit / g_weighted

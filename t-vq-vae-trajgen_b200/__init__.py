@@ -6,11 +6,12 @@ ABI of include/tvq.h.  The directory name carries the project name (`t-vq-vae-tr
 import it as `tvq_b200` through the loader module of that name at the repository root.
 """
 from . import _lib
-from .functional import (VQTrainStep, Workspace, stats_len, stats_offset, vq_backward, vq_ema_update,
+from .functional import (PeerExchange, VQTrainStep, Workspace, stats_len, stats_offset, vq_backward, vq_ema_update,
+                         vq_ema_update_dp,
                          vq_forward_raw, vq_gather, vq_neg_dist, vq_reseed, vq_train_step_raw)
 from .glue import decode_tokens, quantize
 from .vq import EuclideanCodebook, VectorQuantize
 
-__all__ = ["VectorQuantize", "EuclideanCodebook", "quantize", "decode_tokens", "vq_forward_raw", "vq_ema_update",
+__all__ = ["VectorQuantize", "EuclideanCodebook", "quantize", "decode_tokens", "vq_forward_raw", "vq_ema_update", "vq_ema_update_dp", "PeerExchange",
            "vq_train_step_raw", "vq_backward", "vq_gather", "vq_neg_dist", "vq_reseed", "Workspace", "VQTrainStep", "stats_len",
            "stats_offset", "_lib"]

@@ -421,6 +421,36 @@ int tvq_ema_update(const float* stats, float* cluster_size, float* embed_avg, fl
     return launch_status();
 }
 
+size_t tvq_exchange_bytes(int k, int d, int world) {
+    if (k < 1 || d < 4 || world < 1) return 0;
+    const size_t len4 = ((size_t)TVQ_STATS_LEN(k, d) + 3) / 4;
+    return 64 + (((size_t)2 * world * 4 + 63) & ~(size_t)63) + (size_t)2 * world * len4 * 16;
+}
+
+int tvq_ema_update_dp(const float* stats, void* const* peer_bufs, int rank, int world, float* cluster_size, float* embed_avg,
+                      float* embed, float* embed_prev, int k, int d, double decay, double eps, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (k < 1 || d < 4 || (d & 3) || world < 1 || world > 64 || rank < 0 || rank >= world) return TVQ_ERR_UNSUPPORTED;
+    if (TVQ_STATS_LEN(k, d) > (int64_t(1) << 16)) return TVQ_ERR_UNSUPPORTED;   // one CTA: small statistics only
+    if (!stats || !peer_bufs || !cluster_size || !embed_avg || !embed) return TVQ_ERR_BAD_ARG;
+    if (!aligned16(stats) || !aligned16(embed_avg) || !aligned16(embed) || (embed_prev && !aligned16(embed_prev))) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    EmaDpParams p;
+    p.e.stats = stats; p.e.cluster_size = cluster_size; p.e.embed_avg = embed_avg; p.e.embed = embed; p.e.embed_prev = embed_prev;
+    p.e.k = k; p.e.d = d;
+    p.e.decay = (float)decay;
+    p.e.one_minus_decay = (float)(1.0 - decay);
+    p.e.eps = (float)eps;
+    p.e.k_eps = (float)((double)k * eps);
+    p.e.hdr = nullptr;
+    p.peers = peer_bufs; p.rank = rank; p.world = world;
+    p.len4 = (TVQ_STATS_LEN(k, d) + 3) / 4;
+    ema_dp_kernel<<<1, 1024, 0, stream>>>(p);
+    return launch_status();
+}
+
 int tvq_backward(const float* g_q, const float* g_commit, const float* g_weighted, const float* x, const int64_t* idx,
                  const float* codebook, int64_t n, int k, int d, float commitment_weight, float* g_x, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -125,6 +125,121 @@ __global__ void __launch_bounds__(256) ema_kernel(const EmaParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Data-parallel EMA update in ONE kernel: a one-shot all-reduce of the packed statistics over NVLink
+// peer memory, fused with the EMA update (the reference's two dormant all_reduce hooks, vq.py:229 and
+// :234, followed by :231 and :236-242).  Every rank owns an exchange buffer that all peers have mapped:
+//   header (64 B, local only: launch counter) | flags [2 parities][world] u32 | slots [2][world][len4] fp32
+// Step e (parity e & 1): push my statistics into slot [parity][rank] of EVERY rank's buffer (posted
+// remote stores), fence, publish flag = e on every rank, wait until all `world` local flags show e, then
+// add the slots in rank order — the same order on every rank, so the replicas stay bit-identical — and
+// apply the update.  Two parities suffice: a rank can only run one step ahead of the slowest peer
+// (its next step needs that peer's flag of the current one).
+// One CTA (statistics of <= 64 Ki floats); the launch counter lives in device memory so the kernel can be
+// replayed from a CUDA graph.
+struct EmaDpParams {
+    EmaParams e;                 // e.stats = this rank's local statistics (read), buffers updated in place
+    void* const* peers;          // device array [world]: every rank's exchange buffer
+    int rank, world;
+    int64_t len4;                // statistics length in float4 (padded)
+};
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) ema_dp_kernel(const EmaDpParams p) {
+    __shared__ double red[32];
+    __shared__ float s_n;
+    __shared__ unsigned s_epoch;
+    const int tid = threadIdx.x;
+    unsigned char* mine = reinterpret_cast<unsigned char*>(p.peers[p.rank]);
+    if (tid == 0) {
+        unsigned* counter = reinterpret_cast<unsigned*>(mine);
+        s_epoch = *counter + 1u;
+        *counter = s_epoch;
+    }
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const int par = (int)(epoch & 1u);
+    const size_t flags_off = 64, slots_off = 64 + (((size_t)2 * p.world * 4 + 63) & ~(size_t)63);
+    // ---- push
+    const float4* src = reinterpret_cast<const float4*>(p.e.stats);
+    for (int r = 0; r < p.world; ++r) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(p.peers[r]) + slots_off) +
+                      ((size_t)par * p.world + p.rank) * p.len4;
+        for (int64_t f = tid; f < p.len4; f += blockDim.x) dst[f] = src[f];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < p.world) {
+        unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(p.peers[tid]) + flags_off) + par * p.world + p.rank;
+        st_release_sys_u32(flag, epoch);
+        // ---- wait for every rank's contribution to MY buffer (bounded: a lost peer becomes an error, not a hang)
+        const unsigned* lf = reinterpret_cast<const unsigned*>(mine + flags_off) + par * p.world + tid;
+        unsigned long long t0 = 0;
+        for (unsigned spin = 1; ld_acquire_sys_u32(lf) != epoch; ++spin) {
+            if ((spin & 0x3ffu) == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 10000000000ull) __trap();
+            }
+        }
+    }
+    __syncthreads();
+    // ---- reduce (rank order) + EMA update
+    const float4* slots = reinterpret_cast<const float4*>(mine + slots_off) + (size_t)par * p.world * p.len4;
+    const int kp = (p.e.k + 3) & ~3;
+    const int dq = p.e.d >> 2;
+    double part = 0.0;
+    for (int c = tid; c < p.e.k; c += blockDim.x) {
+        float cnt = 0.f;
+        for (int r = 0; r < p.world; ++r) cnt += __ldcg(reinterpret_cast<const float*>(slots + (size_t)r * p.len4) + c);
+        part += (double)ema_mix(p.e.cluster_size[c], cnt, p.e.decay, p.e.one_minus_decay);
+    }
+    double tot = block_sum(part, red);
+    if (tid == 0) s_n = __double2float_rn(tot);
+    __syncthreads();
+    const float n = s_n;
+    const float denom = __fadd_rn(n, p.e.k_eps);
+    float4* avg4 = reinterpret_cast<float4*>(p.e.embed_avg);
+    float4* emb4 = reinterpret_cast<float4*>(p.e.embed);
+    float4* prev4 = reinterpret_cast<float4*>(p.e.embed_prev);
+    for (int64_t f = tid; f < (int64_t)p.e.k * dq; f += blockDim.x) {
+        const int c = (int)(f / dq);
+        float cnt = 0.f;
+        float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < p.world; ++r) {
+            const float4* sl = slots + (size_t)r * p.len4;
+            cnt += __ldcg(reinterpret_cast<const float*>(sl) + c);
+            const float4 v = __ldcg(sl + (kp >> 2) + f);
+            sv.x += v.x; sv.y += v.y; sv.z += v.z; sv.w += v.w;
+        }
+        const float cs = ema_mix(p.e.cluster_size[c], cnt, p.e.decay, p.e.one_minus_decay);
+        const float sm = __fmul_rn(__fdiv_rn(__fadd_rn(cs, p.e.eps), denom), n);
+        float4 a = avg4[f];
+        a.x = ema_mix(a.x, sv.x, p.e.decay, p.e.one_minus_decay);
+        a.y = ema_mix(a.y, sv.y, p.e.decay, p.e.one_minus_decay);
+        a.z = ema_mix(a.z, sv.z, p.e.decay, p.e.one_minus_decay);
+        a.w = ema_mix(a.w, sv.w, p.e.decay, p.e.one_minus_decay);
+        avg4[f] = a;
+        if (prev4) prev4[f] = emb4[f];
+        emb4[f] = make_float4(__fdiv_rn(a.x, sm), __fdiv_rn(a.y, sm), __fdiv_rn(a.z, sm), __fdiv_rn(a.w, sm));
+    }
+    __syncthreads();                                      // every thread has read the old cluster sizes
+    for (int c = tid; c < p.e.k; c += blockDim.x) {
+        float cnt = 0.f;
+        for (int r = 0; r < p.world; ++r) cnt += __ldcg(reinterpret_cast<const float*>(slots + (size_t)r * p.len4) + c);
+        p.e.cluster_size[c] = ema_mix(p.e.cluster_size[c], cnt, p.e.decay, p.e.one_minus_decay);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Backward: g_x = g_q + coef * (x - q_st), coef = g_loss * w * 2 / (n*d); q_st = x + (e[idx]-x).
 // 12d + 8 bytes per latent (the code word comes from the L2-resident codebook).
 __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__ g_q, const float* __restrict__ g_commit,

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["Workspace", "vq_forward_raw", "vq_train_step_raw", "vq_ema_update", "vq_backward", "vq_gather", "vq_neg_dist",
+__all__ = ["Workspace", "vq_forward_raw", "vq_train_step_raw", "vq_ema_update", "PeerExchange", "vq_ema_update_dp", "vq_backward", "vq_gather", "vq_neg_dist",
            "vq_reseed", "stats_offset", "stats_len", "VQTrainStep"]
 
 
@@ -95,6 +95,48 @@ def vq_ema_update(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg: to
                                     embed_prev.data_ptr() if embed_prev is not None else None, k, d, float(decay),
                                     float(eps), ws.buf.data_ptr(), ws.nbytes, _stream())
     _lib.check(rc, "tvq_ema_update")
+
+
+class PeerExchange:
+    """Per-codebook exchange buffers for the fused NVLink all-reduce + EMA kernel (tvq_ema_update_dp).
+
+    Every rank allocates the same buffer with torch's symmetric-memory allocator; the rendezvous maps
+    all peers' buffers into this process, and the device array of peer pointers is what the kernel
+    takes.  PyTorch is plumbing here (allocation + handle exchange); the exchange itself — remote
+    stores, flags, the rank-ordered sum — is in the kernel.  Raises if symmetric memory is not
+    available; the caller then keeps the NCCL all-reduce path."""
+
+    def __init__(self, k: int, d: int, device: torch.device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        lib = _lib.load()
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.k, self.d, self.device = k, d, device
+        nbytes = int(lib.tvq_exchange_bytes(k, d, self.world))
+        if nbytes == 0 or stats_len(k, d) > (1 << 16):
+            raise ValueError("statistics too large for the one-CTA exchange kernel")
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        self.peers = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                 # every rank's buffer is zeroed and mapped before the first step
+
+    def matches(self, k: int, d: int, device: torch.device) -> bool:
+        return self.k == k and self.d == d and self.device == device
+
+
+def vq_ema_update_dp(stats: torch.Tensor, ex: PeerExchange, cluster_size: torch.Tensor, embed_avg: torch.Tensor,
+                     embed: torch.Tensor, embed_prev: Optional[torch.Tensor], decay: float, eps: float) -> None:
+    """tvq_ema_update_dp: all-reduce of the packed statistics over NVLink peer memory + EMA update, one kernel."""
+    _need(stats, "stats"); _need(cluster_size, "cluster_size"); _need(embed_avg, "embed_avg"); _need(embed, "embed")
+    k, d = embed.shape
+    rc = _lib.load().tvq_ema_update_dp(stats.data_ptr(), ex.peers.data_ptr(), ex.rank, ex.world, cluster_size.data_ptr(),
+                                       embed_avg.data_ptr(), embed.data_ptr(),
+                                       embed_prev.data_ptr() if embed_prev is not None else None, k, d, float(decay),
+                                       float(eps), _stream())
+    _lib.check(rc, "tvq_ema_update_dp")
 
 
 def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: float, embed_prev: Optional[torch.Tensor]):
@@ -199,8 +241,7 @@ class VQTrainStep(torch.autograd.Function):
         else:
             idx, q, scalars = vq_forward_raw(x, cb._embed_data(), ws, train=True, write_q=True, idx=given_idx,
                                              commitment_weight=commitment_weight)
-            cb._all_reduce_stats(ws.stats)
-            vq_ema_update(ws.stats, cb.cluster_size, cb.embed_avg, cb._embed_data(), prev, cb.decay, cb.eps, ws)
+            cb._sync_and_update(ws, prev)
             commit, weighted = scalars[0].clone(), scalars[2:3].clone()
         ctx.save_for_backward(x, idx, prev)
         ctx.commitment_weight = float(commitment_weight)

@@ -17,6 +17,8 @@ split, layout) and for the RNG-consuming branches (k-means seeding, dead-code sa
 """
 from __future__ import annotations
 
+import os
+import warnings
 from typing import Optional, Union
 
 import torch
@@ -82,6 +84,7 @@ class EuclideanCodebook(nn.Module):
         self.perplexity = None
         self._last_ind = None
         self._ws: Optional[TF.Workspace] = None
+        self._px = None            # TF.PeerExchange, or False once it is known to be unavailable
         # host mirror of `initted` so the hot path never reads a device flag (the reference syncs
         # on `if self.initted:` every call, vq.py:172)
         self._initted_host: Optional[bool] = not kmeans_init
@@ -100,6 +103,33 @@ class EuclideanCodebook(nn.Module):
         """The reference's two all_reduce hooks (vq.py:229, :234) as ONE call on the packed buffer."""
         if self._ddp_active():
             distributed.all_reduce(stats)
+
+    def _peer_exchange(self, device: torch.device):
+        """Exchange buffers of the fused NVLink all-reduce + EMA kernel, or None (then: all_reduce + EMA kernel).
+        Set up once per codebook, on the first data-parallel training step (a collective: every rank gets here)."""
+        if self._px is False:
+            return None
+        if self._px is None or not self._px.matches(self.codebook_size, self.dim, device):
+            try:
+                if distributed.get_backend() != "nccl" or os.environ.get("TVQ_NO_PEER_EXCHANGE"):
+                    raise RuntimeError("peer exchange needs CUDA peers (nccl process group)")
+                self._px = TF.PeerExchange(self.codebook_size, self.dim, device)
+            except Exception as exc:          # say so once; the NCCL all-reduce path computes the same update
+                warnings.warn(f"tvq_b200: NVLink peer exchange unavailable ({exc}); using all_reduce + EMA kernel")
+                self._px = False
+                return None
+        return self._px
+
+    def _sync_and_update(self, ws, prev) -> None:
+        """EMA update from this call's statistics (ws.stats); data-parallel: summed over the ranks first."""
+        embed = self._embed_data()
+        if self._ddp_active():
+            px = self._peer_exchange(embed.device)
+            if px is not None:
+                TF.vq_ema_update_dp(ws.stats, px, self.cluster_size, self.embed_avg, embed, prev, self.decay, self.eps)
+                return
+            distributed.all_reduce(ws.stats)
+        TF.vq_ema_update(ws.stats, self.cluster_size, self.embed_avg, embed, prev, self.decay, self.eps, ws)
 
     def _embed_data(self) -> torch.Tensor:
         e = self.embed.data if self.learnable_codebook else self.embed
@@ -200,11 +230,9 @@ class EuclideanCodebook(nn.Module):
             else:
                 idx, _, scalars = TF.vq_forward_raw(flat.detach(), self._embed_data(), ws, train=True, write_q=False,
                                                     idx=given)
-                self._all_reduce_stats(ws.stats)
                 q = None
                 prev = torch.empty_like(self._embed_data())
-                TF.vq_ema_update(ws.stats, self.cluster_size, self.embed_avg, self._embed_data(), prev, self.decay,
-                                 self.eps, ws)
+                self._sync_and_update(ws, prev)
                 q = TF.vq_gather(idx.view(1, -1), prev).view(flat.shape)
             self.expire_codes_(x.detach())
         else:
