@@ -121,6 +121,16 @@ TVQ_API int tvq_ema_update_dp(const float *stats, void *const *peer_bufs, int ra
                       float *cluster_size, float *embed_avg, float *embed, float *embed_prev, int k,
                       int d, double decay, double eps, void *stream);
 
+/* tvq_train_step for data-parallel ranks, still ONE kernel per codebook (k <= 32, d <= 128; otherwise
+ * TVQ_ERR_UNSUPPORTED: use tvq_forward + tvq_ema_update_dp): the last CTA to finish sums the statistics
+ * of all ranks through the exchange buffers (same protocol and buffers as tvq_ema_update_dp) and applies
+ * the EMA update.  Every rank must call it, with n >= 1.                                            */
+TVQ_API int tvq_train_step_dp(const float *x, float *embed, float *cluster_size, float *embed_avg,
+                      float *embed_prev, int64_t n, int k, int d, float commitment_weight, double decay,
+                      double eps, int64_t *idx, float *q, float *scalars, float *commit_out,
+                      float *weighted_out, void *workspace, size_t workspace_bytes,
+                      void *const *peer_bufs, int rank, int world, void *stream);
+
 /* Backward of the train forward (autograd through vq.py:357-366):
  *   g_x = g_q + (g_commit + commitment_weight * g_weighted) * 2/(n*d) * (x - q_st)
  *   with q_st recomputed from x, idx and the codebook the forward used.  g_commit / g_weighted

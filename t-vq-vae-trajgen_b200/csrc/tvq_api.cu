@@ -314,6 +314,7 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
     p.idx = idx; p.q = (flags & TVQ_F_WRITE_Q) ? q : nullptr; p.stats = stats; p.scalars = scalars;
     p.hdr = hdr; p.e2 = e2; p.commitment_weight = commitment_weight;
     p.commit_out = nullptr; p.weighted_out = nullptr; p.fuse_ema = 0;
+    p.peers = nullptr; p.dp_rank = 0; p.dp_world = 1;
     p.cluster_size = nullptr; p.embed_avg = nullptr; p.embed = nullptr; p.embed_prev = nullptr;
     p.decay = p.one_minus_decay = p.eps = p.k_eps = 0.f;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
@@ -343,9 +344,13 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
     return train ? dispatch_fwd_simt<true>(dp, p, pl, *di, stream) : dispatch_fwd_simt<false>(dp, p, pl, *di, stream);
 }
 
-int tvq_train_step(const float* x, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t n, int k,
-                   int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
-                   float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* stream_) {
+}  // extern "C"
+
+namespace {
+int train_step_impl(const float* x, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t n, int k,
+                    int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
+                    float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* stream_,
+                    void* const* peers, int dp_rank, int dp_world) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 4 || d > 256 || (d & 3) || n < 0 || (int64_t)k * d >= (int64_t(1) << 31)) return TVQ_ERR_UNSUPPORTED;
     if (!embed || !cluster_size || !embed_avg || !scalars || !workspace || (n > 0 && (!x || !idx || !q))) return TVQ_ERR_BAD_ARG;
@@ -360,6 +365,7 @@ int tvq_train_step(const float* x, float* embed, float* cluster_size, float* emb
     float* e2 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + sizeof(WsHeader));
     float* scratch = e2 + e2_len(k);                          // private statistics: zero on entry, zero on exit
     const bool umma = n > 0 && k <= 32 && d <= 128 && n < (int64_t(1) << 31) - 64;
+    if (dp_world > 1 && !umma) return TVQ_ERR_UNSUPPORTED;   // the fused data-parallel step exists for the resident-codebook kernel only
     const bool use_stream = !umma && n > 0 && n < (int64_t(1) << 31) - 256;
     void* cbh = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_bf16_offset(k, d) : nullptr;
     if (!umma) {
@@ -373,6 +379,7 @@ int tvq_train_step(const float* x, float* embed, float* cluster_size, float* emb
     p.commit_out = commit_out; p.weighted_out = weighted_out;
     p.cluster_size = cluster_size; p.embed_avg = embed_avg; p.embed = embed; p.embed_prev = embed_prev;
     p.decay = (float)decay; p.one_minus_decay = (float)(1.0 - decay); p.eps = (float)eps; p.k_eps = (float)((double)k * eps);
+    p.peers = peers; p.dp_rank = dp_rank; p.dp_world = dp_world;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
     p.exact = 0; p.given_idx = 0; p.use_hist = k <= 2048;
     if (umma) {
@@ -394,6 +401,26 @@ int tvq_train_step(const float* x, float* embed, float* cluster_size, float* emb
         if ((rc = dispatch_fwd_simt<true>(dp, p, pl, *di, stream)) != TVQ_OK) return rc;
     }
     return tvq_ema_update(scratch, cluster_size, embed_avg, embed, embed_prev, k, d, decay, eps, workspace, workspace_bytes, stream_);
+}
+}  // namespace
+
+extern "C" {
+
+int tvq_train_step(const float* x, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t n, int k,
+                   int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
+                   float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* stream_) {
+    return train_step_impl(x, embed, cluster_size, embed_avg, embed_prev, n, k, d, commitment_weight, decay, eps, idx, q, scalars,
+                           commit_out, weighted_out, workspace, workspace_bytes, stream_, nullptr, 0, 1);
+}
+
+int tvq_train_step_dp(const float* x, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t n, int k,
+                      int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
+                      float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* const* peer_bufs,
+                      int rank, int world, void* stream_) {
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || (world > 1 && !peer_bufs)) return TVQ_ERR_BAD_ARG;
+    if (n < 1) return TVQ_ERR_UNSUPPORTED;      // every rank must launch (the exchange is collective)
+    return train_step_impl(x, embed, cluster_size, embed_avg, embed_prev, n, k, d, commitment_weight, decay, eps, idx, q, scalars,
+                           commit_out, weighted_out, workspace, workspace_bytes, stream_, peer_bufs, rank, world);
 }
 
 int tvq_ema_update(const float* stats, float* cluster_size, float* embed_avg, float* embed, float* embed_prev,

@@ -23,7 +23,8 @@ struct WsHeader {
     unsigned n_rescored;   // rows decided by the fp64 re-score
     unsigned n_exact;      // rows that needed the full exact scan
     unsigned ema_ticket;   // same, for the EMA kernel
-    unsigned pad[10];
+    unsigned next_tile;    // dynamic tile scheduler of the resident-codebook forward (reset by the last CTA)
+    unsigned pad[9];
 };
 static_assert(sizeof(WsHeader) == 64, "WsHeader is 64 bytes");
 

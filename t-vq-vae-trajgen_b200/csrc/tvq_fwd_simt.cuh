@@ -49,6 +49,9 @@ struct FwdParams {
     float* embed;         // == cb (written only after every CTA has finished reading it)
     float* embed_prev;    // optional: receives the pre-update codebook
     float decay, one_minus_decay, eps, k_eps;
+    // data-parallel fused step: exchange buffers of every rank (tvq_aux.cuh::ema_dp_kernel layout); world <= 1: local
+    void* const* peers;
+    int dp_rank, dp_world;
 };
 
 // Shared-memory carve-up, computed identically on host and device.
@@ -288,34 +291,88 @@ __device__ __forceinline__ void finish_ticket(const FwdParams& p, double* red, i
             if (p.commit_out) *p.commit_out = commit;
             if (p.weighted_out) *p.weighted_out = __fmul_rn(commit, p.commitment_weight);
             p.hdr->ticket = 0;
+            p.hdr->next_tile = 0u;
             p.hdr->loss_sum = 0.0;             // consumed: the header is clean for the next call
             p.hdr->n_rescored = 0u;
             p.hdr->n_exact = 0u;
         }
         if (TRAIN && p.fuse_ema) {
-            // EMA codebook update (vq.py:231,236-242) by this last CTA: every other CTA has taken its
-            // ticket, i.e. finished reading the codebook and flushing its statistics.  Same arithmetic
-            // as ema_kernel (tvq_aux.cuh); the statistics scratch is zeroed for the next call.
+            // EMA codebook update (vq.py:231,236-242) by this last CTA: every other CTA has taken its ticket,
+            // i.e. finished reading the codebook and flushing its statistics.  Same arithmetic as ema_kernel
+            // (tvq_aux.cuh); the statistics scratch is zeroed for the next call.
+            // Data-parallel (p.dp_world > 1): the statistics are first summed over the ranks by a one-shot
+            // exchange over NVLink peer memory (protocol and buffer layout: tvq_aux.cuh::ema_dp_kernel).
             __syncthreads();
+            const int kp = (p.k + 3) & ~3;
+            const int dq = p.d >> 2;
+            const int world = p.dp_world > 1 ? p.dp_world : 1;
+            const int64_t len4 = (int64_t)(kp + p.k * p.d) >> 2;
+            const float4* slots = reinterpret_cast<const float4*>(p.stats);     // world slots of len4 float4, rank order
+            if (p.dp_world > 1) {
+                unsigned char* mine = reinterpret_cast<unsigned char*>(p.peers[p.dp_rank]);
+                if (tid == 0) {
+                    unsigned* counter = reinterpret_cast<unsigned*>(mine);
+                    misc[2] = (int)(*counter + 1u);
+                    *counter = (unsigned)misc[2];
+                }
+                __syncthreads();
+                const unsigned epoch = (unsigned)misc[2];
+                const int par = (int)(epoch & 1u);
+                const size_t flags_off = 64, slots_off = 64 + (((size_t)2 * world * 4 + 63) & ~(size_t)63);
+                const float4* src = reinterpret_cast<const float4*>(p.stats);
+                for (int r = 0; r < world; ++r) {
+                    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(p.peers[r]) + slots_off) +
+                                  ((size_t)par * world + p.dp_rank) * len4;
+                    for (int64_t f = tid; f < len4; f += blockDim.x) dst[f] = __ldcg(src + f);
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (tid < world) {
+                    unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(p.peers[tid]) + flags_off) + par * world + p.dp_rank;
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+                    const unsigned* lf = reinterpret_cast<const unsigned*>(mine + flags_off) + par * world + tid;
+                    unsigned long long t0 = 0;
+                    for (unsigned spin = 1;; ++spin) {
+                        unsigned v;
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(lf) : "memory");
+                        if (v == epoch) break;
+                        if ((spin & 0x3ffu) == 0) {
+                            unsigned long long t;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                            if (t0 == 0) t0 = t;
+                            else if (t - t0 > 10000000000ull) __trap();
+                        }
+                    }
+                }
+                __syncthreads();
+                slots = reinterpret_cast<const float4*>(mine + slots_off) + (size_t)par * world * len4;
+            }
+            auto count_of = [&](int c) {
+                float cnt = 0.f;
+                for (int r = 0; r < world; ++r) cnt += __ldcg(reinterpret_cast<const float*>(slots + (size_t)r * len4) + c);
+                return cnt;
+            };
             double part = 0.0;
             for (int c = tid; c < p.k; c += blockDim.x)
-                part += (double)fmaf(__ldcg(p.stats + c), p.one_minus_decay, __fmul_rn(p.cluster_size[c], p.decay));
+                part += (double)fmaf(count_of(c), p.one_minus_decay, __fmul_rn(p.cluster_size[c], p.decay));
             const double totn = block_sum(part, red);
             if (tid == 0) red[15] = totn;
             __syncthreads();
             const float nsum = __double2float_rn(red[15]);
             const float denom = __fadd_rn(nsum, p.k_eps);
-            const int kp = (p.k + 3) & ~3;
-            const int dq = p.d >> 2;
             float4* esum4 = reinterpret_cast<float4*>(p.stats + kp);
             float4* avg4 = reinterpret_cast<float4*>(p.embed_avg);
             float4* emb4 = reinterpret_cast<float4*>(p.embed);
             float4* prev4 = reinterpret_cast<float4*>(p.embed_prev);
             for (int f = tid; f < p.k * dq; f += blockDim.x) {
                 const int c = f / dq;
-                const float cs = fmaf(__ldcg(p.stats + c), p.one_minus_decay, __fmul_rn(p.cluster_size[c], p.decay));
+                const float cs = fmaf(count_of(c), p.one_minus_decay, __fmul_rn(p.cluster_size[c], p.decay));
                 const float sm = __fmul_rn(__fdiv_rn(__fadd_rn(cs, p.eps), denom), nsum);
-                const float4 sv = __ldcg(esum4 + f);
+                float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = 0; r < world; ++r) {
+                    const float4 v = __ldcg(slots + (size_t)r * len4 + (kp >> 2) + f);
+                    sv.x += v.x; sv.y += v.y; sv.z += v.z; sv.w += v.w;
+                }
                 float4 a = avg4[f];
                 a.x = fmaf(sv.x, p.one_minus_decay, __fmul_rn(a.x, p.decay));
                 a.y = fmaf(sv.y, p.one_minus_decay, __fmul_rn(a.y, p.decay));
@@ -324,13 +381,14 @@ __device__ __forceinline__ void finish_ticket(const FwdParams& p, double* red, i
                 avg4[f] = a;
                 if (prev4) prev4[f] = emb4[f];
                 emb4[f] = make_float4(__fdiv_rn(a.x, sm), __fdiv_rn(a.y, sm), __fdiv_rn(a.z, sm), __fdiv_rn(a.w, sm));
-                esum4[f] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             __syncthreads();
             for (int c = tid; c < kp; c += blockDim.x) {
-                if (c < p.k) p.cluster_size[c] = fmaf(__ldcg(p.stats + c), p.one_minus_decay, __fmul_rn(p.cluster_size[c], p.decay));
-                p.stats[c] = 0.f;
+                if (c < p.k) p.cluster_size[c] = fmaf(count_of(c), p.one_minus_decay, __fmul_rn(p.cluster_size[c], p.decay));
             }
+            __syncthreads();                              // (the local statistics may be slot 0 of `slots`)
+            for (int f = tid; f < p.k * dq; f += blockDim.x) esum4[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = tid; c < kp; c += blockDim.x) p.stats[c] = 0.f;
         }
     }
 }

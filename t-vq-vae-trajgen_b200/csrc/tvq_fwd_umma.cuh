@@ -57,7 +57,7 @@ constexpr int kUBatch = 4;              // rows a warp keeps in flight in the ap
 
 struct UmmaPlan {
     int stages, stage_bytes;
-    int x, cb, e2s, hist, keys, red, misc, bars, tmem, total;
+    int x, cb, e2s, hist, keys, red, misc, tiles, bars, tmem, total;
 };
 __host__ __device__ inline UmmaPlan make_umma_plan(int dp, int kp, int stages) {
     UmmaPlan u;
@@ -72,6 +72,7 @@ __host__ __device__ inline UmmaPlan make_umma_plan(int dp, int kp, int stages) {
     u.keys = o; o += 4 * kUGroups * 16 * 16;   // per epilogue warp: 16 rows x (4 best keys)
     u.red = o;  o += 16 * 8;
     u.misc = o; o += 16 * 4;
+    u.tiles = o; o += kUMaxStages * 4;          // tile id held by each stage (dynamic scheduler; -1 = no more tiles)
     u.bars = o; o += (2 * kUMaxStages + 2 * kUSlots) * 8;
     u.tmem = o; o += 16;
     u.total = o;
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     int* hist = reinterpret_cast<int*>(smem + pl.hist);
     double* red = reinterpret_cast<double*>(smem + pl.red);
     int* misc = reinterpret_cast<int*>(smem + pl.misc);
+    volatile int* stage_tile = reinterpret_cast<volatile int*>(smem + pl.tiles);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.tmem);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kUMaxStages;
@@ -300,28 +302,43 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     unsigned counters = 0;                                // low 16 bits: re-scored rows, high: fp64 rows
 
     if (warp == 0) {
-        // ============================================================ TMA producer
+        // ============================================================ TMA producer + dynamic tile scheduler
+        // Tiles are handed out by a global counter (a CTA that starts late — e.g. behind the previous launch's
+        // last CTA — simply takes fewer); the tile id travels with the stage.  After the last tile the producer
+        // posts kUGroups end markers so that every epilogue group sees one.
         if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            int it = 0, ends = 0;
+            while (ends < kUGroups) {
                 const int s = it % stages;
                 const uint32_t ph = (uint32_t)(it / stages) & 1u;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(kUM * DP * 4));
+                int tile = -1;
+                if (ends == 0) {
+                    tile = (int)atomicAdd(&p.hdr->next_tile, 1u);
+                    if (tile >= num_tiles) tile = -1;
+                }
+                stage_tile[s] = tile;
+                if (tile >= 0) {
+                    mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(kUM * DP * 4));
 #pragma unroll
-                for (int j = 0; j < NSLAB; ++j)
-                    tma_load_2d(x_base + s * pl.stage_bytes + j * SLAB_X, &tmap_x, bar_full + 8 * s, j * 32, tile * kUM);
+                    for (int j = 0; j < NSLAB; ++j)
+                        tma_load_2d(x_base + s * pl.stage_bytes + j * SLAB_X, &tmap_x, bar_full + 8 * s, j * 32, tile * kUM);
+                } else {
+                    mbar_arrive(bar_full + 8 * s);
+                    ++ends;
+                }
+                ++it;
             }
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(kUM, KP);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int it = 0;; ++it) {
                 const int s = it % stages, slot = it % kUSlots;
                 const uint32_t ph = (uint32_t)(it / stages) & 1u, sph = (uint32_t)(it / kUSlots) & 1u;
                 mbar_wait(bar_full + 8 * s, ph);
+                if (stage_tile[s] < 0) break;
                 mbar_wait(bar_tempty + 8 * slot, sph ^ 1u);
                 tc_fence_after();
                 const uint32_t a0 = x_base + s * pl.stage_bytes;
@@ -356,14 +373,14 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         long long ph_t = clock64();
 #endif
         for (int it = g; ; it += kUGroups) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            if (tile >= num_tiles) break;
             const int s = it % stages, slot = it % kUSlots;
             const uint32_t ph = (uint32_t)(it / stages) & 1u, sph = (uint32_t)(it / kUSlots) & 1u;
-            const int64_t row0 = (int64_t)tile * kUM + quad * 16;     // first of this warp's 16 rows
             const float* xt = reinterpret_cast<const float*>(smem + pl.x + s * pl.stage_bytes);
 
-            mbar_wait(bar_full + 8 * s, ph);              // x tile landed (TMA writes visible)
+            mbar_wait(bar_full + 8 * s, ph);              // x tile landed (TMA writes visible) / end marker
+            const int tile = stage_tile[s];
+            if (tile < 0) break;
+            const int64_t row0 = (int64_t)tile * kUM + quad * 16;     // first of this warp's 16 rows
             TVQ_PH(0);
             mbar_wait(bar_tfull + 8 * slot, sph);         // scores ready
             tc_fence_after();

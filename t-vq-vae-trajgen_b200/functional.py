@@ -139,7 +139,8 @@ def vq_ema_update_dp(stats: torch.Tensor, ex: PeerExchange, cluster_size: torch.
     _lib.check(rc, "tvq_ema_update_dp")
 
 
-def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: float, embed_prev: Optional[torch.Tensor]):
+def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: float, embed_prev: Optional[torch.Tensor],
+                      px: Optional["PeerExchange"] = None):
     """tvq_train_step on a codebook module's buffers: fused forward + EMA (one kernel for k <= 32, d <= 128).
 
     Returns (idx, q_st, scalars[8], commit[()], weighted[1]); the module's cluster_size / embed_avg /
@@ -156,6 +157,14 @@ def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: flo
     weighted = torch.empty(1, dtype=torch.float32, device=x.device)
     if n == 0:
         scalars.fill_(float("nan")); commit.fill_(float("nan")); weighted.fill_(float("nan"))
+    if px is not None:       # data-parallel: the kernel's last CTA sums the statistics of all ranks over NVLink peer memory
+        rc = _lib.load().tvq_train_step_dp(x.data_ptr(), embed.data_ptr(), cb.cluster_size.data_ptr(), cb.embed_avg.data_ptr(),
+                                           embed_prev.data_ptr() if embed_prev is not None else None, n, k, d,
+                                           float(commitment_weight), float(cb.decay), float(cb.eps), idx.data_ptr(),
+                                           q.data_ptr(), scalars.data_ptr(), commit.data_ptr(), weighted.data_ptr(),
+                                           ws.buf.data_ptr(), ws.nbytes, px.peers.data_ptr(), px.rank, px.world, _stream())
+        _lib.check(rc, "tvq_train_step_dp")
+        return idx, q, scalars, commit, weighted
     rc = _lib.load().tvq_train_step(x.data_ptr() if n else None, embed.data_ptr(), cb.cluster_size.data_ptr(),
                                     cb.embed_avg.data_ptr(), embed_prev.data_ptr() if embed_prev is not None else None,
                                     n, k, d, float(commitment_weight), float(cb.decay), float(cb.eps),
@@ -236,8 +245,13 @@ class VQTrainStep(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ws = cb._workspace(x.device)
         prev = torch.empty_like(cb._embed_data()) if ctx.needs_input_grad[0] else None
-        if given_idx is None and not cb._ddp_active():
-            idx, q, scalars, commit, weighted = vq_train_step_raw(x, cb, ws, commitment_weight, prev)
+        px = None
+        fused_dp = False
+        if given_idx is None and cb._ddp_active() and cb.codebook_size <= 32 and cb.dim <= 128 and x.shape[0] >= 1:
+            px = cb._peer_exchange(x.device)
+            fused_dp = px is not None
+        if given_idx is None and (fused_dp or not cb._ddp_active()):
+            idx, q, scalars, commit, weighted = vq_train_step_raw(x, cb, ws, commitment_weight, prev, px)
         else:
             idx, q, scalars = vq_forward_raw(x, cb._embed_data(), ws, train=True, write_q=True, idx=given_idx,
                                              commitment_weight=commitment_weight)
