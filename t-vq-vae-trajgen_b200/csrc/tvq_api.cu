@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "tvq_aux.cuh"
 #include "tvq_common.cuh"
@@ -186,14 +187,14 @@ int make_cb_tensor_map(CUtensorMap* tm, const void* cbh, int k, int dp, int nt) 
     return r == CUDA_SUCCESS ? TVQ_OK : TVQ_ERR_BAD_ARG;
 }
 
-template <int DP, int NT, bool TRAIN>
+template <int DP, int NT, bool TRAIN, int CG>
 int launch_fwd_stream_impl(FwdParams p, const void* cbh, const DeviceInfo& di, cudaStream_t stream) {
-    auto kern = fwd_stream_kernel<DP, NT, TRAIN>;
-    const StreamPlan fixed = make_stream_plan(DP, NT, 0);
-    int stages = (di.max_smem_optin - fixed.total) / (NT * 128);
+    auto kern = fwd_stream_kernel<DP, NT, TRAIN, CG>;
+    const StreamPlan fixed = make_stream_plan(DP, NT, 0, CG);
+    int stages = (di.max_smem_optin - fixed.total) / ((NT / CG) * 128);
     if (stages > kSMaxStages) stages = kSMaxStages;
     if (stages < 2) return TVQ_ERR_UNSUPPORTED;
-    const StreamPlan pl = make_stream_plan(DP, NT, stages);
+    const StreamPlan pl = make_stream_plan(DP, NT, stages, CG);
     static int configured_smem = -1;
     if (pl.total > configured_smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total);
@@ -201,20 +202,49 @@ int launch_fwd_stream_impl(FwdParams p, const void* cbh, const DeviceInfo& di, c
         configured_smem = pl.total;
     }
     CUtensorMap tm;
-    int rc = make_cb_tensor_map(&tm, cbh, p.k, DP, NT);
+    int rc = make_cb_tensor_map(&tm, cbh, p.k, DP, NT / CG);
     if (rc != TVQ_OK) return rc;
     p.num_tiles = (int)((p.n + kSM - 1) / kSM);
-    int grid = p.num_tiles < di.sm_count ? p.num_tiles : di.sm_count;
-    kern<<<grid, kSThreads, pl.total, stream>>>(tm, p, stages);
+    const int groups = (p.num_tiles + CG - 1) / CG, units = di.sm_count / CG;
+    const int grid = CG * (groups < units ? groups : units);
+    if (CG == 1) {
+        kern<<<grid, kSThreads, pl.total, stream>>>(tm, p, stages);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kSThreads);
+        cfg.dynamicSmemBytes = (size_t)pl.total;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, p, stages);
+        if (e != cudaSuccess) return (int)e;
+    }
     return launch_status();
+}
+
+// CTA pairs pay off where the code stream is long enough to matter (k >= 1024) and there are at least two row tiles
+// per pair of SMs; TVQ_STREAM_CG=1|2 in the environment overrides the choice (experiments).
+inline int stream_cg(const FwdParams& p) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("TVQ_STREAM_CG");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 1 || forced == 2) return forced;
+    return (p.k >= 1024 && p.n > kSM) ? 2 : 1;
 }
 
 template <bool TRAIN>
 int dispatch_fwd_stream(const FwdParams& p, const void* cbh, const DeviceInfo& di, cudaStream_t s) {
+    const int cg = stream_cg(p);
     switch (stream_dp(p.d)) {
-        case 64: return launch_fwd_stream_impl<64, 256, TRAIN>(p, cbh, di, s);
-        case 128: return launch_fwd_stream_impl<128, 256, TRAIN>(p, cbh, di, s);
-        case 256: return launch_fwd_stream_impl<256, 128, TRAIN>(p, cbh, di, s);
+        case 64: return cg == 2 ? launch_fwd_stream_impl<64, 256, TRAIN, 2>(p, cbh, di, s) : launch_fwd_stream_impl<64, 256, TRAIN, 1>(p, cbh, di, s);
+        case 128: return cg == 2 ? launch_fwd_stream_impl<128, 256, TRAIN, 2>(p, cbh, di, s) : launch_fwd_stream_impl<128, 256, TRAIN, 1>(p, cbh, di, s);
+        case 256: return cg == 2 ? launch_fwd_stream_impl<256, 256, TRAIN, 2>(p, cbh, di, s) : launch_fwd_stream_impl<256, 128, TRAIN, 1>(p, cbh, di, s);
     }
     return TVQ_ERR_UNSUPPORTED;
 }

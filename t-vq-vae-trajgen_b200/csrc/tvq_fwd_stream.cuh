@@ -71,10 +71,10 @@ struct StreamPlan {
     int stages, stage_bytes, a_bytes;
     int a, b, e2s, brow, cs, cc, drop, mfin, ncnt, ovf, scratch, red, misc, bars, tmem, total;
 };
-__host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages) {
+__host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages, int cg = 1) {
     StreamPlan u;
     u.stages = stages;
-    u.stage_bytes = nt * 128;            // NT codes x 64 bf16
+    u.stage_bytes = (nt / cg) * 128;     // this CTA's share of a code slab: NT/cg codes x 64 bf16
     u.a_bytes = kSM * dp * 2;
     int o = 0;
     u.a = o;     o += 2 * u.a_bytes;
@@ -143,6 +143,50 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float m;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
     return m;
+}
+// ---- CTA pair (cta_group::2): the even CTA of a 2-CTA cluster issues the MMAs for both
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same object in the EVEN CTA of the pair
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release at cluster scope) on a barrier of the pair's even CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {   // one full warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load whose completion bytes are counted on the EVEN CTA's barrier (both CTAs of the pair issue it)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
 }
 template <int REGS> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
@@ -359,7 +403,12 @@ __device__ __forceinline__ int gather_cands(int* list, const int n0, const int n
     return cnt;
 }
 
-template <int DP, int NT, bool TRAIN>
+// CG = 1: one CTA per SM on its own.  CG = 2: CTA pairs (2-CTA clusters, tcgen05 cta_group::2): each CTA keeps its
+// own 128 latents and everything that belongs to them (converters, scan warps, lists, TMEM scores), but only HALF of
+// every code slab: the even CTA issues one M = 256 MMA for both, which reads the A rows and the B half of each
+// CTA from that CTA's shared memory.  Per SM this halves the TMA fill and the L2 traffic of the code stream and
+// takes a third off the shared-memory operand reads.
+template <int DP, int NT, bool TRAIN, int CG>
 __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_cb, const FwdParams p,
                                                                  const int stages) {
     using namespace sm100;
@@ -373,7 +422,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     static_assert(DP == 64 || DP == 128 || DP == 256, "d padded to 64, 128 or 256");
     static_assert(NT == 128 || NT == 256, "code tile of 128 or 256");
 
-    const StreamPlan pl = make_stream_plan(DP, NT, stages);
+    const StreamPlan pl = make_stream_plan(DP, NT, stages, CG);
     float* e2s = reinterpret_cast<float*>(smem + pl.e2s);
     float* brow_ring = reinterpret_cast<float*>(smem + pl.brow);
     float* cand_s = reinterpret_cast<float*>(smem + pl.cs);     // [half][slot][latent]
@@ -397,20 +446,25 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     const int nchunk = p.d >> 2;
     const int n_ct = (p.k + NT - 1) / NT;                 // code tiles
     const int num_tiles = p.num_tiles;                    // row tiles of 128 latents
+    // work distribution: unit u = blockIdx.x / CG walks the tile groups; this CTA takes tile CG * group + rank
+    // (possibly past the end: such a tile has no valid latents but the CTA still takes part in the pair's MMAs)
+    const int crank = CG == 2 ? (int)cluster_ctarank() : 0;
+    const int unit0 = (int)blockIdx.x / CG, nunits = (int)gridDim.x / CG;
+    const int ngroups = (num_tiles + CG - 1) / CG;
 
     // ------------------------------------------------------------------ CTA prologue
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     if (tid == 0) {
         for (int s = 0; s < kSMaxStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, kSCvtWarps); mbar_init(bar_aempty + 8 * s, 1); }
-        for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, kSScanWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, CG * kSCvtWarps); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, CG * kSScanWarps); }
         for (int s = 0; s < kSESlots; ++s) { mbar_init(bar_efull + 8 * s, 1); mbar_init(bar_eempty + 8 * s, kSScanWarps); }
         for (int s = 0; s < kSBrowRing; ++s) { mbar_init(bar_rfull + 8 * s, kSCvtWarps); mbar_init(bar_rempty + 8 * s, kSScanWarps); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_cb);
         for (int i = 4; i < 12; ++i) misc[i] = 0;           // spill counters [parity][quadrant]
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 1) { if (CG == 2) tmem_alloc2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
     // max |e| (error-bound constant): every CTA scans the |e|^2 table (k floats, L2 resident)
     float emax2 = 0.f;
     for (int c = tid; c < p.k; c += kSThreads) emax2 = fmaxf(emax2, __ldg(p.e2 + c));
@@ -420,6 +474,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     if (lane == 0) wmax[warp] = emax2;
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();                      // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     emax2 = 0.f;
@@ -437,7 +492,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
         if (lane == 0) {
             SP_DECL;
             int ib = 0, et = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int grp = unit0; grp < ngroups; grp += nunits) {
                 for (int ct = 0; ct < n_ct; ++ct, ++et) {
                     const int es = et % kSESlots;
                     SP_WAIT(0, bar_eempty + 8 * es, (((uint32_t)(et / kSESlots)) & 1u) ^ 1u);
@@ -446,8 +501,15 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                     for (int j = 0; j < KSLABS; ++j, ++ib) {
                         const int s = ib % stages;
                         SP_WAIT(1, bar_bempty + 8 * s, (((uint32_t)(ib / stages)) & 1u) ^ 1u);
-                        mbar_arrive_expect_tx(bar_bfull + 8 * s, (uint32_t)(NT * 128));
-                        tma_load_2d(b_base + s * pl.stage_bytes, &tmap_cb, bar_bfull + 8 * s, j * 64, ct * NT);
+                        if (CG == 2) {
+                            // the even CTA's barrier counts the bytes of both halves; each CTA fetches its half
+                            if (crank == 0) mbar_arrive_expect_tx(bar_bfull + 8 * s, (uint32_t)(NT * 128));
+                            tma_load_2d_pair(b_base + s * pl.stage_bytes, &tmap_cb, bar_bfull + 8 * s, j * 64,
+                                             ct * NT + crank * (NT / 2));
+                        } else {
+                            mbar_arrive_expect_tx(bar_bfull + 8 * s, (uint32_t)(NT * 128));
+                            tma_load_2d(b_base + s * pl.stage_bytes, &tmap_cb, bar_bfull + 8 * s, j * 64, ct * NT);
+                        }
                     }
                 }
             }
@@ -456,11 +518,11 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kSM, NT);
+        if (lane == 0 && crank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(CG * kSM, NT);
             SP_DECL;
             int ib = 0, tt = 0, it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int grp = unit0; grp < ngroups; grp += nunits, ++it) {
                 const int ab = it & 1;
                 SP_WAIT(0, bar_afull + 8 * ab, ((uint32_t)(it >> 1)) & 1u);
                 tc_fence_after();
@@ -476,14 +538,22 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                         tc_fence_after();
                         const uint32_t b0 = b_base + s * pl.stage_bytes;
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            umma_bf16(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
-                                      umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
-                        umma_commit(bar_bempty + 8 * s);       // stage free once these MMAs have read it
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (CG == 2)
+                                umma_bf16_pair(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
+                                               umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
+                            else
+                                umma_bf16(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
+                                          umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
+                        }
+                        // stage free (in both CTAs of a pair) once these MMAs have read it
+                        if (CG == 2) umma_commit_pair(bar_bempty + 8 * s); else umma_commit(bar_bempty + 8 * s);
                     }
-                    umma_commit(bar_tfull + 8 * slot);         // scores of this code tile complete
+                    // scores of this code tile complete
+                    if (CG == 2) umma_commit_pair(bar_tfull + 8 * slot); else umma_commit(bar_tfull + 8 * slot);
                 }
-                umma_commit(bar_aempty + 8 * ab);              // A buffer free once every MMA of the row tile is done
+                // A buffer free once every MMA of the row tile is done
+                if (CG == 2) umma_commit_pair(bar_aempty + 8 * ab); else umma_commit(bar_aempty + 8 * ab);
             }
             SP_LAP(7);
             SP_DUMP(8);
@@ -494,7 +564,8 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
         constexpr int U = 8;
         SP_DECL;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int grp = unit0; grp < ngroups; grp += nunits, ++it) {
+            const int tile = CG * grp + crank;
             const int ab = it & 1;
             const int64_t row0 = (int64_t)tile * kSM;
             if (cw == 0 && lane == 0) {                       // L2 prefetch of the tile two iterations ahead
@@ -575,9 +646,12 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 }
             }
             }
-            fence_proxy_async_smem();                         // generic-proxy stores -> visible to tcgen05.mma
+            if (CG == 2) fence_proxy_async_all(); else fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma
             __syncwarp();
-            if (lane == 0) { mbar_arrive(bar_afull + 8 * ab); mbar_arrive(bar_rfull + 8 * rs); }
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_leader(bar_afull + 8 * ab); else mbar_arrive(bar_afull + 8 * ab);
+                mbar_arrive(bar_rfull + 8 * rs);
+            }
             SP_LAP(2);
         }
         if (cw == 0 && lane == 0) SP_DUMP(24);
@@ -599,7 +673,8 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
         constexpr int R = NV > 1 ? 2 : 4;                     // latents in flight in the apply phase
         SP_DECL;
         int et = 0, it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int grp = unit0; grp < ngroups; grp += nunits, ++it) {
+            const int tile = CG * grp + crank;
             const int rs = it & (kSBrowRing - 1);
             SP_WAIT(0, bar_rfull + 8 * rs, ((uint32_t)(it / kSBrowRing)) & 1u);     // the row bounds are written
             const float brow = brow_ring[rs * kSM + trow];
@@ -639,7 +714,10 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(bar_tempty + 8 * slot); mbar_arrive(bar_eempty + 8 * es); }
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(bar_tempty + 8 * slot); else mbar_arrive(bar_tempty + 8 * slot);
+                    mbar_arrive(bar_eempty + 8 * es);
+                }
                 SP_LAP(3);
             }
             SP_RESET();
@@ -814,8 +892,9 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     // ------------------------------------------------------------------ teardown
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();                      // the peer may read this CTA's shared memory until its last MMA is done
     tc_fence_after();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) { if (CG == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
     if (lane == 0 && n_resc) {
         atomicAdd(&p.hdr->n_rescored, n_resc);
         if (n_f64) atomicAdd(&p.hdr->n_exact, n_f64);
