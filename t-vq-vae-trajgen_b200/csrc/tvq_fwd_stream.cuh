@@ -60,7 +60,7 @@ constexpr int kSM = 128;                 // latents per row tile
 constexpr int kSThreads = 384;           // 12 warps: 168 registers per thread (the scan and apply phases need them)
 constexpr int kSCvtWarps = 2;            // converter warps (64 latents each)
 constexpr int kSScanWarps = 8;           // two per TMEM lane quadrant
-constexpr int kSCand = 8;                // candidate slots per latent and scan half
+constexpr int kSCand = 12;               // candidate slots per latent and scan half
 constexpr int kSESlots = 8;              // |e|^2 slices in flight
 constexpr int kSBrowRing = 4;            // row-bound buffers (converter runs up to 2 tiles ahead of the scan)
 constexpr int kSMaxStages = 8;
@@ -210,30 +210,32 @@ struct ScanState {
 };
 
 // Candidate list of one latent and one scan half: kSCand slots, kSM words apart so that the 32 latents
-// of a warp never collide on a bank.  Called when the list is full: compact it against the current
-// threshold (which only ever decreases); if it is still full move the WORST entry to the quadrant's
-// spill buffer.  Only if that is full too is an entry really lost.  sd[0] / sd[kSM]: smallest spilled / lost
-// score of this latent and half (shared memory).  Returns the new count (<= kSCand - 1).
-__device__ __noinline__ int cand_compact(const float thr, float* ls, int* lc, float* sd, const OvfBuf ob, const int trow) {
+// of a warp never collide on a bank.  Called when fewer than 4 slots are free (a group of 4 scores is about
+// to be appended): compact the list against the current threshold (which only ever decreases); while it
+// still holds more than kSCand - 4 entries move the WORST one to the quadrant's spill buffer.  Only if that
+// is full too is an entry really lost.  sd[0] / sd[kSM]: smallest spilled / lost score of this latent and
+// half (shared memory).  Returns the new count (<= kSCand - 4).
+__device__ __noinline__ int cand_make_room(const float thr, float* ls, int* lc, float* sd, const OvfBuf ob, const int trow,
+                                           const int cnt) {
     int kept = 0;
-    for (int i = 0; i < kSCand; ++i) {
+    for (int i = 0; i < cnt; ++i) {
         const float v = ls[i * kSM];
         const int c = lc[i * kSM];
         if (v <= thr) { ls[kept * kSM] = v; lc[kept * kSM] = c; ++kept; }
     }
-    if (kept == kSCand) {
+    while (kept > kSCand - 4) {
         int imax = 0;
         float vmax = ls[0];
-        for (int i = 1; i < kSCand; ++i) {
+        for (int i = 1; i < kept; ++i) {
             const float v = ls[i * kSM];
             if (v > vmax) { vmax = v; imax = i; }
         }
         const int pos = atomicAdd(ob.n, 1);
         if (pos < kSOvf) { ob.row[pos] = trow; ob.s[pos] = vmax; ob.c[pos] = lc[imax * kSM]; sd[0] = fminf(sd[0], vmax); }
         else sd[kSM] = fminf(sd[kSM], vmax);
-        ls[imax * kSM] = ls[(kSCand - 1) * kSM];
-        lc[imax * kSM] = lc[(kSCand - 1) * kSM];
-        kept = kSCand - 1;
+        --kept;
+        ls[imax * kSM] = ls[kept * kSM];
+        lc[imax * kSM] = lc[kept * kSM];
     }
     return kept;
 }
@@ -243,6 +245,11 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const float4
                                            ScanState& st, float* ls, int* lc, float* sd, const OvfBuf& ob, const int trow) {
     using namespace sm100;
     float s[32];
+#ifdef TVQ_ABL_NOE2      // ablation builds (tools/profile_stream.py): wrong results, timing only
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
+    if (false)
+#endif
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float4 e = e2c[i];     // the same address for every lane: shared-memory broadcast
@@ -255,20 +262,35 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const float4
     const float cmin = fmin3(fmin3(g[0], g[1], g[2]), fmin3(g[3], g[4], g[5]), fminf(g[6], g[7]));
     st.m = fminf(st.m, cmin);
     const float thr = st.m + brow;
+#ifdef TVQ_ABL_NOSLOW
+    if (false)
+#endif
     if (cmin <= thr) {
+        // which groups of 4 hold a score inside the threshold (straight-line: 8 compares), then one indexed
+        // branch per hit group instead of 8 + 4 sequential tests; the appends themselves are call-free
+        unsigned hm = 0u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (g[i] <= thr) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (s[4 * i + j] <= thr) {
-                        if (st.cnt == kSCand) st.cnt = cand_compact(thr, ls, lc, sd, ob, trow);
-                        ls[st.cnt * kSM] = s[4 * i + j];
-                        lc[st.cnt * kSM] = code0 + 4 * i + j;
-                        ++st.cnt;
-                    }
-                }
+        for (int i = 0; i < 8; ++i) hm |= (g[i] <= thr) ? (1u << i) : 0u;
+        while (hm) {
+            const int gi = __ffs((int)hm) - 1;
+            hm &= hm - 1u;
+            if (st.cnt > kSCand - 4) st.cnt = cand_make_room(thr, ls, lc, sd, ob, trow, st.cnt);
+            float a, b, c, d;
+            switch (gi) {
+                case 0: a = s[0]; b = s[1]; c = s[2]; d = s[3]; break;
+                case 1: a = s[4]; b = s[5]; c = s[6]; d = s[7]; break;
+                case 2: a = s[8]; b = s[9]; c = s[10]; d = s[11]; break;
+                case 3: a = s[12]; b = s[13]; c = s[14]; d = s[15]; break;
+                case 4: a = s[16]; b = s[17]; c = s[18]; d = s[19]; break;
+                case 5: a = s[20]; b = s[21]; c = s[22]; d = s[23]; break;
+                case 6: a = s[24]; b = s[25]; c = s[26]; d = s[27]; break;
+                default: a = s[28]; b = s[29]; c = s[30]; d = s[31]; break;
             }
+            const int cb = code0 + 4 * gi;
+            if (a <= thr) { ls[st.cnt * kSM] = a; lc[st.cnt * kSM] = cb; ++st.cnt; }
+            if (b <= thr) { ls[st.cnt * kSM] = b; lc[st.cnt * kSM] = cb + 1; ++st.cnt; }
+            if (c <= thr) { ls[st.cnt * kSM] = c; lc[st.cnt * kSM] = cb + 2; ++st.cnt; }
+            if (d <= thr) { ls[st.cnt * kSM] = d; lc[st.cnt * kSM] = cb + 3; ++st.cnt; }
         }
     }
 }

@@ -5,14 +5,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "t-vq-vae-trajgen_b200", "csrc")
 SO = os.path.join(CSRC, "_prof", "libtvq_sprof.so")
 
+VARIANTS = {"": [], "noslow": ["-DTVQ_ABL_NOSLOW"], "noe2": ["-DTVQ_ABL_NOE2"],
+            "noslow_noe2": ["-DTVQ_ABL_NOSLOW", "-DTVQ_ABL_NOE2"]}
+
+def so_of(v):
+    return SO if not v else SO.replace(".so", f"_{v}.so")
+
 def build():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
-    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-DTVQ_STREAM_PROF",
-                           "-shared", "-Xcompiler", "-fPIC", "-o", SO, os.path.join(CSRC, "tvq_api.cu")], cwd=CSRC)
+    procs = [subprocess.Popen(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-DTVQ_STREAM_PROF",
+                               *fl, "-shared", "-Xcompiler", "-fPIC", "-o", so_of(v), os.path.join(CSRC, "tvq_api.cu")], cwd=CSRC)
+             for v, fl in VARIANTS.items()]
+    for pr in procs:
+        assert pr.wait() == 0
 
-def run(n, k, d, train):
+def run(n, k, d, train, variant=""):
     import torch
-    lib = ctypes.CDLL(SO)
+    lib = ctypes.CDLL(so_of(variant))
+    print('variant', variant or 'base')
     vp, i64, i, u, f, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_size_t
     lib.tvq_forward.argtypes = [vp, vp, i64, i, i, u, f, vp, vp, vp, vp, vp, sz, vp]
     lib.tvq_workspace_bytes.restype = sz
@@ -53,4 +63,5 @@ if __name__ == "__main__":
     if sys.argv[1] == "build":
         build()
     else:
-        run(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), bool(int(sys.argv[5])) if len(sys.argv) > 5 else False)
+        run(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), bool(int(sys.argv[5])) if len(sys.argv) > 5 else False,
+            sys.argv[6] if len(sys.argv) > 6 else "")
