@@ -20,14 +20,18 @@
 //               code tile), ONE THREAD PER LATENT: tcgen05.ld of 32 scores at a time, score =
 //               |e|^2 - 2 x.e (packed FFMA2), 3-input-min tree, running minimum m and threshold
 //               m + bound; a 32-score chunk is looked at again only if its minimum beats the threshold
-//               (rare after the first chunks), and then its candidates go to a small per-latent list in
-//               shared memory.  After the last code tile the two warps of a quadrant merge their minima,
+//               (rare after the first chunks): a straight-line 8-compare mask of the groups of 4 that hold
+//               a hit, then one indexed branch per hit group; the candidates go to a small per-latent list
+//               in shared memory.  After the last code tile the two warps of a quadrant merge their minima,
 //               and each resolves 16 latents (cascade above), gathers the code words, writes idx / q
 //               (straight-through) / loss partial and adds the EMA statistics (red.global.v4).
 //   warps 2-3   converters: x rows fp32 (global, L2-prefetched two tiles ahead) -> bf16 A operand in
 //               UMMA K-major SWIZZLE_128B layout, double buffered; also |x| -> the row's error bound.
+// For k >= 1024 the CTAs work in PAIRS (template parameter CG = 2: 2-CTA clusters, tcgen05 cta_group::2): see
+// the comment at the kernel.
 // Algorithmic cost per latent: 8d + 8 bytes of HBM (x is re-read once from L2 by the apply phase),
 // 2*k*d tensor FLOP.
+// Nothing in the hot loops may spill: with ~225 KB of shared memory the L1 is gone and local memory lives in L2.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -111,6 +115,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 // 32 lanes x 32-bit, 32 consecutive columns per thread.
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+#ifdef TVQ_ABL_NOLD      // ablation build: no TMEM read at all (timing only)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = taddr + i;
+    return;
+#endif
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -188,8 +197,6 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                  ::"r"(bar), "h"((uint16_t)3)
                  : "memory");
 }
-template <int REGS> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
-template <int REGS> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 __device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
 }
