@@ -568,6 +568,9 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                         const uint32_t b0 = b_base + s * pl.stage_bytes;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
+#ifdef TVQ_ABL_NOMMA     // ablation build: no MMA issued (timing of the scan without tensor-pipe / operand traffic)
+                            continue;
+#endif
                             if (CG == 2)
                                 umma_bf16_pair(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
                                                umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
@@ -762,7 +765,14 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 }
                 // -1: a score inside the final threshold was LOST (or the scores were non-finite): exhaustive scan;
                 // 0x100: the spill buffer holds candidates of this latent
-                ncnt[half * kSM + trow] = (sd[kSM] > thr_fin) ? (kept | (sd[0] <= thr_fin ? 0x100 : 0)) : -1;
+                int nres = (sd[kSM] > thr_fin) ? (kept | (sd[0] <= thr_fin ? 0x100 : 0)) : -1;
+                if (!(thr_fin < INF)) {
+                    // non-finite latent (NaN / Inf in x, or scores that overflowed): every distance is NaN or
+                    // infinite and the reference's argmax degenerates; take code 0 instead of an exhaustive scan
+                    lc[0] = 0;
+                    nres = half == 0 ? 1 : 0;
+                }
+                ncnt[half * kSM + trow] = nres;
             }
             named_bar_sync(1 + quad, 64);
             if (half == 0) thrfin[trow] = thr_fin;            // (both halves have read mfin)

@@ -496,3 +496,28 @@ def test_stream_path_duplicated_codes(tvq, n, k, d, dup, noise):
     assert np.array_equal(idx_u.cpu().numpy(), C.assign(x.cpu().numpy(), e.cpu().numpy()))
     if noise == 0.0:
         assert bool((idx_u % dup == 0).all()), "exact duplicates: the first copy must be chosen"
+
+
+@pytest.mark.parametrize("k,d", [(32, 128), (640, 64), (2048, 128)])
+def test_non_finite_latents_do_not_derail(tvq, k, d):
+    """NaN / Inf latents (a diverged encoder) must neither hang nor slow the kernels down (no exhaustive scans),
+    must get a valid code, and must not disturb the finite latents around them."""
+    torch.manual_seed(5)
+    n = 3000
+    x = torch.randn(n, d)
+    bad = torch.tensor([0, 17, 129, 1500, 2999])
+    xb = x.clone()
+    xb[bad[0], 3] = float("nan")
+    xb[bad[1]] = float("inf")
+    xb[bad[2], :] = float("nan")
+    xb[bad[3], 7] = -float("inf")
+    xb[bad[4], 0] = 3e38
+    e = torch.randn(k, d).to(DEV)
+    ws = tvq.Workspace(k, d, torch.device(DEV))
+    idx_ref, _, _ = tvq.vq_forward_raw(x.to(DEV), e, ws, train=False, write_q=False)
+    idx, q, sc = tvq.vq_forward_raw(xb.to(DEV), e, ws, train=True)
+    torch.cuda.synchronize()
+    assert int(idx.min()) >= 0 and int(idx.max()) < k
+    keep = torch.ones(n, dtype=torch.bool)
+    keep[bad] = False
+    assert torch.equal(idx.cpu()[keep], idx_ref.cpu()[keep])
