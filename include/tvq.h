@@ -152,6 +152,18 @@ TVQ_API int tvq_gather(const int64_t *tokens, const float *codebook, int64_t b, 
 TVQ_API int tvq_neg_dist(const float *x, const float *codebook, int64_t n, int k, int d, float *dist,
                  void *stream);
 
+/* Stage-1 STFT front end in ONE kernel: everything the reference derives from a batch of
+ * trajectories x [b, c, l] before the encoders run.  Any output may be NULL.
+ *   xf        [b, 2c, n_fft/2+1, l/hop+1]  time_to_timefreq(x, n_fft, c)          utils/train_utils.py:293-307
+ *   enc_in_l  (same shape)                 zero_pad_high_freq(xf, copy=True)      :361-372 (models/vq_vae.py:179-180)
+ *   enc_in_h  (same shape)                 zero_pad_low_freq(xf, copy=True)       :375-386
+ *   x_l, x_h  [b, c, l]                    F.interpolate(timefreq_to_time(zero_pad_{high,low}_freq(xf)), l, "linear")
+ *                                          trainers/stage1.py:101-113
+ * hop = n_fft / 4, periodic Hann window, reflect-centred, onesided, normalized — the arguments the reference
+ * passes to torch.stft / torch.istft.  n_fft a multiple of 4 in [4, 64], l > n_fft / 2.                      */
+TVQ_API int tvq_frontend(const float *x, int64_t b, int c, int l, int n_fft, float *xf, float *enc_in_l,
+                 float *enc_in_h, float *x_l, float *x_h, void *stream);
+
 /* Dead-code re-seed (vq.py:181-195): embed[j] = x[rows[j]] where cluster_size[j] < threshold.
  * Only `embed` is touched, as in the reference.  rows [k] int64 (drawn by the host).          */
 TVQ_API int tvq_reseed(const float *x, const int64_t *rows, const float *cluster_size, float threshold,

@@ -8,6 +8,7 @@
 
 #include "tvq_aux.cuh"
 #include "tvq_common.cuh"
+#include "tvq_frontend.cuh"
 #include "tvq_fwd_simt.cuh"
 #include "tvq_fwd_stream.cuh"
 #include "tvq_fwd_umma.cuh"
@@ -560,6 +561,32 @@ int tvq_neg_dist(const float* x, const float* codebook, int64_t n, int k, int d,
     int64_t blocks = (n + 7) / 8;
     if (blocks > 16LL * di->sm_count) blocks = 16LL * di->sm_count;
     neg_dist_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, codebook, n, k, d, dist);
+    return launch_status();
+}
+
+int tvq_frontend(const float* x, int64_t b, int c, int l, int n_fft, float* xf, float* enc_in_l, float* enc_in_h, float* x_l,
+                 float* x_h, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (b < 0 || c < 1 || n_fft < 4 || n_fft > 64 || (n_fft & 3) || l <= n_fft / 2 || l / (n_fft / 4) < 1) return TVQ_ERR_UNSUPPORTED;
+    if (b == 0) return TVQ_OK;
+    if (!x) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    const size_t smem = frontend_smem_bytes(l, n_fft);
+    if (smem > (size_t)di->max_smem_optin) return TVQ_ERR_UNSUPPORTED;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    FrontendParams p;
+    p.x = x; p.rows = b * c; p.c = c; p.l = l; p.n_fft = n_fft;
+    p.xf = xf; p.enc_in_l = enc_in_l; p.enc_in_h = enc_in_h; p.x_l = x_l; p.x_h = x_h;
+    int64_t grid = p.rows;
+    if (grid > 16LL * di->sm_count) grid = 16LL * di->sm_count;
+    frontend_kernel<<<(unsigned)grid, 128, smem, stream>>>(p);
     return launch_status();
 }
 

@@ -1,0 +1,133 @@
+// tvq_frontend.cuh — stage-1 STFT front end in ONE kernel: everything the reference derives
+// from a batch of trajectories before the encoders run,
+//   xf        = time_to_timefreq(x)                      utils/train_utils.py:293-307  (torch.stft, hop = n_fft/4,
+//                                                        periodic Hann, reflect-centred, onesided, normalized)
+//   enc_in_l  = zero_pad_high_freq(xf, copy=True)        :361-372   (LF encoder input, models/vq_vae.py:179-180)
+//   enc_in_h  = zero_pad_low_freq(xf, copy=True)         :375-386   (HF encoder input)
+//   x_l       = interpolate(timefreq_to_time(zero_pad_high_freq(xf)), L)   trainers/stage1.py:101-107 (LF target)
+//   x_h       = interpolate(timefreq_to_time(zero_pad_low_freq(xf)), L)    trainers/stage1.py:108-113 (HF target)
+// which the reference computes with three STFTs, two ISTFTs and a dozen elementwise kernels.  For n_fft = 4 the
+// STFT is a 3-tap filter bank, so this is pure HBM-bound stencil work: one CTA per (trajectory, channel) row keeps
+// the row, its spectrum and the two band-limited reconstructions in shared memory; every output is written once,
+// coalesced along time.  Algorithmic bytes per row: 4 L in, 4 (3 * 2 K T + 2 L) out (K = n_fft/2 + 1, T = L/hop + 1).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tvq {
+
+struct FrontendParams {
+    const float* x;        // [b, c, l]
+    int64_t rows;          // b * c
+    int c, l, n_fft;
+    float* xf;             // [b, 2c, K, T] or null
+    float* enc_in_l;       // [b, 2c, K, T] or null
+    float* enc_in_h;       // [b, 2c, K, T] or null
+    float* x_l;            // [b, c, l] or null
+    float* x_h;            // [b, c, l] or null
+};
+
+__global__ void __launch_bounds__(128) frontend_kernel(const FrontendParams p) {
+    extern __shared__ float fsm[];
+    const int N = p.n_fft, half = N >> 1, hop = N >> 2, K = half + 1;
+    const int L = p.l, T = 1 + L / hop, Ly = hop * (T - 1);
+    float* xs = fsm;                        // [L + N]   reflect-padded row
+    float* xr = xs + ((L + N + 3) & ~3);    // [K][T]    Re X
+    float* xi = xr + K * T;                 // [K][T]    Im X
+    float* yl = xi + K * T;                 // [Ly]      LF reconstruction
+    float* yh = yl + Ly;                    // [Ly]      HF reconstruction
+    float* win = yh + Ly;                   // [N]       periodic Hann window
+    float* twc = win + N;                   // [K][N]    cos(2 pi k n / N)
+    float* tws = twc + K * N;               // [K][N]    sin(2 pi k n / N)
+    const int tid = threadIdx.x;
+    const float scale = rsqrtf((float)N);
+    for (int i = tid; i < N; i += blockDim.x) win[i] = 0.5f - 0.5f * cospif(2.0f * (float)i / (float)N);
+    for (int i = tid; i < K * N; i += blockDim.x) {
+        const int k = i / N, n = i % N;
+        const float a = 2.0f * (float)((k * n) % N) / (float)N;      // exact at the multiples of 1/2 that n_fft = 4 uses
+        twc[i] = cospif(a);
+        tws[i] = sinpif(a);
+    }
+    for (int64_t row = blockIdx.x; row < p.rows; row += gridDim.x) {
+        __syncthreads();
+        const float* xrow = p.x + row * L;
+        for (int j = tid; j < L + N; j += blockDim.x) {
+            int s = j - half;
+            s = s < 0 ? -s : (s >= L ? 2 * (L - 1) - s : s);
+            xs[j] = __ldg(xrow + s);
+        }
+        __syncthreads();
+        // ---- STFT: X[k, t] = N^-1/2 sum_n w[n] xp[t hop + n] e^{-2 pi i k n / N}
+        for (int i = tid; i < K * T; i += blockDim.x) {
+            const int k = i / T, t = i % T;
+            float re = 0.f, im = 0.f;
+            for (int n = 0; n < N; ++n) {
+                const float v = win[n] * xs[t * hop + n];
+                re = fmaf(v, twc[k * N + n], re);
+                im = fmaf(-v, tws[k * N + n], im);
+            }
+            xr[i] = re * scale;
+            xi[i] = im * scale;
+        }
+        __syncthreads();
+        // ---- spectrogram-shaped outputs, channel = c * 2 + (0 real | 1 imag): [row][z][k][t]
+        const int64_t obase = row * 2 * K * T;
+        for (int i = tid; i < 2 * K * T; i += blockDim.x) {
+            const int z = i / (K * T), kt = i % (K * T), k = kt / T, t = kt % T;
+            const float* src = z ? xi : xr;
+            if (p.xf) p.xf[obase + i] = src[kt];
+            if (p.enc_in_l) p.enc_in_l[obase + i] = src[t];                              // bin 0 in every band
+            if (p.enc_in_h) p.enc_in_h[obase + i] = src[(k < 1 ? 1 : k) * T + t];        // bin 1 pasted into bin 0
+        }
+        // ---- ISTFT of the two band-limited spectra (overlap-add of windowed inverse frames / window envelope)
+        if (p.x_l || p.x_h) {
+            for (int j = tid; j < Ly; j += blockDim.x) {
+                const int pos = j + half;
+                int t0 = (pos - N + hop) / hop;                    // ceil((pos - N + 1) / hop) for pos - N + 1 > 0
+                t0 = t0 < 0 ? 0 : t0;
+                int t1 = pos / hop;
+                t1 = t1 > T - 1 ? T - 1 : t1;
+                float al = 0.f, ah = 0.f, env = 0.f;
+                for (int t = t0; t <= t1; ++t) {
+                    const int n = pos - t * hop;
+                    if (n < 0 || n >= N) continue;
+                    const float w = win[n];
+                    float fh = (n & 1) ? -xr[half * T + t] : xr[half * T + t];
+                    for (int k = 1; k < half; ++k)
+                        fh += 2.f * (xr[k * T + t] * twc[k * N + n] - xi[k * T + t] * tws[k * N + n]);
+                    al = fmaf(w, xr[t], al);
+                    ah = fmaf(w, fh, ah);
+                    env = fmaf(w, w, env);
+                }
+                yl[j] = al * scale / env;
+                yh[j] = ah * scale / env;
+            }
+            __syncthreads();
+            // ---- F.interpolate(..., size = L, mode = "linear", align_corners = False)
+            const float ratio = (float)Ly / (float)L;       // ATen: float scale, source coordinate with ONE rounding (fma)
+            for (int j = tid; j < L; j += blockDim.x) {
+                float vl, vh;
+                if (Ly == L) {
+                    vl = yl[j]; vh = yh[j];
+                } else {
+                    const float s = fmaxf(fmaf(ratio, (float)j + 0.5f, -0.5f), 0.f);
+                    int i0 = (int)s;
+                    i0 = i0 > Ly - 1 ? Ly - 1 : i0;
+                    const int i1 = i0 + 1 > Ly - 1 ? Ly - 1 : i0 + 1;
+                    const float lam = s - (float)i0;
+                    vl = yl[i0] * (1.f - lam) + yl[i1] * lam;
+                    vh = yh[i0] * (1.f - lam) + yh[i1] * lam;
+                }
+                if (p.x_l) p.x_l[row * L + j] = vl;
+                if (p.x_h) p.x_h[row * L + j] = vh;
+            }
+        }
+    }
+}
+
+inline size_t frontend_smem_bytes(int l, int n_fft) {
+    const int half = n_fft / 2, hop = n_fft / 4, K = half + 1, T = 1 + l / hop, Ly = hop * (T - 1);
+    return (size_t)(((l + n_fft + 3) & ~3) + 2 * K * T + 2 * Ly + n_fft + 2 * K * n_fft) * sizeof(float);
+}
+
+}  // namespace tvq

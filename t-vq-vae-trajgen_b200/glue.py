@@ -1,7 +1,10 @@
 """Layout glue around the VQ call sites of the reference.
 
 `quantize`  mirrors timevqvae/utils/train_utils.py:338-358 (b c h w <-> b (h w) c around the VQ),
-`decode_tokens` mirrors the token -> decoder-input hand-off of timevqvae/models/maskgit.py:465-470.
+`decode_tokens` mirrors the token -> decoder-input hand-off of timevqvae/models/maskgit.py:465-470,
+`lf_hf_frontend` is the whole STFT front end of a stage-1 step in one kernel:
+timevqvae/utils/train_utils.py:293-321, :361-386 as used by trainers/stage1.py:101-113 and
+models/vq_vae.py:179-180; `time_to_timefreq` keeps the reference's name and signature for its first piece.
 """
 from __future__ import annotations
 
@@ -46,3 +49,43 @@ def decode_tokens(s: torch.Tensor, vq_model, h: int, w: int) -> torch.Tensor:
         zq = vq_model.project_out(TF.vq_gather(s, embed)).transpose(1, 2)
     b, c, n = zq.shape
     return zq.reshape(b, c, h, w)
+
+
+@torch.no_grad()
+def lf_hf_frontend(x: torch.Tensor, n_fft: int, *, want=("xf", "enc_in_l", "enc_in_h", "x_l", "x_h")) -> dict:
+    """x (b, c, l) fp32 CUDA -> dict of the tensors stage 1 derives from x before the encoders:
+
+    xf        (b, 2c, n_fft/2+1, l/hop+1)  time_to_timefreq(x, n_fft, c)
+    enc_in_l  same shape                   zero_pad_high_freq(xf, copy=True)   — LF encoder input
+    enc_in_h  same shape                   zero_pad_low_freq(xf, copy=True)    — HF encoder input
+    x_l, x_h  (b, c, l)                    F.interpolate(timefreq_to_time(zero_pad_{high,low}_freq(xf), ...), l, "linear")
+
+    One kernel launch; only the entries named in `want` are produced.  No gradient (x is data; the reference
+    computes these outside the autograd graph of the parameters as well)."""
+    TF._need(x, "x")
+    if x.dim() != 3:
+        raise ValueError("x must be (b, c, l)")
+    b, c, l = x.shape
+    hop = n_fft // 4
+    if n_fft % 4 or not 4 <= n_fft <= 64 or l <= n_fft // 2:
+        raise NotImplementedError(f"n_fft={n_fft}, l={l}: the front-end kernel needs n_fft % 4 == 0, 4 <= n_fft <= 64, l > n_fft / 2")
+    k, t = n_fft // 2 + 1, l // hop + 1
+    out = {}
+    for name in want:
+        shape = (b, c, l) if name in ("x_l", "x_h") else (b, 2 * c, k, t)
+        out[name] = torch.empty(shape, dtype=torch.float32, device=x.device)
+    ptr = lambda name: out[name].data_ptr() if name in out else None
+    lib = TF._lib.load()
+    rc = lib.tvq_frontend(x.data_ptr(), b, c, l, n_fft, ptr("xf"), ptr("enc_in_l"), ptr("enc_in_h"), ptr("x_l"), ptr("x_h"),
+                          TF._stream())
+    TF._lib.check(rc, "tvq_frontend")
+    return out
+
+
+def time_to_timefreq(x: torch.Tensor, n_fft: int, C: int, norm: bool = True) -> torch.Tensor:
+    """Reference name and signature (utils/train_utils.py:293): x (B, C, L) -> (B, 2C, n_fft/2+1, T)."""
+    if not norm:
+        raise NotImplementedError("the reference only ever calls time_to_timefreq with norm=True")
+    if x.shape[1] != C:
+        raise ValueError(f"x has {x.shape[1]} channels, C={C}")
+    return lf_hf_frontend(x.contiguous(), n_fft, want=("xf",))["xf"]
