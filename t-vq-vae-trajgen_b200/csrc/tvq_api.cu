@@ -584,8 +584,8 @@ int tvq_frontend(const float* x, int64_t b, int c, int l, int n_fft, float* xf, 
     FrontendParams p;
     p.x = x; p.rows = b * c; p.c = c; p.l = l; p.n_fft = n_fft;
     p.xf = xf; p.enc_in_l = enc_in_l; p.enc_in_h = enc_in_h; p.x_l = x_l; p.x_h = x_h;
-    int64_t grid = p.rows;
-    if (grid > 16LL * di->sm_count) grid = 16LL * di->sm_count;
+    int64_t grid = p.rows;                                   // one CTA per row: CTAs retire and start independently
+    if (grid > 64LL * di->sm_count) grid = 64LL * di->sm_count;
     frontend_kernel<<<(unsigned)grid, 128, smem, stream>>>(p);
     return launch_status();
 }

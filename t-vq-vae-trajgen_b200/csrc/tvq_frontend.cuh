@@ -57,30 +57,72 @@ __global__ void __launch_bounds__(128) frontend_kernel(const FrontendParams p) {
             xs[j] = __ldg(xrow + s);
         }
         __syncthreads();
-        // ---- STFT: X[k, t] = N^-1/2 sum_n w[n] xp[t hop + n] e^{-2 pi i k n / N}
-        for (int i = tid; i < K * T; i += blockDim.x) {
-            const int k = i / T, t = i % T;
-            float re = 0.f, im = 0.f;
-            for (int n = 0; n < N; ++n) {
-                const float v = win[n] * xs[t * hop + n];
-                re = fmaf(v, twc[k * N + n], re);
-                im = fmaf(-v, tws[k * N + n], im);
+        // ---- STFT: X[k, t] = N^-1/2 sum_n w[n] xp[t hop + n] e^{-2 pi i k n / N}   (t across threads: no index division)
+        if (N == 4) {
+            // the shipped configuration (configs/config.yaml: n_fft 4): window (0, 1/2, 1, 1/2), twiddles in {0, +-1, +-i}:
+            // a 3-tap filter bank, written out
+            for (int t = tid; t < T; t += blockDim.x) {
+                const float v1 = 0.5f * xs[t + 1], v2 = xs[t + 2], v3 = 0.5f * xs[t + 3];
+                xr[t] = 0.5f * ((v1 + v2) + v3);            xi[t] = 0.f;
+                xr[T + t] = -0.5f * v2;                     xi[T + t] = 0.5f * (v3 - v1);
+                xr[2 * T + t] = 0.5f * ((v2 - v1) - v3);    xi[2 * T + t] = 0.f;
             }
-            xr[i] = re * scale;
-            xi[i] = im * scale;
+        } else {
+            for (int t = tid; t < T; t += blockDim.x) {
+                for (int k = 0; k < K; ++k) {
+                    float re = 0.f, im = 0.f;
+                    for (int n = 0; n < N; ++n) {
+                        const float v = win[n] * xs[t * hop + n];
+                        re = fmaf(v, twc[k * N + n], re);
+                        im = fmaf(-v, tws[k * N + n], im);
+                    }
+                    xr[k * T + t] = re * scale;
+                    xi[k * T + t] = im * scale;
+                }
+            }
         }
         __syncthreads();
-        // ---- spectrogram-shaped outputs, channel = c * 2 + (0 real | 1 imag): [row][z][k][t]
+        // ---- spectrogram-shaped outputs, channel = c * 2 + (0 real | 1 imag): [row][z][k][t], coalesced along t
         const int64_t obase = row * 2 * K * T;
-        for (int i = tid; i < 2 * K * T; i += blockDim.x) {
-            const int z = i / (K * T), kt = i % (K * T), k = kt / T, t = kt % T;
+        for (int zk = 0; zk < 2 * K; ++zk) {
+            const int z = zk >= K, k = zk - z * K;
             const float* src = z ? xi : xr;
-            if (p.xf) p.xf[obase + i] = src[kt];
-            if (p.enc_in_l) p.enc_in_l[obase + i] = src[t];                              // bin 0 in every band
-            if (p.enc_in_h) p.enc_in_h[obase + i] = src[(k < 1 ? 1 : k) * T + t];        // bin 1 pasted into bin 0
+            const int kh = (k < 1 ? 1 : k) * T;
+            for (int t = tid; t < T; t += blockDim.x) {
+                const int64_t o = obase + (int64_t)zk * T + t;
+                if (p.xf) p.xf[o] = src[k * T + t];
+                if (p.enc_in_l) p.enc_in_l[o] = src[t];                  // bin 0 in every band
+                if (p.enc_in_h) p.enc_in_h[o] = src[kh + t];             // bin 1 pasted into bin 0
+            }
         }
         // ---- ISTFT of the two band-limited spectra (overlap-add of windowed inverse frames / window envelope)
         if (p.x_l || p.x_h) {
+            if (N == 4) {
+                // frames t = j + 1, j, j - 1 reach sample j with window taps n = 1, 2, 3 (tap 0 is zero)
+                for (int j = tid; j < Ly; j += blockDim.x) {
+                    float al = 0.f, ah = 0.f, env = 0.f;
+                    if (j + 1 <= T - 1) {                          // n = 1, w = 1/2
+                        const int t = j + 1;
+                        al += 0.5f * xr[t];
+                        ah += 0.5f * (-xr[2 * T + t] - 2.f * xi[T + t]);
+                        env += 0.25f;
+                    }
+                    {                                              // n = 2, w = 1
+                        const int t = j;
+                        al += xr[t];
+                        ah += xr[2 * T + t] - 2.f * xr[T + t];
+                        env += 1.f;
+                    }
+                    if (j >= 1) {                                  // n = 3, w = 1/2
+                        const int t = j - 1;
+                        al += 0.5f * xr[t];
+                        ah += 0.5f * (-xr[2 * T + t] + 2.f * xi[T + t]);
+                        env += 0.25f;
+                    }
+                    yl[j] = al * 0.5f / env;
+                    yh[j] = ah * 0.5f / env;
+                }
+            } else
             for (int j = tid; j < Ly; j += blockDim.x) {
                 const int pos = j + half;
                 int t0 = (pos - N + hop) / hop;                    // ceil((pos - N + 1) / hop) for pos - N + 1 > 0
