@@ -164,6 +164,14 @@ TVQ_API int tvq_neg_dist(const float *x, const float *codebook, int64_t n, int k
 TVQ_API int tvq_frontend(const float *x, int64_t b, int c, int l, int n_fft, float *xf, float *enc_in_l,
                  float *enc_in_h, float *x_l, float *x_h, void *stream);
 
+/* Decoder side of the STFT front end (models/vq_vae.py:259-262, utils/train_utils.py:310-321, :361-386):
+ *   y = F.interpolate(timefreq_to_time(pad_func(u), n_fft, c), l, "linear")   for u [b, 2c, n_fft/2+1, l/hop+1]
+ * with pad_func = identity (band 0), zero_pad_high_freq (band 1: keep bin 0) or zero_pad_low_freq (band 2: keep
+ * bins 1..), in ONE kernel; the backward (adjoint) writes g_u, zero in the bands pad_func removed.            */
+TVQ_API int tvq_band_istft(const float *u, int64_t b, int c, int l, int n_fft, int band, float *y, void *stream);
+TVQ_API int tvq_band_istft_backward(const float *g_y, int64_t b, int c, int l, int n_fft, int band, float *g_u,
+                            void *stream);
+
 /* Dead-code re-seed (vq.py:181-195): embed[j] = x[rows[j]] where cluster_size[j] < threshold.
  * Only `embed` is touched, as in the reference.  rows [k] int64 (drawn by the host).          */
 TVQ_API int tvq_reseed(const float *x, const int64_t *rows, const float *cluster_size, float threshold,

@@ -92,3 +92,9 @@ def frontend(x, n_fft):
             "enc_in_h": zero_pad_low_freq(xf, copy=True).astype(np.float32),
             "x_l": interp_linear(istft(u_l, n_fft), l).astype(np.float32),
             "x_h": interp_linear(istft(u_h, n_fft), l).astype(np.float32)}
+
+
+def band_istft(u, n_fft, band, length):
+    """models/vq_vae.py:259-262: F.interpolate(timefreq_to_time(pad_func(u)), length, 'linear'); band all | lf | hf."""
+    v = u if band == "all" else (zero_pad_high_freq(u) if band == "lf" else zero_pad_low_freq(u))
+    return interp_linear(istft(v, n_fft), length).astype(np.float32)

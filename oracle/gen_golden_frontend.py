@@ -28,5 +28,25 @@ def main():
         print(name, tuple(xf.shape), tuple(x_l.shape))
 
 
+def decoder_side():
+    """models/vq_vae.py:259-262: pad_func -> timefreq_to_time -> interpolate, forward and autograd backward."""
+    _, _, tu = G.load_reference()
+    for name, (b, c, l, n_fft) in {"istft_cfg1": (4, 4, 200, 4), "istft_nfft8": (2, 3, 96, 8), "istft_interp": (2, 2, 333, 8)}.items():
+        g = torch.Generator().manual_seed(11 + l)
+        hop = n_fft // 4
+        u = torch.randn(b, 2 * c, n_fft // 2 + 1, l // hop + 1, generator=g)
+        gy = torch.randn(b, c, l, generator=g)
+        rec = {"u": u.numpy(), "g_y": gy.numpy(), "n_fft": np.int64(n_fft)}
+        for band, pad in (("all", lambda t: t), ("lf", tu.zero_pad_high_freq), ("hf", tu.zero_pad_low_freq)):
+            uu = u.clone().requires_grad_(True)
+            y = F.interpolate(tu.timefreq_to_time(pad(uu), n_fft, c), l, mode="linear")
+            (y * gy).sum().backward()
+            rec["y_" + band] = y.detach().numpy()
+            rec["g_u_" + band] = uu.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, tuple(u.shape))
+
+
 if __name__ == "__main__":
+    decoder_side()
     main()

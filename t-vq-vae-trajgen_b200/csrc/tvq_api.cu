@@ -590,6 +590,48 @@ int tvq_frontend(const float* x, int64_t b, int c, int l, int n_fft, float* xf, 
     return launch_status();
 }
 
+}  // extern "C"
+
+namespace {
+template <bool BACKWARD>
+int launch_band_istft(const BandIstftParams& p, int64_t b, int c, cudaStream_t stream) {
+    if (b < 0 || c < 1 || p.n_fft < 4 || p.n_fft > 64 || (p.n_fft & 3) || p.l <= p.n_fft / 2 || p.band < 0 || p.band > 2)
+        return TVQ_ERR_UNSUPPORTED;
+    if (b == 0) return TVQ_OK;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    const size_t smem = band_istft_smem_bytes(p.l, p.n_fft);
+    if (smem > (size_t)di->max_smem_optin) return TVQ_ERR_UNSUPPORTED;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(band_istft_kernel<BACKWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    int64_t grid = p.rows;
+    if (grid > 64LL * di->sm_count) grid = 64LL * di->sm_count;
+    band_istft_kernel<BACKWARD><<<(unsigned)grid, 128, smem, stream>>>(p);
+    return launch_status();
+}
+}  // namespace
+
+extern "C" {
+
+int tvq_band_istft(const float* u, int64_t b, int c, int l, int n_fft, int band, float* y, void* stream_) {
+    if (b > 0 && (!u || !y)) return TVQ_ERR_BAD_ARG;
+    BandIstftParams p;
+    p.u = u; p.g_y = nullptr; p.y = y; p.g_u = nullptr; p.rows = b * c; p.l = l; p.n_fft = n_fft; p.band = band;
+    return launch_band_istft<false>(p, b, c, (cudaStream_t)stream_);
+}
+
+int tvq_band_istft_backward(const float* g_y, int64_t b, int c, int l, int n_fft, int band, float* g_u, void* stream_) {
+    if (b > 0 && (!g_y || !g_u)) return TVQ_ERR_BAD_ARG;
+    BandIstftParams p;
+    p.u = nullptr; p.g_y = g_y; p.y = nullptr; p.g_u = g_u; p.rows = b * c; p.l = l; p.n_fft = n_fft; p.band = band;
+    return launch_band_istft<true>(p, b, c, (cudaStream_t)stream_);
+}
+
 int tvq_reseed(const float* x, const int64_t* rows, const float* cluster_size, float threshold, float* embed,
                int64_t n, int k, int d, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

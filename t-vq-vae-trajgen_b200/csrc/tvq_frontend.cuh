@@ -173,3 +173,152 @@ inline size_t frontend_smem_bytes(int l, int n_fft) {
 }
 
 }  // namespace tvq
+
+// ------------------------------------------------------------------------------------------------------------
+// Decoder side (models/vq_vae.py:259-262): y = F.interpolate(timefreq_to_time(pad_func(u)), L) for a spectrogram-
+// shaped decoder output u [b, 2c, K, T], where pad_func zeroes every band but one side (zero_pad_high_freq keeps bin
+// 0, zero_pad_low_freq keeps bins 1..).  Forward and backward (the op is linear, the backward is its adjoint: an
+// STFT-like analysis of g / envelope) as one kernel each; the zeroed bands never leave the kernel, their gradient is
+// written as zeros.  band: 0 = all bins (plain timefreq_to_time), 1 = LF (bin 0), 2 = HF (bins >= 1).
+namespace tvq {
+
+struct BandIstftParams {
+    const float* u;        // forward: [b, 2c, K, T] in;  backward: unused
+    const float* g_y;      // backward: [b, c, l] in
+    float* y;              // forward: [b, c, l] out
+    float* g_u;            // backward: [b, 2c, K, T] out
+    int64_t rows;          // b * c
+    int l, n_fft, band;
+};
+
+// window envelope sum_t w^2[j + N/2 - t hop] over the frames that exist (torch.istft's normalisation)
+__device__ __forceinline__ float istft_envelope(const float* win, int j, int N, int hop, int T) {
+    const int pos = j + (N >> 1);
+    int t0 = (pos - N + hop) / hop;
+    t0 = t0 < 0 ? 0 : t0;
+    int t1 = pos / hop;
+    t1 = t1 > T - 1 ? T - 1 : t1;
+    float env = 0.f;
+    for (int t = t0; t <= t1; ++t) {
+        const int n = pos - t * hop;
+        if (n >= 0 && n < N) env = fmaf(win[n], win[n], env);
+    }
+    return env;
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(128) band_istft_kernel(const BandIstftParams p) {
+    extern __shared__ float fsm[];
+    const int N = p.n_fft, half = N >> 1, hop = N >> 2, K = half + 1;
+    const int L = p.l, T = 1 + L / hop, Ly = hop * (T - 1);
+    float* xr = fsm;                        // [K][T]
+    float* xi = xr + K * T;                 // [K][T]
+    float* ys = xi + K * T;                 // [Ly]   signal before the interpolation (forward) / its gradient / envelope (backward)
+    float* win = ys + ((Ly + 3) & ~3);      // [N]
+    float* twc = win + N;                   // [K][N]
+    float* tws = twc + K * N;               // [K][N]
+    const int tid = threadIdx.x;
+    const float scale = rsqrtf((float)N);
+    const int k_lo = p.band == 2 ? 1 : 0, k_hi = p.band == 1 ? 0 : half;     // bins that survive pad_func
+    for (int i = tid; i < N; i += blockDim.x) win[i] = 0.5f - 0.5f * cospif(2.0f * (float)i / (float)N);
+    for (int i = tid; i < K * N; i += blockDim.x) {
+        const int k = i / N, n = i % N;
+        const float a = 2.0f * (float)((k * n) % N) / (float)N;
+        twc[i] = cospif(a);
+        tws[i] = sinpif(a);
+    }
+    const float ratio = (float)Ly / (float)L;
+    for (int64_t row = blockIdx.x; row < p.rows; row += gridDim.x) {
+        __syncthreads();
+        const int64_t ubase = row * 2 * K * T;
+        if (!BACKWARD) {
+            for (int zk = 0; zk < 2 * K; ++zk) {
+                const int z = zk >= K, k = zk - z * K;
+                float* dst = (z ? xi : xr) + k * T;
+                const bool keep = k >= k_lo && k <= k_hi;
+                for (int t = tid; t < T; t += blockDim.x) dst[t] = keep ? __ldg(p.u + ubase + (int64_t)zk * T + t) : 0.f;
+            }
+            __syncthreads();
+            for (int j = tid; j < Ly; j += blockDim.x) {
+                const int pos = j + half;
+                int t0 = (pos - N + hop) / hop;
+                t0 = t0 < 0 ? 0 : t0;
+                int t1 = pos / hop;
+                t1 = t1 > T - 1 ? T - 1 : t1;
+                float acc = 0.f, env = 0.f;
+                for (int t = t0; t <= t1; ++t) {
+                    const int n = pos - t * hop;
+                    if (n < 0 || n >= N) continue;
+                    float f = xr[t] + ((n & 1) ? -xr[half * T + t] : xr[half * T + t]);       // DC and Nyquist: real parts only
+                    for (int k = 1; k < half; ++k)
+                        f += 2.f * (xr[k * T + t] * twc[k * N + n] - xi[k * T + t] * tws[k * N + n]);
+                    acc = fmaf(win[n], f, acc);
+                    env = fmaf(win[n], win[n], env);
+                }
+                ys[j] = acc * scale / env;
+            }
+            __syncthreads();
+            for (int j = tid; j < L; j += blockDim.x) {
+                float v;
+                if (Ly == L) {
+                    v = ys[j];
+                } else {
+                    const float s = fmaxf(fmaf(ratio, (float)j + 0.5f, -0.5f), 0.f);
+                    int i0 = (int)s;
+                    i0 = i0 > Ly - 1 ? Ly - 1 : i0;
+                    const int i1 = i0 + 1 > Ly - 1 ? Ly - 1 : i0 + 1;
+                    const float lam = s - (float)i0;
+                    v = ys[i0] * (1.f - lam) + ys[i1] * lam;
+                }
+                p.y[row * L + j] = v;
+            }
+        } else {
+            // adjoint of the interpolation, then g~[j] = g[j] * scale / envelope[j]
+            for (int j = tid; j < Ly; j += blockDim.x) ys[j] = 0.f;
+            __syncthreads();
+            for (int j = tid; j < L; j += blockDim.x) {
+                const float g = __ldg(p.g_y + row * L + j);
+                if (Ly == L) {
+                    ys[j] = g;
+                } else {
+                    const float s = fmaxf(fmaf(ratio, (float)j + 0.5f, -0.5f), 0.f);
+                    int i0 = (int)s;
+                    i0 = i0 > Ly - 1 ? Ly - 1 : i0;
+                    const int i1 = i0 + 1 > Ly - 1 ? Ly - 1 : i0 + 1;
+                    const float lam = s - (float)i0;
+                    atomicAdd(ys + i0, g * (1.f - lam));
+                    atomicAdd(ys + i1, g * lam);
+                }
+            }
+            __syncthreads();
+            for (int j = tid; j < Ly; j += blockDim.x) ys[j] = ys[j] * scale / istft_envelope(win, j, N, hop, T);
+            __syncthreads();
+            // g_X[k, t] = c_k sum_n g~[t hop + n - N/2] w[n] (cos, -sin)(2 pi k n / N);  c = 1 for DC / Nyquist (cos only), 2 otherwise
+            for (int zk = 0; zk < 2 * K; ++zk) {
+                const int z = zk >= K, k = zk - z * K;
+                const bool keep = k >= k_lo && k <= k_hi && !(z && (k == 0 || k == half));
+                const float ck = (k == 0 || k == half) ? 1.f : 2.f;
+                for (int t = tid; t < T; t += blockDim.x) {
+                    float acc = 0.f;
+                    if (keep) {
+                        for (int n = 0; n < N; ++n) {
+                            const int j = t * hop + n - half;
+                            if (j < 0 || j >= Ly) continue;
+                            const float tw = z ? -tws[k * N + n] : twc[k * N + n];
+                            acc = fmaf(ys[j] * win[n], tw, acc);
+                        }
+                        acc *= ck;
+                    }
+                    p.g_u[ubase + (int64_t)zk * T + t] = acc;
+                }
+            }
+        }
+    }
+}
+
+inline size_t band_istft_smem_bytes(int l, int n_fft) {
+    const int half = n_fft / 2, hop = n_fft / 4, K = half + 1, T = 1 + l / hop, Ly = hop * (T - 1);
+    return (size_t)(2 * K * T + ((Ly + 3) & ~3) + n_fft + 2 * K * n_fft) * sizeof(float);
+}
+
+}  // namespace tvq

@@ -4,7 +4,9 @@
 `decode_tokens` mirrors the token -> decoder-input hand-off of timevqvae/models/maskgit.py:465-470,
 `lf_hf_frontend` is the whole STFT front end of a stage-1 step in one kernel:
 timevqvae/utils/train_utils.py:293-321, :361-386 as used by trainers/stage1.py:101-113 and
-models/vq_vae.py:179-180; `time_to_timefreq` keeps the reference's name and signature for its first piece.
+models/vq_vae.py:179-180; `time_to_timefreq` keeps the reference's name and signature for its first piece;
+`band_timefreq_to_time` is the decoder side (models/vq_vae.py:259-262): pad_func + timefreq_to_time + interpolate,
+differentiable, one kernel per direction; `timefreq_to_time` keeps the reference's name for the plain ISTFT.
 """
 from __future__ import annotations
 
@@ -89,3 +91,53 @@ def time_to_timefreq(x: torch.Tensor, n_fft: int, C: int, norm: bool = True) -> 
     if x.shape[1] != C:
         raise ValueError(f"x has {x.shape[1]} channels, C={C}")
     return lf_hf_frontend(x.contiguous(), n_fft, want=("xf",))["xf"]
+
+
+class _BandISTFT(torch.autograd.Function):
+    """y = F.interpolate(timefreq_to_time(pad_func(u), n_fft, c), length, 'linear'); linear in u, backward = adjoint."""
+
+    @staticmethod
+    def forward(ctx, u, n_fft, band, length):
+        TF._need(u, "u")
+        b, c2, k, t = u.shape
+        c = c2 // 2
+        y = torch.empty(b, c, length, dtype=torch.float32, device=u.device)
+        rc = TF._lib.load().tvq_band_istft(u.data_ptr(), b, c, length, n_fft, band, y.data_ptr(), TF._stream())
+        TF._lib.check(rc, "tvq_band_istft")
+        ctx.meta = (b, c, k, t, n_fft, band, length)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        b, c, k, t, n_fft, band, length = ctx.meta
+        g_y = g_y.contiguous()
+        g_u = torch.empty(b, 2 * c, k, t, dtype=torch.float32, device=g_y.device)
+        rc = TF._lib.load().tvq_band_istft_backward(g_y.data_ptr(), b, c, length, n_fft, band, g_u.data_ptr(), TF._stream())
+        TF._lib.check(rc, "tvq_band_istft_backward")
+        return g_u, None, None, None
+
+
+_BANDS = {"all": 0, None: 0, "lf": 1, "LF": 1, "hf": 2, "HF": 2}
+
+
+def band_timefreq_to_time(u: torch.Tensor, n_fft: int, C: int, band="all", length=None) -> torch.Tensor:
+    """Decoder output u (B, 2C, n_fft/2+1, T) -> time series (B, C, length), differentiable in u.
+
+    band "lf": zero_pad_high_freq(u) first (keep bin 0); "hf": zero_pad_low_freq(u) (keep bins 1..); "all": none.
+    Equals F.interpolate(timefreq_to_time(pad_func(u), n_fft, C), length, mode="linear") of the reference
+    (models/vq_vae.py:259-262); length defaults to the ISTFT's own length, hop * (T - 1)."""
+    if u.dim() != 4 or u.shape[1] != 2 * C or u.shape[2] != n_fft // 2 + 1:
+        raise ValueError(f"u must be (B, {2 * C}, {n_fft // 2 + 1}, T), got {tuple(u.shape)}")
+    hop = n_fft // 4
+    ly = hop * (u.shape[3] - 1)
+    length = ly if length is None else int(length)
+    if length // hop + 1 != u.shape[3]:
+        raise NotImplementedError("the kernel derives T from the output length: need length // hop + 1 == T")
+    return _BandISTFT.apply(u.contiguous().float(), n_fft, _BANDS[band], length)
+
+
+def timefreq_to_time(x: torch.Tensor, n_fft: int, C: int, norm: bool = True) -> torch.Tensor:
+    """Reference name and signature (utils/train_utils.py:310): (B, 2C, N, T) -> (B, C, hop * (T - 1))."""
+    if not norm:
+        raise NotImplementedError("the reference only ever calls timefreq_to_time with norm=True")
+    return band_timefreq_to_time(x, n_fft, C, "all", None)

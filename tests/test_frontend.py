@@ -67,3 +67,54 @@ def test_full_batch_properties(tvq):
     assert torch.equal(out["enc_in_l"], xf[:, :, [0], :].expand_as(xf))
     assert torch.equal(out["enc_in_h"][:, :, 1:], xf[:, :, 1:]) and torch.equal(out["enc_in_h"][:, :, 0], xf[:, :, 1])
     assert float(xf[:, 1::2, 0].abs().max()) == 0.0 and float(xf[:, 1::2, -1].abs().max()) < 1e-6     # DC / Nyquist are real
+
+
+# ------------------------------------------------------------------ decoder side: pad_func + ISTFT + interpolate
+
+ISTFT_CASES = ["istft_cfg1", "istft_nfft8", "istft_interp"]
+
+
+@pytest.mark.parametrize("name", ISTFT_CASES)
+def test_band_istft_oracle_matches_reference_golden(name):
+    g = load_golden(name)
+    l = g["g_y"].shape[-1]
+    for band in ("all", "lf", "hf"):
+        ref = g["y_" + band]
+        np.testing.assert_allclose(FO.band_istft(g["u"], int(g["n_fft"]), band, l), ref, rtol=0,
+                                   atol=2e-6 * max(1.0, float(np.abs(ref).max())), err_msg=band)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ISTFT_CASES)
+def test_band_istft_kernel_matches_reference_golden(tvq, name):
+    """Forward and autograd backward against the unmodified reference (models/vq_vae.py:259-262 under torch autograd)."""
+    g = load_golden(name)
+    n_fft = int(g["n_fft"])
+    gy = torch.from_numpy(g["g_y"]).cuda()
+    c, l = gy.shape[1], gy.shape[2]
+    for band in ("all", "lf", "hf"):
+        u = torch.from_numpy(g["u"]).cuda().requires_grad_(True)
+        y = tvq.band_timefreq_to_time(u, n_fft, c, band, l)
+        (y * gy).sum().backward()
+        ry, rg = torch.from_numpy(g["y_" + band]), torch.from_numpy(g["g_u_" + band])
+        torch.testing.assert_close(y.detach().cpu(), ry, rtol=0, atol=1e-5 * max(1.0, float(ry.abs().max())), msg=lambda m: f"y {band}: {m}")
+        torch.testing.assert_close(u.grad.cpu(), rg, rtol=0, atol=1e-5 * max(1.0, float(rg.abs().max())), msg=lambda m: f"g_u {band}: {m}")
+    if l % (n_fft // 4) == 0:
+        u = torch.from_numpy(g["u"]).cuda()
+        torch.testing.assert_close(tvq.timefreq_to_time(u, n_fft, c).cpu(), torch.from_numpy(g["y_all"]), rtol=0, atol=1e-5 * 4)
+
+
+@pytest.mark.gpu
+def test_band_istft_is_adjoint_and_inverts_the_front_end(tvq):
+    """BASELINE batch: <A u, g> == <u, A^T g> (the backward is the exact adjoint), and ISTFT(STFT(x)) == x."""
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand(1024, 4, 200, device="cuda", generator=gen) * 2 - 1
+    xf = tvq.lf_hf_frontend(x, 4, want=("xf",))["xf"]
+    torch.testing.assert_close(tvq.band_timefreq_to_time(xf, 4, 4, "all", 200), x, rtol=0, atol=2e-6)
+    for band in ("all", "lf", "hf"):
+        u = torch.randn(64, 8, 3, 201, device="cuda", generator=gen).requires_grad_(True)
+        g = torch.randn(64, 4, 200, device="cuda", generator=gen)
+        y = tvq.band_timefreq_to_time(u, 4, 4, band, 200)
+        (gu,) = torch.autograd.grad(y, u, g)
+        lhs, rhs = float((y.detach().double() * g.double()).sum()), float((u.detach().double() * gu.double()).sum())
+        assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0), (band, lhs, rhs)
