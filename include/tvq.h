@@ -172,6 +172,16 @@ TVQ_API int tvq_band_istft(const float *u, int64_t b, int c, int l, int n_fft, i
 TVQ_API int tvq_band_istft_backward(const float *g_y, int64_t b, int c, int l, int n_fft, int band, float *g_u,
                             void *stream);
 
+/* ONE MaskGIT decoding iteration after the transformer, one kernel:
+ * /root/reference/timevqvae/models/maskgit.py:300-346 (= :364-410) with mask_by_random_topk :238-267.
+ *   logits [b,n,k]; s [b,n] current tokens (mask_token_id = unknown); q [b,n,k] Exp(1) noise of the categorical draw
+ *   (Categorical.sample() = argmax(probs / q)); u [b,n] U(0,1) noise of the Gumbel perturbation; mask_len positions
+ *   with the lowest log(p + 1e-5) + temperature * Gumbel(u) are re-masked (known tokens have confidence inf).
+ *   s_new [b,n] out; sampled [b,n] (ids before re-masking) and masking [b,n] (uint8) optional.               */
+TVQ_API int tvq_maskgit_step(const float *logits, const int64_t *s, const float *q, const float *u, int64_t b, int n,
+                     int k, int64_t mask_token_id, int mask_len, float temperature, int64_t *s_new,
+                     int64_t *sampled, uint8_t *masking, void *stream);
+
 /* Dead-code re-seed (vq.py:181-195): embed[j] = x[rows[j]] where cluster_size[j] < threshold.
  * Only `embed` is touched, as in the reference.  rows [k] int64 (drawn by the host).          */
 TVQ_API int tvq_reseed(const float *x, const int64_t *rows, const float *cluster_size, float threshold,

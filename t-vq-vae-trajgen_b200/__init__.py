@@ -9,9 +9,10 @@ from . import _lib
 from .functional import (PeerExchange, VQTrainStep, Workspace, stats_len, stats_offset, vq_backward, vq_ema_update,
                          vq_ema_update_dp,
                          vq_forward_raw, vq_gather, vq_neg_dist, vq_reseed, vq_train_step_raw)
-from .glue import band_timefreq_to_time, decode_tokens, lf_hf_frontend, quantize, time_to_timefreq, timefreq_to_time
+from .glue import (band_timefreq_to_time, decode_tokens, lf_hf_frontend, maskgit_step, quantize, time_to_timefreq,
+                   timefreq_to_time)
 from .vq import EuclideanCodebook, VectorQuantize
 
-__all__ = ["VectorQuantize", "EuclideanCodebook", "quantize", "decode_tokens", "lf_hf_frontend", "time_to_timefreq", "timefreq_to_time", "band_timefreq_to_time", "vq_forward_raw", "vq_ema_update", "vq_ema_update_dp", "PeerExchange",
+__all__ = ["VectorQuantize", "EuclideanCodebook", "quantize", "decode_tokens", "lf_hf_frontend", "time_to_timefreq", "timefreq_to_time", "band_timefreq_to_time", "maskgit_step", "vq_forward_raw", "vq_ema_update", "vq_ema_update_dp", "PeerExchange",
            "vq_train_step_raw", "vq_backward", "vq_gather", "vq_neg_dist", "vq_reseed", "Workspace", "VQTrainStep", "stats_len",
            "stats_offset", "_lib"]

@@ -12,6 +12,7 @@
 #include "tvq_fwd_simt.cuh"
 #include "tvq_fwd_stream.cuh"
 #include "tvq_fwd_umma.cuh"
+#include "tvq_maskgit.cuh"
 
 using namespace tvq;
 
@@ -630,6 +631,25 @@ int tvq_band_istft_backward(const float* g_y, int64_t b, int c, int l, int n_fft
     BandIstftParams p;
     p.u = nullptr; p.g_y = g_y; p.y = nullptr; p.g_u = g_u; p.rows = b * c; p.l = l; p.n_fft = n_fft; p.band = band;
     return launch_band_istft<true>(p, b, c, (cudaStream_t)stream_);
+}
+
+int tvq_maskgit_step(const float* logits, const int64_t* s, const float* q, const float* u, int64_t b, int n, int k,
+                     int64_t mask_token_id, int mask_len, float temperature, int64_t* s_new, int64_t* sampled, uint8_t* masking,
+                     void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (b < 0 || n < 1 || k < 1 || n > 8192 || mask_len < 0) return TVQ_ERR_UNSUPPORTED;
+    if (b == 0) return TVQ_OK;
+    if (!logits || !s || !q || !u || !s_new) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    MaskgitParams p;
+    p.logits = logits; p.s = s; p.q = q; p.u = u; p.b = b; p.n = n; p.k = k; p.mask_token_id = mask_token_id;
+    p.mask_len = mask_len; p.temperature = temperature; p.s_new = s_new; p.sampled = sampled; p.masking = masking;
+    int64_t grid = b;
+    if (grid > 32LL * di->sm_count) grid = 32LL * di->sm_count;
+    maskgit_step_kernel<<<(unsigned)grid, 128, (size_t)n * 8, stream>>>(p);
+    return launch_status();
 }
 
 int tvq_reseed(const float* x, const int64_t* rows, const float* cluster_size, float threshold, float* embed,

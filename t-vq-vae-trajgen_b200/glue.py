@@ -141,3 +141,31 @@ def timefreq_to_time(x: torch.Tensor, n_fft: int, C: int, norm: bool = True) -> 
     if not norm:
         raise NotImplementedError("the reference only ever calls timefreq_to_time with norm=True")
     return band_timefreq_to_time(x, n_fft, C, "all", None)
+
+
+@torch.no_grad()
+def maskgit_step(logits: torch.Tensor, s: torch.Tensor, mask_token_id: int, mask_len: int, temperature: float, *,
+                 generator=None, noise=None, return_details: bool = False):
+    """One MaskGIT decoding iteration after the transformer (models/maskgit.py:300-346 / :364-410 incl.
+    mask_by_random_topk :238-267) in one kernel: logits (b, n, K), s (b, n) int64 -> new s (b, n).
+
+    The noise is drawn from torch's generator exactly as the reference draws it — first the Exp(1) tensor of
+    Categorical.sample() (torch.multinomial's one-draw path: argmax(probs / q)), then the U(0,1) tensor of the Gumbel
+    perturbation — so the same generator state gives the reference's tokens; pass noise=(q, u) to supply it."""
+    TF._need(logits, "logits"); TF._need(s, "s", torch.int64)
+    b, n, k = logits.shape
+    if noise is None:
+        q = torch.empty(b * n, k, dtype=torch.float32, device=logits.device).exponential_(1, generator=generator).view(b, n, k)
+        u = torch.zeros(b, n, dtype=torch.float32, device=logits.device).uniform_(0, 1, generator=generator)
+    else:
+        q, u = noise
+        TF._need(q, "q"); TF._need(u, "u")
+    s_new = torch.empty_like(s)
+    sampled = torch.empty_like(s) if return_details else None
+    masking = torch.empty(b, n, dtype=torch.uint8, device=s.device) if return_details else None
+    rc = TF._lib.load().tvq_maskgit_step(logits.data_ptr(), s.data_ptr(), q.data_ptr(), u.data_ptr(), b, n, k, int(mask_token_id),
+                                         int(mask_len), float(temperature), s_new.data_ptr(),
+                                         sampled.data_ptr() if return_details else None,
+                                         masking.data_ptr() if return_details else None, TF._stream())
+    TF._lib.check(rc, "tvq_maskgit_step")
+    return (s_new, sampled, masking.bool()) if return_details else s_new
