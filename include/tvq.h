@@ -182,6 +182,10 @@ TVQ_API int tvq_maskgit_step(const float *logits, const int64_t *s, const float 
                      int k, int64_t mask_token_id, int mask_len, float temperature, int64_t *s_new,
                      int64_t *sampled, uint8_t *masking, void *stream);
 
+/* Batched 2-D transpose in [b, r, s] -> out [b, s, r]: the layout change around the VQ in quantize(),
+ * utils/train_utils.py:346-349 ('b c h w -> b (h w) c' and back), as a coalesced tiled copy.                  */
+TVQ_API int tvq_transpose(const float *in, int64_t b, int r, int s, float *out, void *stream);
+
 /* Dead-code re-seed (vq.py:181-195): embed[j] = x[rows[j]] where cluster_size[j] < threshold.
  * Only `embed` is touched, as in the reference.  rows [k] int64 (drawn by the host).          */
 TVQ_API int tvq_reseed(const float *x, const int64_t *rows, const float *cluster_size, float threshold,

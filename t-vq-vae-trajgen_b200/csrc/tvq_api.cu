@@ -652,6 +652,20 @@ int tvq_maskgit_step(const float* logits, const int64_t* s, const float* q, cons
     return launch_status();
 }
 
+int tvq_transpose(const float* in, int64_t b, int r, int s, float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (b < 0 || r < 1 || s < 1) return TVQ_ERR_UNSUPPORTED;
+    if (b == 0) return TVQ_OK;
+    if (!in || !out) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    int64_t tiles = b * ((r + 31) / 32) * ((s + 31) / 32);
+    if (tiles > 32LL * di->sm_count) tiles = 32LL * di->sm_count;
+    batched_transpose_kernel<<<(unsigned)tiles, 256, 0, stream>>>(in, out, b, r, s);
+    return launch_status();
+}
+
 int tvq_reseed(const float* x, const int64_t* rows, const float* cluster_size, float threshold, float* embed,
                int64_t n, int k, int d, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

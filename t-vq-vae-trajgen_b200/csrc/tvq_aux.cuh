@@ -309,6 +309,34 @@ __global__ void __launch_bounds__(256) gather_transposed_kernel(const int64_t* _
 }
 
 // ------------------------------------------------------------------------------------------
+// Batched 2-D transpose in[b][r][s] -> out[b][s][r]: the layout change of quantize() (utils/train_utils.py:346-349:
+// 'b c h w -> b (h w) c' before the VQ and back after it) as a shared-memory-tiled copy — both the reads (along s)
+// and the writes (along r) are coalesced 128-byte rows, where the generic strided copy torch runs for
+// rearrange(...).contiguous() reaches about a third of that.  8d bytes per latent per direction.
+__global__ void __launch_bounds__(256) batched_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t b,
+                                                                 int r, int s) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 8 warps
+    const int64_t rt = (r + 31) / 32, st = (s + 31) / 32;
+    const int64_t total = b * rt * st;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const int64_t bi = w / (rt * st);
+        const int64_t rem = w - bi * rt * st;
+        const int r0 = (int)(rem / st) * 32, s0 = (int)(rem % st) * 32;
+        const float* src = in + bi * (int64_t)r * s;
+        float* dst = out + bi * (int64_t)r * s;
+        __syncthreads();
+#pragma unroll
+        for (int i = ty; i < 32; i += 8)
+            if (r0 + i < r && s0 + tx < s) tile[i][tx] = ld_stream_v1(src + (int64_t)(r0 + i) * s + s0 + tx);
+        __syncthreads();
+#pragma unroll
+        for (int i = ty; i < 32; i += 8)
+            if (s0 + i < s && r0 + tx < r) dst[(int64_t)(s0 + i) * r + r0 + tx] = tile[tx][i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Dense -dist matrix for the stochastic branch (vq.py:210-214, fp32 three-term formula).
 // One warp per latent; k is small where this is used (stage 3 / sampler, k = 32).
 __global__ void __launch_bounds__(256) neg_dist_kernel(const float* __restrict__ x, const float* __restrict__ cb,

@@ -65,6 +65,11 @@ __device__ __forceinline__ float4 ld_stream_v4(const float* addr) {
     asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr));
     return v;
 }
+__device__ __forceinline__ float ld_stream_v1(const float* addr) {
+    float v;
+    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(addr));
+    return v;
+}
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

@@ -17,20 +17,45 @@ import torch
 from . import functional as TF
 
 
+class _Transpose(torch.autograd.Function):
+    """x (b, r, s) -> (b, s, r) contiguous, through the tiled transpose kernel; the backward is the same kernel."""
+
+    @staticmethod
+    def forward(ctx, x):
+        b, r, s = x.shape
+        out = torch.empty(b, s, r, dtype=torch.float32, device=x.device)
+        TF._lib.check(TF._lib.load().tvq_transpose(x.data_ptr(), b, r, s, out.data_ptr(), TF._stream()), "tvq_transpose")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Transpose.apply(g.contiguous())
+
+
+def _swap_last_two(x: torch.Tensor) -> torch.Tensor:
+    """(b, r, s) -> (b, s, r) contiguous.  fp32 contiguous CUDA input: the tiled kernel; anything else: torch."""
+    if x.is_cuda and x.dtype == torch.float32 and x.is_contiguous():
+        return _Transpose.apply(x)
+    return x.transpose(1, 2).contiguous()
+
+
 def quantize(z, vq_model, transpose_channel_length_axes: bool = False, svq_temp: Union[float, None] = None):
-    """z: (b c h w) or (b c l) encoder output -> (z_q, indices, vq_loss, perplexity)."""
+    """z: (b c h w) or (b c l) encoder output -> (z_q, indices, vq_loss, perplexity)  (utils/train_utils.py:338-358).
+
+    The two layout changes ('b c h w -> b (h w) c' and back) run as coalesced tiled transposes (tvq_transpose);
+    z_q comes back contiguous in the input's layout."""
     input_dim = z.dim() - 2
     if input_dim == 2:
         b, c, h, w = z.shape
-        z = z.permute(0, 2, 3, 1).reshape(b, h * w, c)
-        z_q, indices, vq_loss, perplexity = vq_model(z, svq_temp)
-        z_q = z_q.reshape(b, h, w, -1).permute(0, 3, 1, 2)
+        zz = _swap_last_two(z.reshape(b, c, h * w))                  # b (h w) c
+        z_q, indices, vq_loss, perplexity = vq_model(zz, svq_temp)
+        z_q = _swap_last_two(z_q).reshape(b, -1, h, w)               # b c h w
     elif input_dim == 1:
         if transpose_channel_length_axes:
-            z = z.transpose(1, 2)
+            z = _swap_last_two(z)
         z_q, indices, vq_loss, perplexity = vq_model(z, svq_temp)
         if transpose_channel_length_axes:
-            z_q = z_q.transpose(1, 2)
+            z_q = _swap_last_two(z_q)
     else:
         raise ValueError
     return z_q, indices, vq_loss, perplexity

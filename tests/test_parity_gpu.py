@@ -521,3 +521,16 @@ def test_non_finite_latents_do_not_derail(tvq, k, d):
     keep = torch.ones(n, dtype=torch.bool)
     keep[bad] = False
     assert torch.equal(idx.cpu()[keep], idx_ref.cpu()[keep])
+
+
+@pytest.mark.parametrize("b,r,s", [(1, 1, 1), (3, 128, 75), (2, 75, 128), (5, 33, 18), (1024, 128, 18), (2, 200, 7)])
+def test_tiled_transpose(tvq, b, r, s):
+    """quantize()'s layout change (utils/train_utils.py:346-349) as a tiled copy: exact, any shape; the backward is the
+    same kernel."""
+    x = torch.randn(b, r, s, device=DEV, requires_grad=True)
+    from tvq_b200.glue import _swap_last_two
+    y = _swap_last_two(x)
+    assert y.is_contiguous() and torch.equal(y, x.transpose(1, 2))
+    g = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, g)
+    assert torch.equal(gx, g.transpose(1, 2))
