@@ -131,6 +131,24 @@ TVQ_API int tvq_train_step_dp(const float *x, float *embed, float *cluster_size,
                       float *weighted_out, void *workspace, size_t workspace_bytes,
                       void *const *peer_bufs, int rank, int world, void *stream);
 
+/* tvq_forward / tvq_train_step(_dp) writing q CHANNELS-FIRST: q [n / q_hw, d, q_hw] — the 'b c (h w)' layout of the
+ * caller (utils/train_utils.py:349), so that quantize() needs no transpose after the VQ.  x stays [n, d]; idx stays
+ * [n].  Resident-codebook kernel only (k <= 32 train / 64 eval, d <= 128), n % q_hw == 0; TVQ_ERR_UNSUPPORTED
+ * otherwise (use the row-major call + tvq_transpose).  world = 1: local EMA update (peer_bufs may be NULL).       */
+TVQ_API int tvq_forward_qcf(const float *x, const float *codebook, int64_t n, int k, int d, unsigned flags,
+                    float commitment_weight, int64_t *idx, float *q, float *stats, float *scalars,
+                    void *workspace, size_t workspace_bytes, int q_hw, void *stream);
+TVQ_API int tvq_train_step_qcf(const float *x, float *embed, float *cluster_size, float *embed_avg,
+                       float *embed_prev, int64_t n, int k, int d, float commitment_weight, double decay,
+                       double eps, int64_t *idx, float *q, float *scalars, float *commit_out,
+                       float *weighted_out, void *workspace, size_t workspace_bytes,
+                       void *const *peer_bufs, int rank, int world, int q_hw, void *stream);
+/* Backward for the same caller: g_zq and g_z are channels-first [b, d, hw], x [b*hw, d] and idx [b*hw] row-major
+ * (as the forward saw them).  One kernel instead of transpose + tvq_backward + transpose.                        */
+TVQ_API int tvq_backward_cf(const float *g_zq, const float *g_commit, const float *g_weighted, const float *x,
+                    const int64_t *idx, const float *codebook, int64_t b, int hw, int k, int d,
+                    float commitment_weight, float *g_z, void *stream);
+
 /* Backward of the train forward (autograd through vq.py:357-366):
  *   g_x = g_q + (g_commit + commitment_weight * g_weighted) * 2/(n*d) * (x - q_st)
  *   with q_st recomputed from x, idx and the codebook the forward used.  g_commit / g_weighted

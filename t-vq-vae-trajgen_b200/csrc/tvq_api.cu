@@ -313,9 +313,12 @@ size_t tvq_workspace_bytes(int64_t n, int k, int d) {
     return ws_bf16_offset((int)kk, (int)dd) + kk * (size_t)stream_dp((int)dd) * 2 + 256;
 }
 
-int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, unsigned flags,
-                float commitment_weight, int64_t* idx, float* q, float* stats, float* scalars, void* workspace,
-                size_t workspace_bytes, void* stream_) {
+}  // extern "C"
+
+namespace {
+int forward_impl(const float* x, const float* codebook, int64_t n, int k, int d, unsigned flags,
+                 float commitment_weight, int64_t* idx, float* q, float* stats, float* scalars, void* workspace,
+                 size_t workspace_bytes, void* stream_, int q_hw) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 4 || d > 256 || (d & 3) || n < 0 || (int64_t)k * d >= (int64_t(1) << 31)) return TVQ_ERR_UNSUPPORTED;
     if (!x || !codebook || !idx || !stats || !scalars || !workspace) return TVQ_ERR_BAD_ARG;
@@ -334,6 +337,8 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
 
     // Streamed-codebook tcgen05 path: every shape the resident-codebook path does not take.
     const bool resident = k <= (train ? 32 : 64) && d <= 128;
+    if (q_hw > 0 && (!resident || (flags & (TVQ_F_EXACT | TVQ_F_GIVEN_IDX | TVQ_F_NO_UMMA)) || n % q_hw != 0 || n >= (int64_t(1) << 31) - 64))
+        return TVQ_ERR_UNSUPPORTED;      // the channels-first q store exists in the resident-codebook kernel only
     const bool use_stream = !(flags & (TVQ_F_EXACT | TVQ_F_GIVEN_IDX | TVQ_F_NO_UMMA)) && !resident && n > 0 &&
                             n < (int64_t(1) << 31) - 256;
     void* cbh = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_bf16_offset(k, d) : nullptr;
@@ -346,7 +351,7 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
     p.idx = idx; p.q = (flags & TVQ_F_WRITE_Q) ? q : nullptr; p.stats = stats; p.scalars = scalars;
     p.hdr = hdr; p.e2 = e2; p.commitment_weight = commitment_weight;
     p.commit_out = nullptr; p.weighted_out = nullptr; p.fuse_ema = 0;
-    p.peers = nullptr; p.dp_rank = 0; p.dp_world = 1;
+    p.peers = nullptr; p.dp_rank = 0; p.dp_world = 1; p.q_hw = q_hw;
     p.cluster_size = nullptr; p.embed_avg = nullptr; p.embed = nullptr; p.embed_prev = nullptr;
     p.decay = p.one_minus_decay = p.eps = p.k_eps = 0.f;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
@@ -376,13 +381,10 @@ int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, 
     return train ? dispatch_fwd_simt<true>(dp, p, pl, *di, stream) : dispatch_fwd_simt<false>(dp, p, pl, *di, stream);
 }
 
-}  // extern "C"
-
-namespace {
 int train_step_impl(const float* x, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t n, int k,
                     int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
                     float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* stream_,
-                    void* const* peers, int dp_rank, int dp_world) {
+                    void* const* peers, int dp_rank, int dp_world, int q_hw = 0) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 4 || d > 256 || (d & 3) || n < 0 || (int64_t)k * d >= (int64_t(1) << 31)) return TVQ_ERR_UNSUPPORTED;
     if (!embed || !cluster_size || !embed_avg || !scalars || !workspace || (n > 0 && (!x || !idx || !q))) return TVQ_ERR_BAD_ARG;
@@ -398,6 +400,7 @@ int train_step_impl(const float* x, float* embed, float* cluster_size, float* em
     float* scratch = e2 + e2_len(k);                          // private statistics: zero on entry, zero on exit
     const bool umma = n > 0 && k <= 32 && d <= 128 && n < (int64_t(1) << 31) - 64;
     if (dp_world > 1 && !umma) return TVQ_ERR_UNSUPPORTED;   // the fused data-parallel step exists for the resident-codebook kernel only
+    if (q_hw > 0 && (!umma || n % q_hw != 0)) return TVQ_ERR_UNSUPPORTED;   // so does the channels-first q store
     const bool use_stream = !umma && n > 0 && n < (int64_t(1) << 31) - 256;
     void* cbh = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_bf16_offset(k, d) : nullptr;
     if (!umma) {
@@ -411,7 +414,7 @@ int train_step_impl(const float* x, float* embed, float* cluster_size, float* em
     p.commit_out = commit_out; p.weighted_out = weighted_out;
     p.cluster_size = cluster_size; p.embed_avg = embed_avg; p.embed = embed; p.embed_prev = embed_prev;
     p.decay = (float)decay; p.one_minus_decay = (float)(1.0 - decay); p.eps = (float)eps; p.k_eps = (float)((double)k * eps);
-    p.peers = peers; p.dp_rank = dp_rank; p.dp_world = dp_world;
+    p.peers = peers; p.dp_rank = dp_rank; p.dp_world = dp_world; p.q_hw = q_hw;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
     p.exact = 0; p.given_idx = 0; p.use_hist = k <= 2048;
     if (umma) {
@@ -437,6 +440,47 @@ int train_step_impl(const float* x, float* embed, float* cluster_size, float* em
 }  // namespace
 
 extern "C" {
+
+int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, unsigned flags,
+                float commitment_weight, int64_t* idx, float* q, float* stats, float* scalars, void* workspace,
+                size_t workspace_bytes, void* stream_) {
+    return forward_impl(x, codebook, n, k, d, flags, commitment_weight, idx, q, stats, scalars, workspace, workspace_bytes, stream_, 0);
+}
+
+int tvq_forward_qcf(const float* x, const float* codebook, int64_t n, int k, int d, unsigned flags,
+                    float commitment_weight, int64_t* idx, float* q, float* stats, float* scalars, void* workspace,
+                    size_t workspace_bytes, int q_hw, void* stream_) {
+    if (q_hw < 1 || !q || !(flags & TVQ_F_WRITE_Q)) return TVQ_ERR_BAD_ARG;
+    return forward_impl(x, codebook, n, k, d, flags, commitment_weight, idx, q, stats, scalars, workspace, workspace_bytes, stream_, q_hw);
+}
+
+int tvq_train_step_qcf(const float* x, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t n, int k,
+                       int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
+                       float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* const* peer_bufs,
+                       int rank, int world, int q_hw, void* stream_) {
+    if (q_hw < 1 || n < 1 || world < 1 || world > 64 || rank < 0 || rank >= world || (world > 1 && !peer_bufs)) return TVQ_ERR_BAD_ARG;
+    return train_step_impl(x, embed, cluster_size, embed_avg, embed_prev, n, k, d, commitment_weight, decay, eps, idx, q, scalars,
+                           commit_out, weighted_out, workspace, workspace_bytes, stream_, world > 1 ? peer_bufs : nullptr, rank, world,
+                           q_hw);
+}
+
+int tvq_backward_cf(const float* g_zq, const float* g_commit, const float* g_weighted, const float* x, const int64_t* idx,
+                    const float* codebook, int64_t b, int hw, int k, int d, float commitment_weight, float* g_z, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    (void)k;
+    if (d < 1 || hw < 1 || b < 0) return TVQ_ERR_UNSUPPORTED;
+    if (b == 0) return TVQ_OK;
+    if (!x || !idx || !codebook || !g_z) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    const float scale = (float)(2.0 / ((double)b * (double)hw * (double)d));
+    int64_t tiles = b * ((hw + 31) / 32) * ((d + 31) / 32);
+    if (tiles > 32LL * di->sm_count) tiles = 32LL * di->sm_count;
+    backward_cf_kernel<<<(unsigned)tiles, 256, 0, stream>>>(g_zq, g_commit, g_weighted, x, idx, codebook, b, hw, d, commitment_weight,
+                                                             scale, g_z);
+    return launch_status();
+}
 
 int tvq_train_step(const float* x, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t n, int k,
                    int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,

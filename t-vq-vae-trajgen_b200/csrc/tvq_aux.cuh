@@ -309,6 +309,52 @@ __global__ void __launch_bounds__(256) gather_transposed_kernel(const int64_t* _
 }
 
 // ------------------------------------------------------------------------------------------
+// Backward of the train forward for a caller that works in 'b c (h w)' (utils/train_utils.py:346-349): the gradient
+// w.r.t. z_q arrives channels-first, the gradient w.r.t. z must leave channels-first, while x (the latents the forward
+// saw) and idx are row-major.  One kernel instead of [transpose g, backward_kernel, transpose g_x]: 32 x 32 tiles are
+// turned through shared memory, so every global access is a coalesced 128-byte row.
+//   g_z[b, c, t] = g_zq[b, c, t] + coef * (x[b t, c] - q_st[b t, c]),  q_st = x + (e[idx] - x)
+__global__ void __launch_bounds__(256) backward_cf_kernel(const float* __restrict__ g_zq, const float* __restrict__ g_commit,
+                                                           const float* __restrict__ g_weighted, const float* __restrict__ x,
+                                                           const int64_t* __restrict__ idx, const float* __restrict__ cb, int64_t b,
+                                                           int hw, int d, float weight, float scale, float* __restrict__ g_z) {
+    __shared__ float tg[32][33];
+    __shared__ float to[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float coef = fmaf(weight, g_weighted ? __ldg(g_weighted) : 0.f, g_commit ? __ldg(g_commit) : 0.f) * scale;
+    const int64_t tt = (hw + 31) / 32, ct = (d + 31) / 32;
+    const int64_t total = b * tt * ct;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const int64_t bi = w / (tt * ct);
+        const int64_t rem = w - bi * tt * ct;
+        const int t0 = (int)(rem / ct) * 32, c0 = (int)(rem % ct) * 32;
+        __syncthreads();
+        if (g_zq) {
+#pragma unroll
+            for (int i = ty; i < 32; i += 8)       // i: channel, tx: position — coalesced along (h w)
+                tg[i][tx] = (c0 + i < d && t0 + tx < hw) ? ld_stream_v1(g_zq + (bi * d + c0 + i) * hw + t0 + tx) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = ty; i < 32; i += 8) {         // i: position, tx: channel — coalesced along c
+            float r = 0.f;
+            if (t0 + i < hw && c0 + tx < d) {
+                const int64_t row = bi * hw + t0 + i;
+                const float xv = ld_stream_v1(x + row * d + c0 + tx);
+                const float ev = __ldg(cb + (size_t)__ldg(idx + row) * d + c0 + tx);
+                const float qst = __fadd_rn(xv, __fsub_rn(ev, xv));
+                r = fmaf(coef, __fsub_rn(xv, qst), g_zq ? tg[tx][i] : 0.f);
+            }
+            to[tx][i] = r;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = ty; i < 32; i += 8)           // i: channel, tx: position
+            if (c0 + i < d && t0 + tx < hw) g_z[(bi * d + c0 + i) * hw + t0 + tx] = to[i][tx];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Batched 2-D transpose in[b][r][s] -> out[b][s][r]: the layout change of quantize() (utils/train_utils.py:346-349:
 // 'b c h w -> b (h w) c' before the VQ and back after it) as a shared-memory-tiled copy — both the reads (along s)
 // and the writes (along r) are coalesced 128-byte rows, where the generic strided copy torch runs for

@@ -52,6 +52,9 @@ struct FwdParams {
     // data-parallel fused step: exchange buffers of every rank (tvq_aux.cuh::ema_dp_kernel layout); world <= 1: local
     void* const* peers;
     int dp_rank, dp_world;
+    // q layout: 0 = [n, d] row-major; hw > 0 = channels-first [n / hw, d, hw] (the 'b c (h w)' layout of the caller,
+    // utils/train_utils.py:349): resident-codebook tcgen05 kernel only
+    int q_hw;
 };
 
 // Shared-memory carve-up, computed identically on host and device.

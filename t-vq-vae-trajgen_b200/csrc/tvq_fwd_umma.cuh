@@ -170,7 +170,7 @@ template <int DP, int KP, bool TRAIN>
 __device__ __noinline__ RowResult row_generic(float* q, int64_t* idx, const int d, const int k, const float* xt,
                                               const float* cbs, const float* e2s, int* hist, const float4 key, const int trow,
                                               const int64_t grow, const bool has_chunk, const int lane, const float emax,
-                                              const float err_c, const uint32_t acc_base) {
+                                              const float err_c, const uint32_t acc_base, const int q_hw) {
     unsigned counters = 0;
     using namespace sm100;
     const float BIG = 1e30f;
@@ -205,7 +205,15 @@ __device__ __noinline__ RowResult row_generic(float* q, int64_t* idx, const int 
             const float dx = __fsub_rn(o.x, xv.x), dy = __fsub_rn(o.y, xv.y), dz = __fsub_rn(o.z, xv.z), dw = __fsub_rn(o.w, xv.w);
             loss = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
         }
-        if (q != nullptr && has_chunk) st_stream_v4(q + (size_t)grow * d + 4 * lane, o);
+        if (q != nullptr && has_chunk) {
+            if (q_hw > 0) {      // channels-first output [n / hw, d, hw]
+                const int64_t bi = grow / q_hw, hw = grow - bi * q_hw;
+                float* qc = q + (bi * d + 4 * lane) * q_hw + hw;
+                qc[0] = o.x; qc[q_hw] = o.y; qc[2 * (size_t)q_hw] = o.z; qc[3 * (size_t)q_hw] = o.w;
+            } else {
+                st_stream_v4(q + (size_t)grow * d + 4 * lane, o);
+            }
+        }
     }
     if (TRAIN) {
         __syncwarp();
@@ -480,7 +488,16 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                                 loss = fmaf(dz, dz, loss);
                                 loss = fmaf(dw, dw, loss);
                             }
-                            if (qp != nullptr && has_chunk) st_stream_v4(qp + u * qstep, o);
+                            if (qp != nullptr && has_chunk) {
+                                if (p.q_hw > 0) {
+                                    // channels-first output: park q in the x tile (this lane's own chunk, already in
+                                    // registers) and store the warp's 16 rows transposed once they are all done
+                                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xb + u * 128 + ((l7s ^ (u << 4)) ^ bsw)),
+                                                 "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                                } else {
+                                    st_stream_v4(qp + u * qstep, o);
+                                }
+                            }
                         }
                         if (qp != nullptr) qp += 4 * qstep;
                     }
@@ -526,10 +543,28 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                     atomicAdd(hist + mycode, 1);
                     p.idx[row0 + lane] = (int64_t)mycode;
                 }
+                if (p.q != nullptr && p.q_hw > 0) {
+                    // transposed store of the 16 rows x d channels parked in the tile: lane = (row, channel parity);
+                    // for one channel 16 lanes write 16 consecutive positions of 'b c (h w)' (64-byte runs)
+                    __syncwarp();
+                    const int r = lane & 15, par = lane >> 4;
+                    const int64_t grow = row0 + r;
+                    const int64_t bi = grow / p.q_hw, hw = grow - bi * p.q_hw;
+                    float* qc = p.q + bi * (int64_t)p.d * p.q_hw + hw;
+                    const float* trow = xt + (quad * 16 + r) * 32;             // row inside a 32-float slab
+                    const int rsw = (quad * 16 + r) & 7;
+#pragma unroll 4
+                    for (int cc = 0; cc < (p.d >> 1); ++cc) {
+                        const int c = 2 * cc + par;
+                        const float v = trow[(c >> 5) * (kUM * 32) + ((((c >> 2) & 7) ^ rsw) << 2) + (c & 3)];
+                        qc[(int64_t)c * p.q_hw] = v;
+                    }
+                    __syncwarp();
+                }
             } else {
                 for (int r = 0; r < nvalid; ++r) {        // last, partial tile: one fully checked row at a time
                     const RowResult rr = row_generic<DP, KP, TRAIN>(p.q, p.idx, p.d, p.k, xt, cbs, e2s, hist, keys[r], quad * 16 + r,
-                                                                    row0 + r, has_chunk, lane, emax, err_c, acc_base);
+                                                                    row0 + r, has_chunk, lane, emax, err_c, acc_base, p.q_hw);
                     loss += rr.loss;
                     counters += rr.counters;
                 }

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 
 __all__ = ["Workspace", "vq_forward_raw", "vq_train_step_raw", "vq_ema_update", "PeerExchange", "vq_ema_update_dp", "vq_backward", "vq_gather", "vq_neg_dist",
-           "vq_reseed", "stats_offset", "stats_len", "VQTrainStep"]
+           "vq_reseed", "stats_offset", "stats_len", "VQTrainStep", "VQTrainStepCF", "transpose12", "vq_forward_qcf"]
 
 
 def stats_offset(k: int) -> int:
@@ -272,3 +272,87 @@ class VQTrainStep(torch.autograd.Function):
         g_commit = g_commit.contiguous() if g_commit is not None else None
         g_weighted = g_weighted.contiguous() if g_weighted is not None else None
         return vq_backward(g_q, g_commit, g_weighted, x, idx, prev, ctx.commitment_weight), None, None, None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Channels-first call site: quantize() hands over z as 'b c (h w)' and wants z_q back the same way.
+
+def transpose12(x: torch.Tensor) -> torch.Tensor:
+    """(b, r, s) fp32 contiguous CUDA -> (b, s, r) contiguous through the tiled transpose kernel (no autograd)."""
+    _need(x, "x")
+    b, r, s = x.shape
+    out = torch.empty(b, s, r, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().tvq_transpose(x.data_ptr(), b, r, s, out.data_ptr(), _stream()), "tvq_transpose")
+    return out
+
+
+def vq_forward_qcf(x: torch.Tensor, codebook: torch.Tensor, ws: Workspace, hw: int, *, train: bool,
+                   commitment_weight: float = 1.0):
+    """tvq_forward_qcf: x [n, d] row-major -> (idx [n], q [n / hw, d, hw] channels-first, scalars[8])."""
+    _need(x, "x"); _need(codebook, "codebook")
+    n, d = x.shape
+    k = codebook.shape[0]
+    idx = torch.empty(n, dtype=torch.int64, device=x.device)
+    q = torch.empty(n // hw, d, hw, dtype=torch.float32, device=x.device)
+    scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32, device=x.device)
+    f = (_lib.F_TRAIN if train else 0) | _lib.F_WRITE_Q
+    rc = _lib.load().tvq_forward_qcf(x.data_ptr(), codebook.data_ptr(), n, k, d, f, float(commitment_weight), idx.data_ptr(),
+                                     q.data_ptr(), ws.stats.data_ptr(), scalars.data_ptr(), ws.buf.data_ptr(), ws.nbytes, int(hw),
+                                     _stream())
+    _lib.check(rc, "tvq_forward_qcf")
+    return idx, q, scalars
+
+
+class VQTrainStepCF(torch.autograd.Function):
+    """VQTrainStep for a channels-first caller: z [b, d, hw] in, q_st [b, d, hw] out, differentiable in z.
+
+    forward: one tiled transpose (z -> x [b hw, d], kept for the backward) + the fused train step writing q
+    channels-first (tvq_train_step_qcf; data-parallel: the same kernel exchanges the statistics over NVLink).
+    backward: ONE kernel (tvq_backward_cf) reads g channels-first and writes g_z channels-first."""
+
+    @staticmethod
+    def forward(ctx, z, cb, commitment_weight):
+        ctx.set_materialize_grads(False)
+        b, d, hw = z.shape
+        x = transpose12(z).view(b * hw, d)
+        ws = cb._workspace(z.device)
+        embed = cb._embed_data()
+        k = embed.shape[0]
+        prev = torch.empty_like(embed) if ctx.needs_input_grad[0] else None
+        n = b * hw
+        idx = torch.empty(n, dtype=torch.int64, device=z.device)
+        q = torch.empty(b, d, hw, dtype=torch.float32, device=z.device)
+        scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32, device=z.device)
+        commit = torch.empty((), dtype=torch.float32, device=z.device)
+        weighted = torch.empty(1, dtype=torch.float32, device=z.device)
+        px = cb._peer_exchange(z.device) if cb._ddp_active() else None
+        if cb._ddp_active() and px is None:
+            raise RuntimeError("internal: the channels-first step needs the peer exchange when data-parallel")
+        rc = _lib.load().tvq_train_step_qcf(x.data_ptr(), embed.data_ptr(), cb.cluster_size.data_ptr(), cb.embed_avg.data_ptr(),
+                                            prev.data_ptr() if prev is not None else None, n, k, d, float(commitment_weight),
+                                            float(cb.decay), float(cb.eps), idx.data_ptr(), q.data_ptr(), scalars.data_ptr(),
+                                            commit.data_ptr(), weighted.data_ptr(), ws.buf.data_ptr(), ws.nbytes,
+                                            px.peers.data_ptr() if px is not None else None, px.rank if px is not None else 0,
+                                            px.world if px is not None else 1, int(hw), _stream())
+        _lib.check(rc, "tvq_train_step_qcf")
+        ctx.save_for_backward(x, idx, prev)
+        ctx.meta = (b, hw, float(commitment_weight))
+        ctx.mark_non_differentiable(idx, scalars)
+        return q, idx, scalars, commit, weighted
+
+    @staticmethod
+    def backward(ctx, g_q, g_idx, g_scalars, g_commit, g_weighted):
+        x, idx, prev = ctx.saved_tensors
+        b, hw, w = ctx.meta
+        d = x.shape[1]
+        if g_commit is None and g_weighted is None:
+            return (g_q.contiguous() if g_q is not None else None), None, None
+        g_q = g_q.contiguous() if g_q is not None else None
+        g_commit = g_commit.contiguous() if g_commit is not None else None
+        g_weighted = g_weighted.contiguous() if g_weighted is not None else None
+        g_z = torch.empty(b, d, hw, dtype=torch.float32, device=x.device)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        rc = _lib.load().tvq_backward_cf(ptr(g_q), ptr(g_commit), ptr(g_weighted), x.data_ptr(), idx.data_ptr(), prev.data_ptr(),
+                                         b, hw, prev.shape[0], d, w, g_z.data_ptr(), _stream())
+        _lib.check(rc, "tvq_backward_cf")
+        return g_z, None, None

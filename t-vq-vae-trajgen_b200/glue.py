@@ -45,6 +45,10 @@ def quantize(z, vq_model, transpose_channel_length_axes: bool = False, svq_temp:
     The two layout changes ('b c h w -> b (h w) c' and back) run as coalesced tiled transposes (tvq_transpose);
     z_q comes back contiguous in the input's layout."""
     input_dim = z.dim() - 2
+    fused = getattr(vq_model, "_channels_first_ok", None)
+    if fused is not None and (input_dim == 2 or (input_dim == 1 and transpose_channel_length_axes)) and fused(z, svq_temp):
+        # the module takes 'b c (h w)' directly: one transpose in, z_q written channels-first, one-kernel backward
+        return vq_model.forward_channels_first(z)
     if input_dim == 2:
         b, c, h, w = z.shape
         zz = _swap_last_two(z.reshape(b, c, h * w))                  # b (h w) c

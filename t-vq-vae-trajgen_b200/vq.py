@@ -339,6 +339,44 @@ class VectorQuantize(nn.Module):
             embed_ind = embed_ind.reshape(b, height, width, *embed_ind.shape[2:])
         return quantize, embed_ind, vq_loss, self._codebook.perplexity
 
+    def _channels_first_ok(self, z: torch.Tensor, svq_temp) -> bool:
+        """Can forward_channels_first take this call?  (plain module, fp32 CUDA, codebook on the resident-codebook kernel)"""
+        cb = self._codebook
+        return (isinstance(z, torch.Tensor) and z.is_cuda and z.dtype == torch.float32 and z.dim() in (3, 4)
+                and not svq_temp and self.heads == 1 and self.channel_last and not self.accept_image_fmap
+                and isinstance(self.project_in, nn.Identity) and isinstance(self.project_out, nn.Identity)
+                and self.orthogonal_reg_weight == 0 and not cb.learnable_codebook and not cb.emb_dropout
+                and cb.threshold_ema_dead_code == 0 and cb._initted_host is True and cb.dim <= 128
+                and cb.codebook_size <= (32 if self.training else 64) and z.shape[1] == cb.dim
+                and z.numel() > 0 and z.shape[0] * z[0, 0].numel() < 2 ** 31 - 64
+                and (not (self.training and cb._ddp_active()) or cb._peer_exchange(z.device) is not None))
+
+    def forward_channels_first(self, z: torch.Tensor):
+        """z (b, c, h, w) or (b, c, l) -> (z_q in the same layout, embed_ind (b, h*w), vq_loss, perplexity): what
+        quantize() (utils/train_utils.py:338-358) computes with two rearranges around forward().  One tiled transpose on
+        the way in; the kernel writes z_q channels-first; the backward is one kernel."""
+        cb = self._codebook
+        shape = z.shape
+        b, c = shape[0], shape[1]
+        zz = z.contiguous().view(b, c, -1)
+        hw = zz.shape[2]
+        vq_loss = {"loss": None, "commit_loss": 0.0, "orthogonal_reg_loss": 0.0}
+        if self.training:
+            want_commit = self.commitment_weight > 0
+            q, idx, scalars, commit, weighted = TF.VQTrainStepCF.apply(zz, cb, self.commitment_weight if want_commit else 0.0)
+            if want_commit:
+                vq_loss["commit_loss"] = commit
+                vq_loss["loss"] = weighted
+        else:
+            with torch.no_grad():
+                x = TF.transpose12(zz.detach()).view(b * hw, c)
+                idx, q, scalars = TF.vq_forward_qcf(x, cb._embed_data(), cb._workspace(z.device), hw, train=False)
+        if vq_loss["loss"] is None:
+            vq_loss["loss"] = torch.zeros(1, device=z.device, requires_grad=self.training)
+        cb.perplexity = scalars[1].detach()
+        cb._last_ind = idx.view(b, hw)
+        return q.view(shape), idx.view(b, hw), vq_loss, cb.perplexity
+
     @torch.no_grad()
     def tokenize(self, x: torch.Tensor) -> torch.Tensor:
         """Indices only (what stage 2/3 keep of an eval call, models/maskgit.py:130-134): skips the q write."""

@@ -534,3 +534,39 @@ def test_tiled_transpose(tvq, b, r, s):
     g = torch.randn_like(y)
     (gx,) = torch.autograd.grad(y, x, g)
     assert torch.equal(gx, g.transpose(1, 2))
+
+
+# ------------------------------------------------ f-1: channels-first call site (quantize() without rearranges)
+
+@pytest.mark.parametrize("b,hw,k,d", [(32, 75, 32, 128), (32, 18, 32, 128), (7, 75, 20, 64), (1024, 75, 32, 128), (3, 5, 32, 128)])
+@pytest.mark.parametrize("train", [True, False])
+def test_channels_first_quantize_equals_row_major_path(tvq, b, hw, k, d, train):
+    """quantize(z 'b c h w') through forward_channels_first (transpose in, q written channels-first by the kernel,
+    one-kernel backward) must equal the plain path — the module on 'b (h w) c' between two rearranges, which is what the
+    reference's quantize() does (utils/train_utils.py:346-349): same indices, same z_q bits, same losses, EMA state and
+    gradient within 1e-5 (the statistics flush order differs between two launches)."""
+    torch.manual_seed(b + hw)
+    vq1 = tvq.VectorQuantize(d, k).to(DEV)
+    vq2 = tvq.VectorQuantize(d, k).to(DEV)
+    vq2.load_state_dict(vq1.state_dict())
+    vq1.train(train); vq2.train(train)
+    z = torch.randn(b, d, 1, hw, device=DEV)
+    z1 = z.clone().requires_grad_(train)
+    z2 = z.clone().requires_grad_(train)
+    assert vq1._channels_first_ok(z1, None)
+    zq1, i1, l1, p1 = tvq.quantize(z1, vq1)
+    x2 = z2.permute(0, 2, 3, 1).reshape(b, hw, d)
+    q2, i2, l2, p2 = vq2(x2)
+    zq2 = q2.reshape(b, 1, hw, d).permute(0, 3, 1, 2)
+    assert zq1.shape == z.shape and zq1.is_contiguous()
+    assert torch.equal(i1, i2)
+    assert torch.equal(zq1, zq2)
+    close(p1, p2, what="perplexity")
+    if train:
+        close(l1["loss"], l2["loss"], what="loss")
+        g = torch.randn_like(z)
+        (g1,) = torch.autograd.grad([zq1, l1["loss"]], [z1], [g, torch.ones(1, device=DEV)])
+        (g2,) = torch.autograd.grad([zq2, l2["loss"]], [z2], [g, torch.ones(1, device=DEV)])
+        close(g1, g2, what="grad z")
+        for name in ("cluster_size", "embed_avg", "embed"):
+            close(getattr(vq1._codebook, name), getattr(vq2._codebook, name), what=name)
