@@ -467,7 +467,6 @@ int tvq_train_step_qcf(const float* x, float* embed, float* cluster_size, float*
 int tvq_backward_cf(const float* g_zq, const float* g_commit, const float* g_weighted, const float* x, const int64_t* idx,
                     const float* codebook, int64_t b, int hw, int k, int d, float commitment_weight, float* g_z, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    (void)k;
     if (d < 1 || hw < 1 || b < 0) return TVQ_ERR_UNSUPPORTED;
     if (b == 0) return TVQ_OK;
     if (!x || !idx || !codebook || !g_z) return TVQ_ERR_BAD_ARG;
@@ -475,6 +474,19 @@ int tvq_backward_cf(const float* g_zq, const float* g_commit, const float* g_wei
     int rc = device_info(&di);
     if (rc != TVQ_OK) return rc;
     const float scale = (float)(2.0 / ((double)b * (double)hw * (double)d));
+    const size_t slab = ((size_t)hw * (d + 1) + (size_t)k * (d + 1) + (size_t)hw) * sizeof(float);
+    if (k >= 1 && (d & 3) == 0 && aligned16(x) && aligned16(codebook) && slab <= 100 * 1024) {
+        static size_t configured = 48 * 1024;
+        if (slab > configured) {
+            cudaError_t e = cudaFuncSetAttribute(backward_cf_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab);
+            if (e != cudaSuccess) return (int)e;
+            configured = slab;
+        }
+        int64_t grid = b < 8LL * di->sm_count ? b : 8LL * di->sm_count;
+        backward_cf_slab_kernel<<<(unsigned)grid, 256, slab, stream>>>(g_zq, g_commit, g_weighted, x, idx, codebook, b, hw, k, d,
+                                                                      commitment_weight, scale, g_z);
+        return launch_status();
+    }
     int64_t tiles = b * ((hw + 31) / 32) * ((d + 31) / 32);
     if (tiles > 32LL * di->sm_count) tiles = 32LL * di->sm_count;
     backward_cf_kernel<<<(unsigned)tiles, 256, 0, stream>>>(g_zq, g_commit, g_weighted, x, idx, codebook, b, hw, d, commitment_weight,

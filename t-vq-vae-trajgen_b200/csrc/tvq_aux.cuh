@@ -354,6 +354,77 @@ __global__ void __launch_bounds__(256) backward_cf_kernel(const float* __restric
     }
 }
 
+// The same, one CTA per batch element (used when its x slab and the codebook fit in shared memory: always at the
+// shipped shapes).  Per batch element g_zq[b], x[b] and g_z[b] are CONTIGUOUS blocks of hw*d floats: x[b] is read with
+// coalesced 16-byte loads into a padded shared-memory slab (row stride d + 1: a column read is conflict-free), the
+// codebook likewise, and the output is produced in g's own (c, t) order — two phases instead of three per 32 x 32 tile.
+__global__ void __launch_bounds__(256) backward_cf_slab_kernel(const float* __restrict__ g_zq, const float* __restrict__ g_commit,
+                                                                const float* __restrict__ g_weighted, const float* __restrict__ x,
+                                                                const int64_t* __restrict__ idx, const float* __restrict__ cb,
+                                                                int64_t b, int hw, int k, int d, float weight, float scale,
+                                                                float* __restrict__ g_z) {
+    extern __shared__ float bsm[];
+    const int ds = d + 1;
+    float* xs = bsm;                                     // [hw][d + 1]
+    float* es = xs + hw * ds;                            // [k][d + 1]
+    int* cs = reinterpret_cast<int*>(es + k * ds);       // [hw] codes
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const float coef = fmaf(weight, g_weighted ? __ldg(g_weighted) : 0.f, g_commit ? __ldg(g_commit) : 0.f) * scale;
+    const int dq = d >> 2;
+    for (int f = tid; f < k * dq; f += blockDim.x) {     // codebook -> padded shared memory (once per CTA)
+        const int row = f / dq, c4 = f - row * dq;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(cb + (size_t)row * d) + c4);
+        float* dst = es + row * ds + 4 * c4;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    for (int64_t bi = blockIdx.x; bi < b; bi += gridDim.x) {
+        __syncthreads();
+        const float4* xb = reinterpret_cast<const float4*>(x + bi * (int64_t)hw * d);
+#pragma unroll 4
+        for (int f = tid; f < hw * dq; f += blockDim.x) {
+            const int row = f / dq, c4 = f - row * dq;
+            const float4 v = ld_stream_v4(reinterpret_cast<const float*>(xb + f));
+            float* dst = xs + row * ds + 4 * c4;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        for (int t = tid; t < hw; t += blockDim.x) {
+            int64_t code = __ldg(idx + bi * hw + t);
+            cs[t] = (int)(code < 0 ? 0 : (code >= k ? k - 1 : code));
+        }
+        __syncthreads();
+        const float* gb = g_zq ? g_zq + bi * (int64_t)hw * d : nullptr;
+        float* ob = g_z + bi * (int64_t)hw * d;
+        // four channels per warp pass, positions across lanes: the (independent) g loads of a pass are all in flight
+        // before the first one is used
+        for (int c0 = 4 * warp; c0 < d; c0 += 4 * nwarps) {
+            for (int t0 = 0; t0 < hw; t0 += 64) {
+                float g[4][2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int t = t0 + lane + 32 * u;
+                        g[j][u] = (gb && t < hw && c0 + j < d) ? ld_stream_v1(gb + (c0 + j) * hw + t) : 0.f;
+                    }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int t = t0 + lane + 32 * u;
+                    if (t >= hw) continue;
+                    const int code = cs[t];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (c0 + j >= d) continue;
+                        const float xv = xs[t * ds + c0 + j];
+                        const float ev = es[code * ds + c0 + j];
+                        const float qst = __fadd_rn(xv, __fsub_rn(ev, xv));
+                        ob[(c0 + j) * hw + t] = fmaf(coef, __fsub_rn(xv, qst), g[j][u]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Batched 2-D transpose in[b][r][s] -> out[b][s][r]: the layout change of quantize() (utils/train_utils.py:346-349:
 // 'b c h w -> b (h w) c' before the VQ and back after it) as a shared-memory-tiled copy — both the reads (along s)

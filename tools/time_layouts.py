@@ -1,5 +1,6 @@
-"""Where the time of a quantize() call goes at BASELINE configs[1] sizes (experiment helper, not product)."""
-import os, sys, torch
+"""Where the time of a quantize() call goes at BASELINE configs[1] sizes (experiment helper, not product):
+the reference-shaped glue (torch permute / contiguous around the module) against tvq_b200.quantize()."""
+import os, sys, json, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import tvq_b200 as tvq
 dev = torch.device("cuda")
@@ -18,17 +19,27 @@ def graph_us(fn, reps=20):
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1000
 
+def reference_glue(z, vq):
+    b, c, h, w = z.shape
+    zz = z.permute(0, 2, 3, 1).reshape(b, h * w, c)               # rearrange 'b c h w -> b (h w) c'
+    q, i, l, p = vq(zz)
+    return q.reshape(b, h, w, -1).permute(0, 3, 1, 2), i, l, p    # rearrange back (a view, as einops gives)
+
+out = {}
 for (b, hw) in ((1024, 18), (1024, 75)):
     z = torch.randn(b, 128, 1, hw, device=dev)
-    vq = tvq.VectorQuantize(128, 32).to(dev).eval()
-    with torch.no_grad():
-        t_new = graph_us(lambda: tvq.quantize(z, vq))
-        def old():
-            zz = z.permute(0, 2, 3, 1).reshape(b, hw, 128)
-            q, i, l, p = vq(zz)
-            return q.reshape(b, 1, hw, -1).permute(0, 3, 1, 2).contiguous()
-        t_old = graph_us(old)
-        zz = z.permute(0, 2, 3, 1).reshape(b, hw, 128).contiguous()
-        t_vq = graph_us(lambda: vq(zz))
-        t_tr = graph_us(lambda: tvq.glue._swap_last_two(z.view(b, 128, hw)))
-    print(f"b={b} hw={hw}: quantize() eval {t_new:.1f} us (torch permute/contiguous around the module: {t_old:.1f} us; module alone {t_vq:.1f} us; one tiled transpose {t_tr:.1f} us)")
+    g = torch.randn(b, 128, 1, hw, device=dev)
+    ones = torch.ones(1, device=dev)
+    vq = tvq.VectorQuantize(128, 32).to(dev)
+    res = {}
+    for mode in ("eval", "train"):
+        vq.train(mode == "train")
+        def run(glue):
+            zz = z.detach().requires_grad_(mode == "train")
+            with torch.set_grad_enabled(mode == "train"):
+                zq, i, l, p = glue(zz, vq)
+                if mode == "train":
+                    torch.autograd.grad([zq, l["loss"]], [zz], [g, ones])
+        res[mode] = {"tvq_quantize_us": graph_us(lambda: run(tvq.quantize)), "reference_glue_us": graph_us(lambda: run(reference_glue))}
+    out[f"b{b}_hw{hw}"] = res
+    print(f"b={b} hw={hw}:", json.dumps(res))
