@@ -275,6 +275,9 @@ __attribute__((visibility("default"))) int tvq_debug_stream_prof(unsigned long l
 __attribute__((visibility("default"))) int tvq_debug_phases(unsigned long long* out32) {
     return (int)cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(unsigned long long) * 32);
 }
+__attribute__((visibility("default"))) int tvq_debug_tiles(unsigned long long* out32) {
+    return (int)cudaMemcpyFromSymbol(out32, g_tile_clk, sizeof(unsigned long long) * 32);
+}
 __attribute__((visibility("default"))) int tvq_debug_gt(unsigned long long* out4, int reset) {
     if (reset) {
         unsigned long long init[4] = {~0ull, 0ull, 0ull, 0ull};

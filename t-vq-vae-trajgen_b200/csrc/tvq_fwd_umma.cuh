@@ -38,6 +38,7 @@ namespace tvq {
 #ifdef TVQ_PROFILE_PHASES
 // Experiment build only (tools/profile_phases.py): per-phase clock64 totals of CTA 0's epilogue warps.
 __device__ unsigned long long g_phase_clk[2][16];
+__device__ unsigned long long g_tile_clk[8][4];   // CTA 0, warp 2: per tile (first 8): clocks at tile landed / scores ready / scan done / apply done
 __device__ unsigned long long g_gt[4];   // [0] min CTA start (globaltimer ns), [1] max CTA end, [2] max CTA clocks, [3] max main-loop-end clocks
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TVQ_PH(i) do { long long _t = clock64(); ph_acc[i] += _t - ph_t; ph_t = _t; } while (0)
@@ -229,6 +230,113 @@ __device__ __noinline__ RowResult row_generic(float* q, int64_t* idx, const int 
     return rr;
 }
 
+// Last-CTA epilogue of the resident-codebook kernel (k <= 64; EMA: k <= 32, single rank): the same arithmetic as
+// finish_ticket / ema_kernel, arranged for latency — at BASELINE configs[1] sizes the whole launch is ~30 us, so
+// the serial tail matters.  embed_avg and cluster_size (which no CTA of this launch writes before the last ticket)
+// are loaded BEFORE the ticket; after it there is ONE batch of L2 loads (counts, sums, loss), warp-level
+// reductions (one code per lane) instead of block-wide ones, and the stores.
+template <int KP, bool TRAIN>
+__device__ __forceinline__ void finish_resident(const FwdParams& p, const float* cbs, int* misc) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool ema = TRAIN && p.fuse_ema;
+    constexpr int J = (KP * 32 + kUThreads - 1) / kUThreads;       // float4 cells of the [k, d] buffers per thread
+    const int dq = p.d >> 2, cells = p.k * dq, kp = (p.k + 3) & ~3;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 avg[J];
+    float cs_old = 0.f;
+    if (ema) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int f = tid + j * kUThreads;
+            avg[j] = f < cells ? __ldcg(reinterpret_cast<const float4*>(p.embed_avg) + f) : z4;
+        }
+        if (lane < p.k) cs_old = __ldcg(p.cluster_size + lane);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(&p.hdr->ticket, 1u);
+        misc[1] = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!misc[1]) return;
+    __threadfence();
+    // ---- one batch of loads
+    const float cnt0 = lane < p.k ? __ldcg(p.stats + lane) : 0.f;
+    const float cnt1 = (KP > 32 && lane + 32 < p.k) ? __ldcg(p.stats + lane + 32) : 0.f;
+    float4* esum4 = reinterpret_cast<float4*>(p.stats + kp);
+    float4 sv[J];
+    if (ema) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int f = tid + j * kUThreads;
+            sv[j] = f < cells ? __ldcg(esum4 + f) : z4;
+        }
+    }
+    double ls = 0.0;
+    unsigned n_resc = 0, n_ex = 0;
+    if (tid == 0) {
+        ls = *reinterpret_cast<volatile double*>(&p.hdr->loss_sum);
+        n_resc = *reinterpret_cast<volatile unsigned*>(&p.hdr->n_rescored);
+        n_ex = *reinterpret_cast<volatile unsigned*>(&p.hdr->n_exact);
+    }
+    // ---- perplexity = exp(-sum p log(p + 1e-10)), p = counts / n  (vq.py:246-247); every warp computes it
+    const float fn = (float)p.n;
+    const float pr0 = __fdiv_rn(cnt0, fn), pr1 = __fdiv_rn(cnt1, fn);
+    double part = lane < p.k ? (double)(pr0 * logf(pr0 + 1e-10f)) : 0.0;
+    if (KP > 32 && lane + 32 < p.k) part += (double)(pr1 * logf(pr1 + 1e-10f));
+    const double tot = butterfly_sum(part);
+    if (tid == 0) {
+        p.scalars[1] = expf(-(float)tot);
+        const float commit = TRAIN ? (float)(ls / ((double)p.n * (double)p.d)) : 0.f;
+        p.scalars[0] = commit;
+        p.scalars[2] = __fmul_rn(commit, p.commitment_weight);
+        p.scalars[3] = 0.f;
+        reinterpret_cast<unsigned*>(p.scalars)[4] = n_resc;
+        reinterpret_cast<unsigned*>(p.scalars)[5] = n_ex;
+        p.scalars[6] = 0.f;
+        p.scalars[7] = 0.f;
+        if (p.commit_out) *p.commit_out = commit;
+        if (p.weighted_out) *p.weighted_out = __fmul_rn(commit, p.commitment_weight);
+        p.hdr->ticket = 0;
+        p.hdr->next_tile = 0u;
+        p.hdr->loss_sum = 0.0;                 // consumed: the header is clean for the next call
+        p.hdr->n_rescored = 0u;
+        p.hdr->n_exact = 0u;
+    }
+    if (!ema) return;
+    // ---- EMA update (vq.py:231,236-242): every other CTA has finished reading the codebook and flushing
+    const float cs_new = lane < p.k ? fmaf(cnt0, p.one_minus_decay, __fmul_rn(cs_old, p.decay)) : 0.f;
+    const float nsum = __double2float_rn(butterfly_sum((double)cs_new));
+    const float denom = __fadd_rn(nsum, p.k_eps);
+    float4* avg4 = reinterpret_cast<float4*>(p.embed_avg);
+    float4* emb4 = reinterpret_cast<float4*>(p.embed);
+    float4* prev4 = reinterpret_cast<float4*>(p.embed_prev);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int f = tid + j * kUThreads;
+        const int c = f < cells ? f / dq : 0;
+        const float cs = __shfl_sync(0xffffffffu, cs_new, c);
+        if (f < cells) {
+            const float sm = __fmul_rn(__fdiv_rn(__fadd_rn(cs, p.eps), denom), nsum);
+            float4 a = avg[j];
+            a.x = fmaf(sv[j].x, p.one_minus_decay, __fmul_rn(a.x, p.decay));
+            a.y = fmaf(sv[j].y, p.one_minus_decay, __fmul_rn(a.y, p.decay));
+            a.z = fmaf(sv[j].z, p.one_minus_decay, __fmul_rn(a.z, p.decay));
+            a.w = fmaf(sv[j].w, p.one_minus_decay, __fmul_rn(a.w, p.decay));
+            avg4[f] = a;
+            if (prev4) prev4[f] = *reinterpret_cast<const float4*>(cbs + tile_off<KP>(c, f - c * dq));   // pre-update code word
+            emb4[f] = make_float4(__fdiv_rn(a.x, sm), __fdiv_rn(a.y, sm), __fdiv_rn(a.z, sm), __fdiv_rn(a.w, sm));
+            esum4[f] = z4;                     // statistics consumed: the scratch is zero for the next call
+        }
+    }
+    __syncthreads();                           // every warp has read the counts
+    if (tid < kp) {
+        if (tid < p.k) p.cluster_size[tid] = cs_new;
+        p.stats[tid] = 0.f;
+    }
+}
+
 template <int DP, int KP, bool TRAIN, bool FULLD>
 __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const FwdParams p,
                                                                const int stages) {
@@ -273,18 +381,6 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
 
     // ------------------------------------------------------------------ CTA prologue
     if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need 1024-byte alignment
-    for (int f = tid; f < KP * DPC; f += kUThreads) {     // codebook -> UMMA B-operand layout (zero padded)
-        const int row = f / DPC, c4 = f % DPC;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < p.k && c4 < nchunk) v = __ldg(reinterpret_cast<const float4*>(p.cb + (size_t)row * p.d) + c4);
-        *reinterpret_cast<float4*>(cbs + tile_off<KP>(row, c4)) = v;
-    }
-    for (int c = warp; c < KP; c += kUThreads / 32) {     // canonical |e|^2 (one warp per code), BIG for padding
-        float v = BIG;
-        if (c < p.k) v = __double2float_rn(canon_dot_global(p.cb + (size_t)c * p.d, p.cb + (size_t)c * p.d, nchunk, lane));
-        if (lane == 0) { e2s[c] = v; hist[c] = 0; }
-    }
-    fence_proxy_async_smem();                             // generic-proxy writes -> visible to tcgen05.mma
     if (tid == 0) {
         for (int s = 0; s < kUMaxStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 4); }
         for (int s = 0; s < kUSlots; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
@@ -292,6 +388,51 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         tma_prefetch_desc(&tmap_x);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    // The first tiles of every CTA are fixed (tile = blockIdx.x * grab + j): their TMA loads are issued right here,
+    // so that HBM latency overlaps the codebook set-up below; the rest are handed out by the global counter.
+    const int num_tiles = p.num_tiles;                    // tiles of 64 rows
+    int grab = (num_tiles / (int)gridDim.x) >> 1;
+    grab = grab < 1 ? 1 : grab > stages ? stages : grab;  // gridDim.x <= num_tiles: every fixed tile exists
+    if (tid == 0) {
+        for (int j = 0; j < grab; ++j) {
+            const int tile = (int)blockIdx.x * grab + j;
+            stage_tile[j] = tile;
+            mbar_arrive_expect_tx(bar_full + 8 * j, (uint32_t)(kUM * DP * 4));
+#pragma unroll
+            for (int jj = 0; jj < NSLAB; ++jj)
+                tma_load_2d(x_base + j * pl.stage_bytes + jj * SLAB_X, &tmap_x, bar_full + 8 * j, jj * 32, tile * kUM);
+        }
+    }
+    {   // codebook -> UMMA B-operand layout (zero padded) and canonical |e|^2 (one warp per code, BIG for padding);
+        // all loads of a thread are issued before the first use (one L2 round trip, not one per iteration)
+        constexpr int NW = kUThreads / 32;
+        constexpr int CB_IT = (KP * DPC + kUThreads - 1) / kUThreads, E_IT = (KP + NW - 1) / NW;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* cb4 = reinterpret_cast<const float4*>(p.cb);
+        float4 cv[CB_IT], ev[E_IT];
+#pragma unroll
+        for (int j = 0; j < CB_IT; ++j) {
+            const int f = tid + j * kUThreads, row = f / DPC, c4 = f % DPC;
+            cv[j] = (f < KP * DPC && row < p.k && c4 < nchunk) ? __ldcg(cb4 + (size_t)row * nchunk + c4) : z4;
+        }
+#pragma unroll
+        for (int j = 0; j < E_IT; ++j) {
+            const int c = warp + j * NW;
+            ev[j] = (c < p.k && lane < nchunk) ? __ldcg(cb4 + (size_t)c * nchunk + lane) : z4;   // nchunk <= 32 here
+        }
+#pragma unroll
+        for (int j = 0; j < CB_IT; ++j) {
+            const int f = tid + j * kUThreads, row = f / DPC, c4 = f % DPC;
+            if (f < KP * DPC) *reinterpret_cast<float4*>(cbs + tile_off<KP>(row, c4)) = cv[j];
+        }
+#pragma unroll
+        for (int j = 0; j < E_IT; ++j) {
+            const int c = warp + j * NW;
+            const double v = butterfly_sum(dot4(0.0, ev[j], ev[j]));
+            if (c < KP && lane == 0) { e2s[c] = c < p.k ? __double2float_rn(v) : BIG; hist[c] = 0; }
+        }
+    }
+    fence_proxy_async_smem();                             // generic-proxy writes -> visible to tcgen05.mma
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -305,7 +446,6 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     // plus the fp32 roundings of both formulas and the 6 key bits that carry the code (64 ulps).
     const float err_c = 2.2e-3f + 3e-5f;
 
-    const int num_tiles = p.num_tiles;                    // tiles of 64 rows
     float loss = 0.f;
     unsigned counters = 0;                                // low 16 bits: re-scored rows, high: fp64 rows
 
@@ -315,14 +455,14 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         // last CTA — simply takes fewer); the tile id travels with the stage.  After the last tile the producer
         // posts kUGroups end markers so that every epilogue group sees one.
         if (lane == 0) {
-            int it = 0, ends = 0;
+            int it = grab, ends = 0;                      // stages 0 .. grab-1 were filled in the prologue
             while (ends < kUGroups) {
                 const int s = it % stages;
                 const uint32_t ph = (uint32_t)(it / stages) & 1u;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                 int tile = -1;
                 if (ends == 0) {
-                    tile = (int)atomicAdd(&p.hdr->next_tile, 1u);
+                    tile = (int)gridDim.x * grab + (int)atomicAdd(&p.hdr->next_tile, 1u);
                     if (tile >= num_tiles) tile = -1;
                 }
                 stage_tile[s] = tile;
@@ -390,9 +530,17 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
             if (tile < 0) break;
             const int64_t row0 = (int64_t)tile * kUM + quad * 16;     // first of this warp's 16 rows
             TVQ_PH(0);
+#ifdef TVQ_PROFILE_PHASES
+            const int tix = it / kUGroups;
+            const bool trec = blockIdx.x == 0 && warp == 2 && lane == 0 && tix < 8;
+            if (trec) g_tile_clk[tix][0] = (unsigned long long)(clock64() - kt[0]);
+#endif
             mbar_wait(bar_tfull + 8 * slot, sph);         // scores ready
             tc_fence_after();
             TVQ_PH(1);
+#ifdef TVQ_PROFILE_PHASES
+            if (trec) g_tile_clk[tix][1] = (unsigned long long)(clock64() - kt[0]);
+#endif
             // ---- 1. scan: lane l < 16 owns row l of the quadrant (M = 64 accumulator layout)
             {
                 float t0 = BIG, t1 = BIG, t2 = BIG, t3 = BIG;
@@ -413,6 +561,9 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                 __syncwarp();
             }
             TVQ_PH(2);
+#ifdef TVQ_PROFILE_PHASES
+            if (trec) g_tile_clk[tix][2] = (unsigned long long)(clock64() - kt[0]);
+#endif
             // ---- 2-4. apply: all lanes on one row, 4 rows in flight
             const int nvalid = (int)((p.n - row0) < 16 ? (p.n - row0) : 16);      // rows of this warp inside n
             if (nvalid == 16) {
@@ -570,6 +721,9 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                 }
             }
             TVQ_PH(3);
+#ifdef TVQ_PROFILE_PHASES
+            if (trec) g_tile_clk[tix][3] = (unsigned long long)(clock64() - kt[0]);
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // this warp is done with the stage
             TVQ_PH(4);
@@ -587,21 +741,29 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     __syncthreads();                                      // all tiles consumed: the stages are free
     tc_fence_after();
     TVQ_KT(3);
-    float4* dump = reinterpret_cast<float4*>(smem + pl.x);   // [4 quadrants][KP][32 lanes] float4
+    // Every epilogue warp adds its TMEM accumulators into the (now idle) tile ring: one [4 quadrants][KP][32 lanes]
+    // float4 area per group when the ring is large enough for all groups at once (d = 128: one pass), otherwise
+    // `par` groups per pass; then the CTA's total goes out with one red.global.add.v4 per 16 bytes.
+    constexpr int DUMP_CELLS = 4 * KP * 32;
+    float4* dump = reinterpret_cast<float4*>(smem + pl.x);
+    int par = (stages * pl.stage_bytes) / (DUMP_CELLS * 16);
+    par = par > kUGroups ? kUGroups : par;                // >= 1 (checked by the host)
     if (TRAIN) {
-        for (int round = 0; round < kUGroups; ++round) {  // one group at a time adds its TMEM accumulators
-            if (warp >= 2 && ((warp - 2) >> 2) == round) {
+        for (int g0 = 0; g0 < kUGroups; g0 += par) {
+            const int g = warp >= 2 ? (warp - 2) >> 2 : -1;
+            if (g >= g0 && g < g0 + par) {
                 const int quad = warp & 3;
-                const uint32_t acc_base = tmem_base + ((uint32_t)(quad * 32) << 16) + kUSlots * KP + round * (4 * KP);
-                for (int c0 = 0; c0 < KP; c0 += 4) {
-                    float4 v[4];
+                const uint32_t acc_base = tmem_base + ((uint32_t)(quad * 32) << 16) + kUSlots * KP + g * (4 * KP);
+                float4* area = dump + (g - g0) * DUMP_CELLS + quad * KP * 32 + lane;
+                for (int c0 = 0; c0 < KP; c0 += 8) {
+                    float4 v[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = tmem_ld_x4(acc_base + 4 * (c0 + j));
+                    for (int j = 0; j < 8; ++j) v[j] = tmem_ld_x4(acc_base + 4 * (c0 + j));
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float4* cell = dump + (quad * KP + c0 + j) * 32 + lane;
-                        if (round > 0) { const float4 o = *cell; v[j].x += o.x; v[j].y += o.y; v[j].z += o.z; v[j].w += o.w; }
+                    for (int j = 0; j < 8; ++j) {
+                        float4* cell = area + (c0 + j) * 32;
+                        if (g0 > 0) { const float4 o = *cell; v[j].x += o.x; v[j].y += o.y; v[j].z += o.z; v[j].w += o.w; }
                         *cell = v[j];
                     }
                 }
@@ -617,9 +779,8 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         for (int f = tid; f < KP * 32; f += kUThreads) {
             const int c = f >> 5, l = f & 31;
             if (c < p.k && l < nchunk && l < DPC) {
-                float4 a = dump[c * 32 + l];
-#pragma unroll
-                for (int w = 1; w < 4; ++w) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int w = 0; w < 4 * par; ++w) {       // (area, quadrant) pairs: area stride = 4 * KP * 32
                     const float4 b = dump[(w * KP + c) * 32 + l];
                     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
                 }
@@ -641,7 +802,8 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         if (tid == 0) atomicAdd(&p.hdr->loss_sum, t);
     }
     TVQ_KT(6);
-    finish_ticket<TRAIN>(p, red, misc);
+    if (p.dp_world > 1) finish_ticket<TRAIN>(p, red, misc);      // data-parallel: statistics exchange over peer memory
+    else finish_resident<KP, TRAIN>(p, cbs, misc);
     TVQ_KT(7);
 #ifdef TVQ_PROFILE_PHASES
     if (blockIdx.x == 0 && (tid == 0 || tid == 64))

@@ -59,7 +59,47 @@ def run(n=1 << 22, k=32, d=128, train=True, variant='base'):
         tot = sum(out[g * 16 + j] for j in range(8))
         print(f" group {g}: total {tot} clk;", ", ".join(f"{names[j]}={out[g*16+j]/max(1,per_cta/2):.0f}" for j in range(8)), "(clk per tile)")
 
+def run_step(n, k=32, d=128, variant='base'):
+    """Fused train step (forward + EMA, one launch): kernel timeline of CTA 0 and the global span."""
+    lib = ctypes.CDLL(so_path(variant))
+    dev = torch.device("cuda:0")
+    lib.tvq_workspace_bytes.restype = ctypes.c_size_t
+    lib.tvq_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+    vp, i64, i, f, dbl, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t
+    lib.tvq_train_step.argtypes = [vp, vp, vp, vp, vp, i64, i, i, f, dbl, dbl, vp, vp, vp, vp, vp, vp, sz, vp]
+    x = torch.randn(n, d, device=dev); e = torch.randn(k, d, device=dev); cs = torch.zeros(k, device=dev); avg = e.clone(); prev = e.clone()
+    idx = torch.empty(n, dtype=torch.int64, device=dev); q = torch.empty_like(x); sc = torch.empty(8, device=dev)
+    wsb = lib.tvq_workspace_bytes(n, k, d); ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+    call = lambda: lib.tvq_train_step(x.data_ptr(), e.data_ptr(), cs.data_ptr(), avg.data_ptr(), prev.data_ptr(), n, k, d, 1.0, 0.8, 1e-5,
+                                      idx.data_ptr(), q.data_ptr(), sc.data_ptr(), None, None, ws.data_ptr(), wsb, None)
+    for _ in range(3):
+        assert call() == 0
+    torch.cuda.synchronize()
+    gt = (ctypes.c_ulonglong * 4)()
+    lib.tvq_debug_gt(gt, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); call(); e1.record(); torch.cuda.synchronize()
+    out = (ctypes.c_ulonglong * 32)()
+    lib.tvq_debug_phases(out)
+    lib.tvq_debug_gt(gt, 0)
+    print(f"train_step n={n}: event {e0.elapsed_time(e1)*1000:.1f} us; first CTA start -> last CTA end {(gt[1]-gt[0])/1000:.2f} us; max CTA clocks {gt[2]}; max clocks to end of main loop {gt[3]}")
+    print("  timeline (clk from start: prologue, main loop, sync, dump, flush, loss, finish) thread0:", [int(out[8 + j]) for j in range(8)], " thread64:", [int(out[16 + 8 + j]) for j in range(8)])
+    names = ["wait_full", "wait_tmem", "scan", "apply_rest", "release", "ap_load+shfl", "ap_butterfly", "ap_decide+out"]
+    for g in range(2):
+        print(f"  CTA0 group {g} totals:", ", ".join(f"{names[j]}={int(out[g*16+j])}" for j in range(8)))
+    tl = (ctypes.c_ulonglong * 32)()
+    lib.tvq_debug_tiles(tl)
+    print("  CTA0 warp2 per tile [landed, scores, scan done, apply done]:", [[int(tl[4 * t + j]) for j in range(4)] for t in range(4)])
+    ts = []
+    for _ in range(8):
+        e0.record(); call(); e1.record(); torch.cuda.synchronize(); ts.append(round(e0.elapsed_time(e1) * 1000, 1))
+    print("  8 more eager launches, event us each:", ts)
+
 if __name__ == "__main__":
+    if "--step" in sys.argv:
+        for n in (18432, 76800, 1 << 20):
+            run_step(n)
+        sys.exit(0)
     if "--build" in sys.argv:
         build()
     else:
