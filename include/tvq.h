@@ -149,6 +149,23 @@ TVQ_API int tvq_backward_cf(const float *g_zq, const float *g_commit, const floa
                     const int64_t *idx, const float *codebook, int64_t b, int hw, int k, int d,
                     float commitment_weight, float *g_z, void *stream);
 
+/* The call site's own layout on BOTH sides: z and q are the encoder output / decoder input
+ * 'b c (h w)' tensors [b, d, hw] of utils/train_utils.py:338-358, read and written in place — neither of the two
+ * rearrange copies of :347,:349 exists.  idx is [b * hw] (latent b*hw + t).  Resident-codebook kernel only
+ * (k <= 32 train / 64 eval, d <= 128, b * hw < 2^31 - 64); TVQ_ERR_UNSUPPORTED otherwise.  tvq_forward_cf: q may be
+ * NULL iff TVQ_F_WRITE_Q is clear (tokenise).  tvq_backward_cfx is the matching backward (z, g_zq, g_z all [b, d, hw]). */
+TVQ_API int tvq_forward_cf(const float *z, const float *codebook, int64_t b, int hw, int k, int d, unsigned flags,
+                   float commitment_weight, int64_t *idx, float *q, float *stats, float *scalars,
+                   void *workspace, size_t workspace_bytes, void *stream);
+TVQ_API int tvq_train_step_cf(const float *z, float *embed, float *cluster_size, float *embed_avg,
+                      float *embed_prev, int64_t b, int hw, int k, int d, float commitment_weight, double decay,
+                      double eps, int64_t *idx, float *q, float *scalars, float *commit_out,
+                      float *weighted_out, void *workspace, size_t workspace_bytes,
+                      void *const *peer_bufs, int rank, int world, void *stream);
+TVQ_API int tvq_backward_cfx(const float *g_zq, const float *g_commit, const float *g_weighted, const float *z,
+                     const int64_t *idx, const float *codebook, int64_t b, int hw, int k, int d,
+                     float commitment_weight, float *g_z, void *stream);
+
 /* Backward of the train forward (autograd through vq.py:357-366):
  *   g_x = g_q + (g_commit + commitment_weight * g_weighted) * 2/(n*d) * (x - q_st)
  *   with q_st recomputed from x, idx and the codebook the forward used.  g_commit / g_weighted

@@ -16,7 +16,8 @@ F_TRAIN, F_WRITE_Q, F_EXACT, F_NO_UMMA, F_GIVEN_IDX = 1, 2, 4, 8, 16
 NUM_SCALARS = 8      # [0] commit, [1] perplexity, [2] weight*commit, [4:6] uint32 diagnostics
 
 EXPORTS = ("tvq_abi_version", "tvq_error_string", "tvq_device_check", "tvq_workspace_bytes", "tvq_forward",
-           "tvq_train_step", "tvq_train_step_dp", "tvq_ema_update", "tvq_exchange_bytes", "tvq_ema_update_dp", "tvq_backward", "tvq_gather", "tvq_neg_dist", "tvq_reseed", "tvq_frontend", "tvq_band_istft", "tvq_band_istft_backward", "tvq_maskgit_step", "tvq_transpose", "tvq_forward_qcf", "tvq_train_step_qcf", "tvq_backward_cf")
+           "tvq_train_step", "tvq_train_step_dp", "tvq_ema_update", "tvq_exchange_bytes", "tvq_ema_update_dp", "tvq_backward", "tvq_gather", "tvq_neg_dist", "tvq_reseed", "tvq_frontend", "tvq_band_istft", "tvq_band_istft_backward", "tvq_maskgit_step", "tvq_transpose", "tvq_forward_qcf", "tvq_train_step_qcf", "tvq_backward_cf",
+           "tvq_forward_cf", "tvq_train_step_cf", "tvq_backward_cfx")
 
 _c = ctypes
 _vp, _i, _i64, _u, _f, _d, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint, _c.c_float, _c.c_double, _c.c_size_t
@@ -44,6 +45,10 @@ _SIGNATURES = {
     "tvq_train_step_qcf": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _i,
                                _i, _vp]),
     "tvq_backward_cf": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _vp, _vp]),
+    "tvq_forward_cf": (_i, [_vp, _vp, _i64, _i, _i, _i, _u, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "tvq_train_step_cf": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _i,
+                              _vp]),
+    "tvq_backward_cfx": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _vp, _vp]),
     "tvq_reseed": (_i, [_vp, _vp, _vp, _f, _vp, _i64, _i, _i, _vp]),
 }
 

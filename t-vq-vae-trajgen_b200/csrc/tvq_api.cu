@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "tvq_aux.cuh"
 #include "tvq_common.cuh"
@@ -121,9 +122,9 @@ int make_x_tensor_map(CUtensorMap* tm, const float* x, int64_t n, int d, int row
     return r == CUDA_SUCCESS ? TVQ_OK : TVQ_ERR_BAD_ARG;
 }
 
-template <int DP, int KP, bool TRAIN, bool FULLD>
+template <int DP, int KP, bool TRAIN, bool FULLD, bool XCF = false>
 int launch_fwd_umma_impl(FwdParams p, const DeviceInfo& di, cudaStream_t stream) {
-    auto kern = fwd_umma_kernel<DP, KP, TRAIN, FULLD>;
+    auto kern = fwd_umma_kernel<DP, KP, TRAIN, FULLD, XCF>;
     const UmmaPlan fixed = make_umma_plan(DP, KP, 0);
     int stages = (di.max_smem_optin - fixed.total) / (kUM * DP * 4);
     if (stages > kUMaxStages) stages = kUMaxStages;
@@ -137,8 +138,11 @@ int launch_fwd_umma_impl(FwdParams p, const DeviceInfo& di, cudaStream_t stream)
         configured_smem = pl.total;
     }
     CUtensorMap tm;
-    int rc = make_x_tensor_map(&tm, p.x, p.n, p.d, kUM);
-    if (rc != TVQ_OK) return rc;
+    memset(&tm, 0, sizeof(tm));                       // channels-first x: loaded with cp.async, no tensor map
+    if (!XCF) {
+        int rc = make_x_tensor_map(&tm, p.x, p.n, p.d, kUM);
+        if (rc != TVQ_OK) return rc;
+    }
     p.num_tiles = (int)((p.n + kUM - 1) / kUM);
     int grid = p.num_tiles < di.sm_count ? p.num_tiles : di.sm_count;
     kern<<<grid, kUThreads, pl.total, stream>>>(tm, p, stages);
@@ -147,6 +151,7 @@ int launch_fwd_umma_impl(FwdParams p, const DeviceInfo& di, cudaStream_t stream)
 
 template <int DP, int KP, bool TRAIN>
 int launch_fwd_umma(const FwdParams& p, const DeviceInfo& di, cudaStream_t stream) {
+    if (p.x_hw > 0) return launch_fwd_umma_impl<DP, KP, TRAIN, false, true>(p, di, stream);
     if (DP == 128 && p.d == 128) return launch_fwd_umma_impl<DP, KP, TRAIN, (DP == 128)>(p, di, stream);
     return launch_fwd_umma_impl<DP, KP, TRAIN, false>(p, di, stream);
 }
@@ -321,7 +326,7 @@ size_t tvq_workspace_bytes(int64_t n, int k, int d) {
 namespace {
 int forward_impl(const float* x, const float* codebook, int64_t n, int k, int d, unsigned flags,
                  float commitment_weight, int64_t* idx, float* q, float* stats, float* scalars, void* workspace,
-                 size_t workspace_bytes, void* stream_, int q_hw) {
+                 size_t workspace_bytes, void* stream_, int q_hw, int x_hw = 0) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 4 || d > 256 || (d & 3) || n < 0 || (int64_t)k * d >= (int64_t(1) << 31)) return TVQ_ERR_UNSUPPORTED;
     if (!x || !codebook || !idx || !stats || !scalars || !workspace) return TVQ_ERR_BAD_ARG;
@@ -342,6 +347,9 @@ int forward_impl(const float* x, const float* codebook, int64_t n, int k, int d,
     const bool resident = k <= (train ? 32 : 64) && d <= 128;
     if (q_hw > 0 && (!resident || (flags & (TVQ_F_EXACT | TVQ_F_GIVEN_IDX | TVQ_F_NO_UMMA)) || n % q_hw != 0 || n >= (int64_t(1) << 31) - 64))
         return TVQ_ERR_UNSUPPORTED;      // the channels-first q store exists in the resident-codebook kernel only
+    if (x_hw > 0 && (!resident || (flags & (TVQ_F_EXACT | TVQ_F_GIVEN_IDX | TVQ_F_NO_UMMA)) || n % x_hw != 0 || n >= (int64_t(1) << 31) - 64 ||
+                     (q_hw > 0 && q_hw != x_hw) || (q_hw == 0 && (flags & TVQ_F_WRITE_Q))))
+        return TVQ_ERR_UNSUPPORTED;      // so does the channels-first x load (q, if written, in the same layout)
     const bool use_stream = !(flags & (TVQ_F_EXACT | TVQ_F_GIVEN_IDX | TVQ_F_NO_UMMA)) && !resident && n > 0 &&
                             n < (int64_t(1) << 31) - 256;
     void* cbh = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_bf16_offset(k, d) : nullptr;
@@ -354,7 +362,7 @@ int forward_impl(const float* x, const float* codebook, int64_t n, int k, int d,
     p.idx = idx; p.q = (flags & TVQ_F_WRITE_Q) ? q : nullptr; p.stats = stats; p.scalars = scalars;
     p.hdr = hdr; p.e2 = e2; p.commitment_weight = commitment_weight;
     p.commit_out = nullptr; p.weighted_out = nullptr; p.fuse_ema = 0;
-    p.peers = nullptr; p.dp_rank = 0; p.dp_world = 1; p.q_hw = q_hw;
+    p.peers = nullptr; p.dp_rank = 0; p.dp_world = 1; p.q_hw = q_hw; p.x_hw = x_hw;
     p.cluster_size = nullptr; p.embed_avg = nullptr; p.embed = nullptr; p.embed_prev = nullptr;
     p.decay = p.one_minus_decay = p.eps = p.k_eps = 0.f;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
@@ -387,7 +395,7 @@ int forward_impl(const float* x, const float* codebook, int64_t n, int k, int d,
 int train_step_impl(const float* x, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t n, int k,
                     int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
                     float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* stream_,
-                    void* const* peers, int dp_rank, int dp_world, int q_hw = 0) {
+                    void* const* peers, int dp_rank, int dp_world, int q_hw = 0, int x_hw = 0) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 4 || d > 256 || (d & 3) || n < 0 || (int64_t)k * d >= (int64_t(1) << 31)) return TVQ_ERR_UNSUPPORTED;
     if (!embed || !cluster_size || !embed_avg || !scalars || !workspace || (n > 0 && (!x || !idx || !q))) return TVQ_ERR_BAD_ARG;
@@ -404,6 +412,7 @@ int train_step_impl(const float* x, float* embed, float* cluster_size, float* em
     const bool umma = n > 0 && k <= 32 && d <= 128 && n < (int64_t(1) << 31) - 64;
     if (dp_world > 1 && !umma) return TVQ_ERR_UNSUPPORTED;   // the fused data-parallel step exists for the resident-codebook kernel only
     if (q_hw > 0 && (!umma || n % q_hw != 0)) return TVQ_ERR_UNSUPPORTED;   // so does the channels-first q store
+    if (x_hw > 0 && (!umma || x_hw != q_hw)) return TVQ_ERR_UNSUPPORTED;    // and the channels-first x load
     const bool use_stream = !umma && n > 0 && n < (int64_t(1) << 31) - 256;
     void* cbh = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_bf16_offset(k, d) : nullptr;
     if (!umma) {
@@ -417,7 +426,7 @@ int train_step_impl(const float* x, float* embed, float* cluster_size, float* em
     p.commit_out = commit_out; p.weighted_out = weighted_out;
     p.cluster_size = cluster_size; p.embed_avg = embed_avg; p.embed = embed; p.embed_prev = embed_prev;
     p.decay = (float)decay; p.one_minus_decay = (float)(1.0 - decay); p.eps = (float)eps; p.k_eps = (float)((double)k * eps);
-    p.peers = peers; p.dp_rank = dp_rank; p.dp_world = dp_world; p.q_hw = q_hw;
+    p.peers = peers; p.dp_rank = dp_rank; p.dp_world = dp_world; p.q_hw = q_hw; p.x_hw = x_hw;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
     p.exact = 0; p.given_idx = 0; p.use_hist = k <= 2048;
     if (umma) {
@@ -465,6 +474,54 @@ int tvq_train_step_qcf(const float* x, float* embed, float* cluster_size, float*
     return train_step_impl(x, embed, cluster_size, embed_avg, embed_prev, n, k, d, commitment_weight, decay, eps, idx, q, scalars,
                            commit_out, weighted_out, workspace, workspace_bytes, stream_, world > 1 ? peer_bufs : nullptr, rank, world,
                            q_hw);
+}
+
+int tvq_forward_cf(const float* z, const float* codebook, int64_t b, int hw, int k, int d, unsigned flags, float commitment_weight,
+                   int64_t* idx, float* q, float* stats, float* scalars, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (hw < 1 || b < 1 || b * (int64_t)hw >= (int64_t(1) << 31) - 64) return TVQ_ERR_BAD_ARG;
+    if (((flags & TVQ_F_WRITE_Q) != 0) != (q != nullptr)) return TVQ_ERR_BAD_ARG;
+    return forward_impl(z, codebook, b * hw, k, d, flags, commitment_weight, idx, q, stats, scalars, workspace, workspace_bytes, stream_,
+                        q ? hw : 0, hw);
+}
+
+int tvq_train_step_cf(const float* z, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t b, int hw, int k,
+                      int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
+                      float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* const* peer_bufs,
+                      int rank, int world, void* stream_) {
+    if (hw < 1 || b < 1 || b * (int64_t)hw >= (int64_t(1) << 31) - 64 || world < 1 || world > 64 || rank < 0 || rank >= world ||
+        (world > 1 && !peer_bufs))
+        return TVQ_ERR_BAD_ARG;
+    return train_step_impl(z, embed, cluster_size, embed_avg, embed_prev, b * hw, k, d, commitment_weight, decay, eps, idx, q, scalars,
+                           commit_out, weighted_out, workspace, workspace_bytes, stream_, world > 1 ? peer_bufs : nullptr, rank, world,
+                           hw, hw);
+}
+
+int tvq_backward_cfx(const float* g_zq, const float* g_commit, const float* g_weighted, const float* z, const int64_t* idx,
+                     const float* codebook, int64_t b, int hw, int k, int d, float commitment_weight, float* g_z, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (d < 1 || hw < 1 || b < 0 || k < 1) return TVQ_ERR_UNSUPPORTED;
+    if (b == 0) return TVQ_OK;
+    if (!z || !idx || !codebook || !g_z) return TVQ_ERR_BAD_ARG;
+    const size_t smem = ((size_t)k * (d + 1) + (size_t)hw) * sizeof(float);
+    const bool vec = ((int64_t)hw * d) % 4 == 0 && aligned16(z) && aligned16(g_z) && (!g_zq || aligned16(g_zq));
+    if (smem > 100 * 1024) return TVQ_ERR_UNSUPPORTED;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(backward_cfx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(backward_cfx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    const float scale = (float)(2.0 / ((double)b * (double)hw * (double)d));
+    int64_t grid = b < 8LL * di->sm_count ? b : 8LL * di->sm_count;
+    if (vec) backward_cfx_kernel<true><<<(unsigned)grid, 256, smem, stream>>>(g_zq, g_commit, g_weighted, z, idx, codebook, b, hw, k, d,
+                                                                          commitment_weight, scale, g_z);
+    else backward_cfx_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(g_zq, g_commit, g_weighted, z, idx, codebook, b, hw, k, d,
+                                                                        commitment_weight, scale, g_z);
+    return launch_status();
 }
 
 int tvq_backward_cf(const float* g_zq, const float* g_commit, const float* g_weighted, const float* x, const int64_t* idx,

@@ -426,6 +426,64 @@ __global__ void __launch_bounds__(256) backward_cf_slab_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------------------------------
+// Backward with EVERYTHING channels-first (the forward read z in place, tvq_forward_cf / tvq_train_step_cf):
+//   g_z[b, c, t] = g_zq[b, c, t] + coef * (z[b, c, t] - q_st[b, c, t]),  q_st = z + (e[idx[b, t]][c] - z)
+// Per batch element z[b], g_zq[b] and g_z[b] are contiguous blocks of d * hw floats, so the kernel is a flat 16-byte
+// streaming pass; the code words come from a padded shared-memory copy of the codebook (row stride d + 1: the lanes of
+// a warp hold consecutive positions t, i.e. different codes, of mostly one channel).  12 d bytes per latent.
+template <bool VEC>
+__global__ void __launch_bounds__(256) backward_cfx_kernel(const float* __restrict__ g_zq, const float* __restrict__ g_commit,
+                                                            const float* __restrict__ g_weighted, const float* __restrict__ z,
+                                                            const int64_t* __restrict__ idx, const float* __restrict__ cb, int64_t b,
+                                                            int hw, int k, int d, float weight, float scale,
+                                                            float* __restrict__ g_z) {
+    extern __shared__ float bsm[];
+    const int ds = d + 1;
+    float* es = bsm;                                     // [k][d + 1]
+    int* cs = reinterpret_cast<int*>(es + k * ds);       // [hw] codes of the current batch element
+    const int tid = threadIdx.x;
+    const float coef = fmaf(weight, g_weighted ? __ldg(g_weighted) : 0.f, g_commit ? __ldg(g_commit) : 0.f) * scale;
+    for (int f = tid; f < k * d; f += blockDim.x) es[(f / d) * ds + (f % d)] = __ldg(cb + f);
+    const int slab = hw * d;
+    for (int64_t bi = blockIdx.x; bi < b; bi += gridDim.x) {
+        __syncthreads();                                 // the previous element's codes are no longer read
+        for (int t = tid; t < hw; t += blockDim.x) {
+            const int64_t code = __ldg(idx + bi * hw + t);
+            cs[t] = (int)(code < 0 ? 0 : (code >= k ? k - 1 : code));
+        }
+        __syncthreads();
+        const float* zb = z + bi * (int64_t)slab;
+        const float* gb = g_zq ? g_zq + bi * (int64_t)slab : nullptr;
+        float* ob = g_z + bi * (int64_t)slab;
+        if (VEC) {
+            for (int f = tid; f < (slab >> 2); f += blockDim.x) {
+                const float4 xv = ld_stream_v4(zb + 4 * f);
+                const float4 gv = gb ? ld_stream_v4(gb + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                int c = (4 * f) / hw, t = 4 * f - c * hw;
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float ev = es[cs[t] * ds + c];
+                    const float qst = __fadd_rn(xs[j], __fsub_rn(ev, xs[j]));
+                    o[j] = fmaf(coef, __fsub_rn(xs[j], qst), gs[j]);
+                    if (++t == hw) { t = 0; ++c; }
+                }
+                st_stream_v4(ob + 4 * f, make_float4(o[0], o[1], o[2], o[3]));
+            }
+        } else {
+            for (int f = tid; f < slab; f += blockDim.x) {
+                const int c = f / hw, t = f - c * hw;
+                const float xv = ld_stream_v1(zb + f);
+                const float ev = es[cs[t] * ds + c];
+                const float qst = __fadd_rn(xv, __fsub_rn(ev, xv));
+                ob[f] = fmaf(coef, __fsub_rn(xv, qst), gb ? ld_stream_v1(gb + f) : 0.f);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Batched 2-D transpose in[b][r][s] -> out[b][s][r]: the layout change of quantize() (utils/train_utils.py:346-349:
 // 'b c h w -> b (h w) c' before the VQ and back after it) as a shared-memory-tiled copy — both the reads (along s)
 // and the writes (along r) are coalesced 128-byte rows, where the generic strided copy torch runs for

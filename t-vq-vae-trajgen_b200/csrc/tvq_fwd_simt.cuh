@@ -55,6 +55,9 @@ struct FwdParams {
     // q layout: 0 = [n, d] row-major; hw > 0 = channels-first [n / hw, d, hw] (the 'b c (h w)' layout of the caller,
     // utils/train_utils.py:349): resident-codebook tcgen05 kernel only
     int q_hw;
+    // x layout: 0 = [n, d] row-major; hw > 0 = channels-first [n / hw, d, hw] (== q_hw when q is written): the caller's
+    // 'b c (h w)' tensor read in place; resident-codebook tcgen05 kernel only
+    int x_hw;
 };
 
 // Shared-memory carve-up, computed identically on host and device.

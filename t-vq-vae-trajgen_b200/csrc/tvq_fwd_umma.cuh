@@ -51,7 +51,9 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #endif
 constexpr int kUM = 64;                 // latents per UMMA tile (M)
 constexpr int kUGroups = TVQ_UGROUPS;   // epilogue groups of 4 warps (one warp per TMEM lane quadrant)
-constexpr int kUThreads = 64 + 128 * kUGroups;   // producer warp + MMA warp + epilogue warps
+constexpr int kUThreads = 64 + 128 * kUGroups + 32;   // producer warp + MMA warp + epilogue warps + second loader warp (XCF)
+constexpr int kUWarpL2 = 2 + 4 * kUGroups;       // the second loader warp of the channels-first variant (idle otherwise)
+constexpr int kXcfDepth = 3;                     // channels-first loader: tiles in flight behind the one being issued
 constexpr int kUSlots = 4;              // TMEM score slots
 constexpr int kUMaxStages = 8;
 constexpr int kUBatch = 4;              // rows a warp keeps in flight in the apply phase
@@ -230,6 +232,42 @@ __device__ __noinline__ RowResult row_generic(float* q, int64_t* idx, const int 
     return rr;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Channels-first x: x is the caller's 'b c (h w)' tensor [n / hw, d, hw] (utils/train_utils.py:346-347
+// reads it through a rearrange copy; here the forward kernel reads it in place).  TMA cannot address that view (the
+// stride between channels, 4 * hw bytes, is not a multiple of 16), so two loader warps fill the SWIZZLE_128B tile with
+// 4-byte cp.async copies (consecutive latents of one channel are contiguous in global memory).  Completion:
+// cp.async.wait_group -> fence.proxy.async (the MMA reads the tile through the async proxy) -> mbarrier arrive.
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const float* src, unsigned src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One loader warp's half of a tile: lane = latent (rows 32*lw .. 32*lw+31), one channel per instruction — one or two
+// 128-byte lines of global memory per instruction, 4-way bank conflicts on the shared-memory side.  (Measured against
+// a lane = 8 latents x 4 channels mapping, which is conflict-free in shared memory but touches 4-8 lines: 71 vs 86 us
+// per 76 800-latent launch.)
+template <int DP>
+__device__ __forceinline__ void xcf_issue_tile(const FwdParams& p, const uint32_t stage_base, const int tile, const int lw,
+                                               const int lane) {
+    const unsigned hw = (unsigned)p.x_hw;
+    const int row = 32 * lw + lane;
+    const int64_t n = (int64_t)tile * kUM + row;
+    const bool rv = n < p.n;
+    const unsigned nn = rv ? (unsigned)n : 0u;
+    const unsigned bi = nn / hw, pos = nn - bi * hw;
+    const float* src = p.x + (size_t)bi * p.d * hw + pos;
+    const uint32_t dst_row = stage_base + (uint32_t)row * 128u;
+    const uint32_t x7 = (uint32_t)(row & 7) << 4;
+#pragma unroll 8
+    for (int c = 0; c < DP; ++c) {
+        const uint32_t dst = dst_row + (uint32_t)(c >> 5) * (kUM * 128) + ((((uint32_t)(c >> 2) & 7u) << 4) ^ x7) + ((uint32_t)(c & 3) << 2);
+        const bool ok = rv && c < p.d;
+        cp_async4_zfill(dst, ok ? src + (size_t)c * hw : p.x, ok ? 4u : 0u);
+    }
+}
+
 // Last-CTA epilogue of the resident-codebook kernel (k <= 64; EMA: k <= 32, single rank): the same arithmetic as
 // finish_ticket / ema_kernel, arranged for latency — at BASELINE configs[1] sizes the whole launch is ~30 us, so
 // the serial tail matters.  embed_avg and cluster_size (which no CTA of this launch writes before the last ticket)
@@ -337,7 +375,7 @@ __device__ __forceinline__ void finish_resident(const FwdParams& p, const float*
     }
 }
 
-template <int DP, int KP, bool TRAIN, bool FULLD>
+template <int DP, int KP, bool TRAIN, bool FULLD, bool XCF = false>
 __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const FwdParams p,
                                                                const int stages) {
     using namespace sm100;
@@ -382,10 +420,11 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     // ------------------------------------------------------------------ CTA prologue
     if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need 1024-byte alignment
     if (tid == 0) {
-        for (int s = 0; s < kUMaxStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 4); }
+        // "tile landed": one arrive.expect_tx by the TMA producer, or one arrive per loader warp (channels-first x)
+        for (int s = 0; s < kUMaxStages; ++s) { mbar_init(bar_full + 8 * s, XCF ? 2 : 1); mbar_init(bar_empty + 8 * s, 4); }
         for (int s = 0; s < kUSlots; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
         fence_mbar_init();
-        tma_prefetch_desc(&tmap_x);
+        if (!XCF) tma_prefetch_desc(&tmap_x);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     // The first tiles of every CTA are fixed (tile = blockIdx.x * grab + j): their TMA loads are issued right here,
@@ -393,7 +432,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     const int num_tiles = p.num_tiles;                    // tiles of 64 rows
     int grab = (num_tiles / (int)gridDim.x) >> 1;
     grab = grab < 1 ? 1 : grab > stages ? stages : grab;  // gridDim.x <= num_tiles: every fixed tile exists
-    if (tid == 0) {
+    if (!XCF && tid == 0) {
         for (int j = 0; j < grab; ++j) {
             const int tile = (int)blockIdx.x * grab + j;
             stage_tile[j] = tile;
@@ -449,7 +488,43 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     float loss = 0.f;
     unsigned counters = 0;                                // low 16 bits: re-scored rows, high: fp64 rows
 
-    if (warp == 0) {
+    if (XCF && (warp == 0 || warp == kUWarpL2)) {
+        // ============================================================ channels-first loaders (two warps, half a tile each)
+        // Trip t issues iteration t (a tile, or an end marker once the tiles are exhausted) as one cp.async group and
+        // completes iteration t - kXcfDepth.  Lane 0 of warp 0 is the only one that draws tiles; the id reaches the other
+        // loader warp through stage_tile[] and a 64-thread named barrier.
+        const int lw = warp == 0 ? 0 : 1;
+        int issued = 0, ends = 0;
+        for (int t = 0;; ++t) {
+            if (ends < kUGroups) {
+                const int s = t % stages;
+                const uint32_t ph = (uint32_t)(t / stages) & 1u;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                if (lw == 0 && lane == 0) {
+                    int tile = -1;
+                    if (ends == 0) {
+                        tile = t < grab ? (int)blockIdx.x * grab + t : (int)gridDim.x * grab + (int)atomicAdd(&p.hdr->next_tile, 1u);
+                        if (tile >= num_tiles) tile = -1;
+                    }
+                    stage_tile[s] = tile;
+                }
+                named_bar_sync(1, 64);
+                const int tile = stage_tile[s];
+                if (tile >= 0) xcf_issue_tile<DP>(p, x_base + s * pl.stage_bytes, tile, lw, lane);
+                else ++ends;
+                ++issued;
+            }
+            cp_async_commit();
+            cp_async_wait_n<kXcfDepth>();
+            const int a = t - kXcfDepth;
+            if (a >= 0 && a < issued) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + 8 * (a % stages));
+            }
+            if (ends >= kUGroups && a >= issued - 1) break;
+        }
+    } else if (!XCF && warp == 0) {
         // ============================================================ TMA producer + dynamic tile scheduler
         // Tiles are handed out by a global counter (a CTA that starts late — e.g. behind the previous launch's
         // last CTA — simply takes fewer); the tile id travels with the stage.  After the last tile the producer
@@ -499,7 +574,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                 umma_commit(bar_tfull + 8 * slot);
             }
         }
-    } else {
+    } else if (warp >= 2 && warp < kUWarpL2) {
         // ============================================================ epilogue warps
         const int g = (warp - 2) >> 2;                    // epilogue group: tiles g, g + kUGroups, ...
         const int quad = warp & 3;                        // TMEM lane quadrant this warp may access
@@ -750,7 +825,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     par = par > kUGroups ? kUGroups : par;                // >= 1 (checked by the host)
     if (TRAIN) {
         for (int g0 = 0; g0 < kUGroups; g0 += par) {
-            const int g = warp >= 2 ? (warp - 2) >> 2 : -1;
+            const int g = (warp >= 2 && warp < kUWarpL2) ? (warp - 2) >> 2 : -1;
             if (g >= g0 && g < g0 + par) {
                 const int quad = warp & 3;
                 const uint32_t acc_base = tmem_base + ((uint32_t)(quad * 32) << 16) + kUSlots * KP + g * (4 * KP);

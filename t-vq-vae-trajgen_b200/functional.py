@@ -13,7 +13,7 @@ import torch
 from . import _lib
 
 __all__ = ["Workspace", "vq_forward_raw", "vq_train_step_raw", "vq_ema_update", "PeerExchange", "vq_ema_update_dp", "vq_backward", "vq_gather", "vq_neg_dist",
-           "vq_reseed", "stats_offset", "stats_len", "VQTrainStep", "VQTrainStepCF", "transpose12", "vq_forward_qcf"]
+           "vq_reseed", "stats_offset", "stats_len", "VQTrainStep", "VQTrainStepCF", "transpose12", "vq_forward_qcf", "vq_forward_cf"]
 
 
 def stats_offset(k: int) -> int:
@@ -303,18 +303,39 @@ def vq_forward_qcf(x: torch.Tensor, codebook: torch.Tensor, ws: Workspace, hw: i
     return idx, q, scalars
 
 
+def vq_forward_cf(z: torch.Tensor, codebook: torch.Tensor, ws: Workspace, *, train: bool, write_q: bool = True,
+                  commitment_weight: float = 1.0):
+    """tvq_forward_cf: z [b, d, hw] channels-first, read in place -> (idx [b * hw], q [b, d, hw] or None, scalars[8])."""
+    _need(z, "z"); _need(codebook, "codebook")
+    b, d, hw = z.shape
+    k = codebook.shape[0]
+    idx = torch.empty(b * hw, dtype=torch.int64, device=z.device)
+    q = torch.empty(b, d, hw, dtype=torch.float32, device=z.device) if write_q else None
+    scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32, device=z.device)
+    f = (_lib.F_TRAIN if train else 0) | (_lib.F_WRITE_Q if write_q else 0)
+    rc = _lib.load().tvq_forward_cf(z.data_ptr(), codebook.data_ptr(), b, hw, k, d, f, float(commitment_weight), idx.data_ptr(),
+                                    q.data_ptr() if q is not None else None, ws.stats.data_ptr(), scalars.data_ptr(),
+                                    ws.buf.data_ptr(), ws.nbytes, _stream())
+    _lib.check(rc, "tvq_forward_cf")
+    return idx, q, scalars
+
+
 class VQTrainStepCF(torch.autograd.Function):
     """VQTrainStep for a channels-first caller: z [b, d, hw] in, q_st [b, d, hw] out, differentiable in z.
 
-    forward: one tiled transpose (z -> x [b hw, d], kept for the backward) + the fused train step writing q
-    channels-first (tvq_train_step_qcf; data-parallel: the same kernel exchanges the statistics over NVLink).
-    backward: ONE kernel (tvq_backward_cf) reads g channels-first and writes g_z channels-first."""
+    forward: one tiled transpose (z -> x [b hw, d], a temporary) + the fused train step writing q channels-first
+    (tvq_train_step_qcf; data-parallel: the same kernel exchanges the statistics over NVLink).  With IN_PLACE the
+    kernel reads z itself (tvq_train_step_cf: no copy on either side of the VQ) — parity-tested,
+    but its 4-byte cp.async tile fill is slower on B200 than transpose + TMA (86 vs 59 us at 1024 x 75 latents), so it
+    is not the default.  backward: ONE kernel (tvq_backward_cfx) on the caller's own z, everything channels-first."""
+
+    IN_PLACE = False
 
     @staticmethod
     def forward(ctx, z, cb, commitment_weight):
         ctx.set_materialize_grads(False)
         b, d, hw = z.shape
-        x = transpose12(z).view(b * hw, d)
+        x = z
         ws = cb._workspace(z.device)
         embed = cb._embed_data()
         k = embed.shape[0]
@@ -328,13 +349,16 @@ class VQTrainStepCF(torch.autograd.Function):
         px = cb._peer_exchange(z.device) if cb._ddp_active() else None
         if cb._ddp_active() and px is None:
             raise RuntimeError("internal: the channels-first step needs the peer exchange when data-parallel")
-        rc = _lib.load().tvq_train_step_qcf(x.data_ptr(), embed.data_ptr(), cb.cluster_size.data_ptr(), cb.embed_avg.data_ptr(),
-                                            prev.data_ptr() if prev is not None else None, n, k, d, float(commitment_weight),
-                                            float(cb.decay), float(cb.eps), idx.data_ptr(), q.data_ptr(), scalars.data_ptr(),
-                                            commit.data_ptr(), weighted.data_ptr(), ws.buf.data_ptr(), ws.nbytes,
-                                            px.peers.data_ptr() if px is not None else None, px.rank if px is not None else 0,
-                                            px.world if px is not None else 1, int(hw), _stream())
-        _lib.check(rc, "tvq_train_step_qcf")
+        tail = (px.peers.data_ptr() if px is not None else None, px.rank if px is not None else 0, px.world if px is not None else 1)
+        head = (embed.data_ptr(), cb.cluster_size.data_ptr(), cb.embed_avg.data_ptr(), prev.data_ptr() if prev is not None else None)
+        outs = (float(commitment_weight), float(cb.decay), float(cb.eps), idx.data_ptr(), q.data_ptr(), scalars.data_ptr(),
+                commit.data_ptr(), weighted.data_ptr(), ws.buf.data_ptr(), ws.nbytes)
+        if VQTrainStepCF.IN_PLACE:
+            rc = _lib.load().tvq_train_step_cf(z.data_ptr(), *head, b, int(hw), k, d, *outs, *tail, _stream())
+        else:
+            xr = transpose12(z)                           # [b, hw, d]: dropped right after the launch
+            rc = _lib.load().tvq_train_step_qcf(xr.data_ptr(), *head, n, k, d, *outs, *tail, int(hw), _stream())
+        _lib.check(rc, "tvq_train_step_cf")
         ctx.save_for_backward(x, idx, prev)
         ctx.meta = (b, hw, float(commitment_weight))
         ctx.mark_non_differentiable(idx, scalars)
@@ -342,7 +366,7 @@ class VQTrainStepCF(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_q, g_idx, g_scalars, g_commit, g_weighted):
-        x, idx, prev = ctx.saved_tensors
+        x, idx, prev = ctx.saved_tensors                  # x: the caller's z [b, d, hw]
         b, hw, w = ctx.meta
         d = x.shape[1]
         if g_commit is None and g_weighted is None:
@@ -352,7 +376,7 @@ class VQTrainStepCF(torch.autograd.Function):
         g_weighted = g_weighted.contiguous() if g_weighted is not None else None
         g_z = torch.empty(b, d, hw, dtype=torch.float32, device=x.device)
         ptr = lambda t: t.data_ptr() if t is not None else None
-        rc = _lib.load().tvq_backward_cf(ptr(g_q), ptr(g_commit), ptr(g_weighted), x.data_ptr(), idx.data_ptr(), prev.data_ptr(),
-                                         b, hw, prev.shape[0], d, w, g_z.data_ptr(), _stream())
-        _lib.check(rc, "tvq_backward_cf")
+        rc = _lib.load().tvq_backward_cfx(ptr(g_q), ptr(g_commit), ptr(g_weighted), x.data_ptr(), idx.data_ptr(), prev.data_ptr(),
+                                          b, hw, prev.shape[0], d, w, g_z.data_ptr(), _stream())
+        _lib.check(rc, "tvq_backward_cfx")
         return g_z, None, None

@@ -354,7 +354,8 @@ class VectorQuantize(nn.Module):
     def forward_channels_first(self, z: torch.Tensor):
         """z (b, c, h, w) or (b, c, l) -> (z_q in the same layout, embed_ind (b, h*w), vq_loss, perplexity): what
         quantize() (utils/train_utils.py:338-358) computes with two rearranges around forward().  One tiled transpose on
-        the way in; the kernel writes z_q channels-first; the backward is one kernel."""
+        the way in (or none: TF.VQTrainStepCF.IN_PLACE), the kernel writes z_q channels-first, and the backward is one
+        kernel on z itself."""
         cb = self._codebook
         shape = z.shape
         b, c = shape[0], shape[1]
@@ -369,8 +370,11 @@ class VectorQuantize(nn.Module):
                 vq_loss["loss"] = weighted
         else:
             with torch.no_grad():
-                x = TF.transpose12(zz.detach()).view(b * hw, c)
-                idx, q, scalars = TF.vq_forward_qcf(x, cb._embed_data(), cb._workspace(z.device), hw, train=False)
+                if TF.VQTrainStepCF.IN_PLACE:
+                    idx, q, scalars = TF.vq_forward_cf(zz.detach(), cb._embed_data(), cb._workspace(z.device), train=False)
+                else:
+                    x = TF.transpose12(zz.detach()).view(b * hw, c)
+                    idx, q, scalars = TF.vq_forward_qcf(x, cb._embed_data(), cb._workspace(z.device), hw, train=False)
         if vq_loss["loss"] is None:
             vq_loss["loss"] = torch.zeros(1, device=z.device, requires_grad=self.training)
         cb.perplexity = scalars[1].detach()

@@ -538,13 +538,17 @@ def test_tiled_transpose(tvq, b, r, s):
 
 # ------------------------------------------------ f-1: channels-first call site (quantize() without rearranges)
 
-@pytest.mark.parametrize("b,hw,k,d", [(32, 75, 32, 128), (32, 18, 32, 128), (7, 75, 20, 64), (1024, 75, 32, 128), (3, 5, 32, 128)])
+@pytest.mark.parametrize("b,hw,k,d", [(32, 75, 32, 128), (32, 18, 32, 128), (7, 75, 20, 64), (1024, 75, 32, 128), (3, 5, 32, 128),
+                                      (5, 130, 32, 128), (9, 1, 32, 128), (6, 33, 24, 100), (300, 7, 9, 36)])
 @pytest.mark.parametrize("train", [True, False])
-def test_channels_first_quantize_equals_row_major_path(tvq, b, hw, k, d, train):
-    """quantize(z 'b c h w') through forward_channels_first (transpose in, q written channels-first by the kernel,
-    one-kernel backward) must equal the plain path — the module on 'b (h w) c' between two rearranges, which is what the
+@pytest.mark.parametrize("in_place", [False, True])
+def test_channels_first_quantize_equals_row_major_path(tvq, b, hw, k, d, train, in_place, monkeypatch):
+    """quantize(z 'b c h w') through forward_channels_first (z read in place by the kernel's cp.async loaders, q written
+    channels-first, one-kernel channels-first backward) must equal the plain path — the module on 'b (h w) c' between two rearranges, which is what the
     reference's quantize() does (utils/train_utils.py:346-349): same indices, same z_q bits, same losses, EMA state and
     gradient within 1e-5 (the statistics flush order differs between two launches)."""
+    from tvq_b200 import functional as TF
+    monkeypatch.setattr(TF.VQTrainStepCF, "IN_PLACE", in_place)    # z read by the kernel itself vs one transpose in
     torch.manual_seed(b + hw)
     vq1 = tvq.VectorQuantize(d, k).to(DEV)
     vq2 = tvq.VectorQuantize(d, k).to(DEV)
@@ -570,3 +574,42 @@ def test_channels_first_quantize_equals_row_major_path(tvq, b, hw, k, d, train):
         close(g1, g2, what="grad z")
         for name in ("cluster_size", "embed_avg", "embed"):
             close(getattr(vq1._codebook, name), getattr(vq2._codebook, name), what=name)
+
+
+@pytest.mark.parametrize("b,hw,k,d", [(64, 75, 64, 128), (17, 18, 40, 64), (1024, 75, 32, 128)])
+def test_channels_first_raw_calls(tvq, b, hw, k, d):
+    """tvq_forward_cf (eval, k up to 64; with and without the q write) and the older row-major-x / channels-first-q
+    entry points (tvq_forward_qcf, tvq_backward_cf) against the row-major kernel on the transposed input."""
+    from tvq_b200 import functional as TF
+    torch.manual_seed(3 * b + hw)
+    dev = torch.device(DEV)
+    z = torch.randn(b, d, hw, device=dev)
+    e = torch.randn(k, d, device=dev)
+    ws = tvq.Workspace(k, d, dev)
+    x = z.transpose(1, 2).reshape(b * hw, d).contiguous()
+    idx_r, q_r, sc_r = tvq.vq_forward_raw(x, e, ws, train=False)
+    idx_c, q_c, sc_c = TF.vq_forward_cf(z, e, ws, train=False)
+    idx_t, q_t, _ = TF.vq_forward_cf(z, e, ws, train=False, write_q=False)
+    idx_q, q_q, _ = TF.vq_forward_qcf(x, e, ws, hw, train=False)
+    torch.cuda.synchronize()
+    assert q_t is None
+    assert torch.equal(idx_c, idx_r) and torch.equal(idx_t, idx_r) and torch.equal(idx_q, idx_r)
+    want = q_r.view(b, hw, d).transpose(1, 2)
+    assert torch.equal(q_c, want) and torch.equal(q_q, want)
+    close(sc_c[1], sc_r[1], what="perplexity")
+    # the two channels-first backward kernels agree with the row-major one
+    g = torch.randn(b, d, hw, device=dev)
+    one = torch.ones(1, device=dev)
+    lib = tvq._lib.load()
+    gz1 = torch.empty_like(z); gz2 = torch.empty_like(z); gx = torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.tvq_backward_cfx(g.data_ptr(), None, one.data_ptr(), z.data_ptr(), idx_r.data_ptr(), e.data_ptr(), b, hw, k, d, 0.25,
+                                gz1.data_ptr(), st) == 0
+    assert lib.tvq_backward_cf(g.data_ptr(), None, one.data_ptr(), x.data_ptr(), idx_r.data_ptr(), e.data_ptr(), b, hw, k, d, 0.25,
+                               gz2.data_ptr(), st) == 0
+    gr = g.transpose(1, 2).reshape(b * hw, d).contiguous()
+    assert lib.tvq_backward(gr.data_ptr(), None, one.data_ptr(), x.data_ptr(), idx_r.data_ptr(), e.data_ptr(), b * hw, k, d, 0.25,
+                            gx.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    want_g = gx.view(b, hw, d).transpose(1, 2)
+    assert torch.equal(gz1, want_g) and torch.equal(gz2, want_g)

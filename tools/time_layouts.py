@@ -15,9 +15,12 @@ def graph_us(fn, reps=20):
             for _ in range(reps): fn()
     torch.cuda.current_stream().wait_stream(s)
     g.replay(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps * 1000
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / reps * 1000)
+    return best
 
 def reference_glue(z, vq):
     b, c, h, w = z.shape
