@@ -508,19 +508,19 @@ int tvq_backward_cfx(const float* g_zq, const float* g_commit, const float* g_we
     DeviceInfo* di = nullptr;
     int rc = device_info(&di);
     if (rc != TVQ_OK) return rc;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(backward_cfx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(backward_cfx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
-    const float scale = (float)(2.0 / ((double)b * (double)hw * (double)d));
-    int64_t grid = b < 8LL * di->sm_count ? b : 8LL * di->sm_count;
-    if (vec) backward_cfx_kernel<true><<<(unsigned)grid, 256, smem, stream>>>(g_zq, g_commit, g_weighted, z, idx, codebook, b, hw, k, d,
-                                                                          commitment_weight, scale, g_z);
-    else backward_cfx_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(g_zq, g_commit, g_weighted, z, idx, codebook, b, hw, k, d,
-                                                                        commitment_weight, scale, g_z);
+    auto launch = [&](auto kern) -> int {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        const float scale = (float)(2.0 / ((double)b * (double)hw * (double)d));
+        int64_t grid = b < 8LL * di->sm_count ? b : 8LL * di->sm_count;
+        kern<<<(unsigned)grid, 256, smem, stream>>>(g_zq, g_commit, g_weighted, z, idx, codebook, b, hw, k, d, commitment_weight, scale, g_z);
+        return TVQ_OK;
+    };
+    if (k <= 256) rc = vec ? launch(backward_cfx_kernel<true, unsigned char>) : launch(backward_cfx_kernel<false, unsigned char>);
+    else rc = vec ? launch(backward_cfx_kernel<true, int>) : launch(backward_cfx_kernel<false, int>);
+    if (rc != TVQ_OK) return rc;
     return launch_status();
 }
 

@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(256) backward_cf_slab_kernel(const float* __re
 // Per batch element z[b], g_zq[b] and g_z[b] are contiguous blocks of d * hw floats, so the kernel is a flat 16-byte
 // streaming pass; the code words come from a padded shared-memory copy of the codebook (row stride d + 1: the lanes of
 // a warp hold consecutive positions t, i.e. different codes, of mostly one channel).  12 d bytes per latent.
-template <bool VEC>
+template <bool VEC, typename CodeT>
 __global__ void __launch_bounds__(256) backward_cfx_kernel(const float* __restrict__ g_zq, const float* __restrict__ g_commit,
                                                             const float* __restrict__ g_weighted, const float* __restrict__ z,
                                                             const int64_t* __restrict__ idx, const float* __restrict__ cb, int64_t b,
@@ -439,43 +439,49 @@ __global__ void __launch_bounds__(256) backward_cfx_kernel(const float* __restri
                                                             float* __restrict__ g_z) {
     extern __shared__ float bsm[];
     const int ds = d + 1;
-    float* es = bsm;                                     // [k][d + 1]
-    int* cs = reinterpret_cast<int*>(es + k * ds);       // [hw] codes of the current batch element
+    float* es = bsm;                                     // [k][d + 1]: distinct codes of one channel -> distinct banks (k <= 32)
+    CodeT* cs = reinterpret_cast<CodeT*>(es + k * ds);   // [hw] codes of the current batch element (bytes for k <= 256:
+                                                         //  the 4 consecutive positions of a lane share a word, lanes differ)
     const int tid = threadIdx.x;
     const float coef = fmaf(weight, g_weighted ? __ldg(g_weighted) : 0.f, g_commit ? __ldg(g_commit) : 0.f) * scale;
     for (int f = tid; f < k * d; f += blockDim.x) es[(f / d) * ds + (f % d)] = __ldg(cb + f);
     const int slab = hw * d;
+    // element 4 * (tid + i * blockDim) = channel c, position t; one step of the loop advances it by 4 * blockDim elements
+    const int step_c = (4 * (int)blockDim.x) / hw, step_t = 4 * (int)blockDim.x - step_c * hw;
     for (int64_t bi = blockIdx.x; bi < b; bi += gridDim.x) {
         __syncthreads();                                 // the previous element's codes are no longer read
         for (int t = tid; t < hw; t += blockDim.x) {
             const int64_t code = __ldg(idx + bi * hw + t);
-            cs[t] = (int)(code < 0 ? 0 : (code >= k ? k - 1 : code));
+            cs[t] = (CodeT)(code < 0 ? 0 : (code >= k ? k - 1 : code));
         }
         __syncthreads();
         const float* zb = z + bi * (int64_t)slab;
         const float* gb = g_zq ? g_zq + bi * (int64_t)slab : nullptr;
         float* ob = g_z + bi * (int64_t)slab;
         if (VEC) {
+            int c0 = (4 * tid) / hw, t0 = 4 * tid - c0 * hw;
             for (int f = tid; f < (slab >> 2); f += blockDim.x) {
                 const float4 xv = ld_stream_v4(zb + 4 * f);
                 const float4 gv = gb ? ld_stream_v4(gb + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-                int c = (4 * f) / hw, t = 4 * f - c * hw;
+                int c = c0, t = t0;
                 const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
                 float o[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float ev = es[cs[t] * ds + c];
+                    const float ev = es[(int)cs[t] * ds + c];
                     const float qst = __fadd_rn(xs[j], __fsub_rn(ev, xs[j]));
                     o[j] = fmaf(coef, __fsub_rn(xs[j], qst), gs[j]);
                     if (++t == hw) { t = 0; ++c; }
                 }
                 st_stream_v4(ob + 4 * f, make_float4(o[0], o[1], o[2], o[3]));
+                c0 += step_c; t0 += step_t;
+                if (t0 >= hw) { t0 -= hw; ++c0; }
             }
         } else {
             for (int f = tid; f < slab; f += blockDim.x) {
                 const int c = f / hw, t = f - c * hw;
                 const float xv = ld_stream_v1(zb + f);
-                const float ev = es[cs[t] * ds + c];
+                const float ev = es[(int)cs[t] * ds + c];
                 const float qst = __fadd_rn(xv, __fsub_rn(ev, xv));
                 ob[f] = fmaf(coef, __fsub_rn(xv, qst), gb ? ld_stream_v1(gb + f) : 0.f);
             }

@@ -173,7 +173,7 @@ template <int DP, int KP, bool TRAIN>
 __device__ __noinline__ RowResult row_generic(float* q, int64_t* idx, const int d, const int k, const float* xt,
                                               const float* cbs, const float* e2s, int* hist, const float4 key, const int trow,
                                               const int64_t grow, const bool has_chunk, const int lane, const float emax,
-                                              const float err_c, const uint32_t acc_base, const int q_hw) {
+                                              const float err_p, const float err_s, const uint32_t acc_base, const int q_hw) {
     unsigned counters = 0;
     using namespace sm100;
     const float BIG = 1e30f;
@@ -182,9 +182,10 @@ __device__ __noinline__ RowResult row_generic(float* q, int64_t* idx, const int 
     float ss = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, xv.w * xv.w)));
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    const float bnd = fmaf(sqrt_approx(ss), 1.0001f, emax);
+    const float xn = sqrt_approx(ss) * 1.0001f;
+    const float bnd = xn + emax;
     const float bnd2 = bnd * bnd;
-    const float lim = fmaf(err_c, bnd2, key.x);
+    const float lim = fmaf(err_p, xn, fmaf(err_s, bnd2, key.x));
     int code = (int)(__float_as_uint(key.x) & 63u);
     if (!(key.y > lim) || !(key.x < BIG)) {
         const int nc = 1 + (key.y <= lim) + (key.z <= lim) + (key.w <= lim);
@@ -480,10 +481,12 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     float emax2 = 0.f;
     for (int c = 0; c < KP; ++c) emax2 = fmaxf(emax2, (c < p.k) ? e2s[c] : 0.f);
     const float emax = sqrtf(emax2) * 1.0001f;
-    // |(s_a - s_b) - (d_a - d_b)| <= err_c * (|x| + max|e|)^2: tf32 operands (each within 2^-10
-    // relative, truncated or rounded) and fp32 accumulation give 2^-9 on the dot product; 10 % slack,
-    // plus the fp32 roundings of both formulas and the 6 key bits that carry the code (64 ulps).
-    const float err_c = 2.2e-3f + 3e-5f;
+    // |(s_a - s_b) - (d_a - d_b)| <= err_p * |x| * max|e| + err_s * (|x| + max|e|)^2: tf32 operands (each within 2^-10
+    // relative, truncated or rounded) and fp32 accumulation give 2^-9 * |x| |e| on a dot product, i.e. 2^-8 on a score
+    // and 2^-7 * |x| * max|e| on a score difference (10 % slack: 8.8e-3); err_s covers the fp32 roundings of both
+    // formulas and the 6 key bits that carry the code (64 ulps).  (The product form matters once training has pulled
+    // the code words towards the data mean: |x| >> |e| makes it half of the older (|x| + max|e|)^2 / 4 form.)
+    const float err_p = 8.8e-3f * emax, err_s = 3e-5f;
 
     float loss = 0.f;
     unsigned counters = 0;                                // low 16 bits: re-scored rows, high: fp64 rows
@@ -671,9 +674,10 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                     int cd[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {          // (a) decisions
-                        const float bnd = fmaf(sqrt_approx(ss[u]), 1.0001f, emax);
+                        const float xn = sqrt_approx(ss[u]) * 1.0001f;
+                        const float bnd = xn + emax;
                         const float bnd2 = bnd * bnd;
-                        const float lim = fmaf(err_c, bnd2, key[u].x);
+                        const float lim = fmaf(err_p, xn, fmaf(err_s, bnd2, key[u].x));
                         int code = (int)(__float_as_uint(key[u].x) & 63u);
                         if (!(key[u].y > lim)) {
                             // second best inside the bound (or non-finite scores: the comparison is
@@ -790,7 +794,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
             } else {
                 for (int r = 0; r < nvalid; ++r) {        // last, partial tile: one fully checked row at a time
                     const RowResult rr = row_generic<DP, KP, TRAIN>(p.q, p.idx, p.d, p.k, xt, cbs, e2s, hist, keys[r], quad * 16 + r,
-                                                                    row0 + r, has_chunk, lane, emax, err_c, acc_base, p.q_hw);
+                                                                    row0 + r, has_chunk, lane, emax, err_p, err_s, acc_base, p.q_hw);
                     loss += rr.loss;
                     counters += rr.counters;
                 }
