@@ -175,6 +175,10 @@ def our_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     hbm_gbs, bf16_tf, peak_src = load_peaks()
 
+    def note(msg):      # progress on stderr (stdout carries only the JSON line); a hung phase is then visible in the log
+        if rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
     torch.manual_seed(0)                                        # identical replicas
     vq_l = tvq.VectorQuantize(DIM, K_CODES, sync_codebook=world > 1).to(dev).train()
     vq_h = tvq.VectorQuantize(DIM, K_CODES, sync_codebook=world > 1).to(dev).train()
@@ -192,7 +196,16 @@ def our_arm(args):
         """One VQ train step (both codebooks), forward + backward, via the public module API.
         The LF and HF quantisers are independent, so each runs on its own stream (an explicit
         HF-forward-before-LF-forward dependency was tried and is slower: the tail of one forward kernel
-        overlaps the head of the other when the hardware is free to schedule them)."""
+        overlaps the head of the other when the hardware is free to schedule them).
+        Data-parallel runs use ONE stream: each fused kernel's last CTA waits for the same codebook's statistics from
+        every peer, and two such kernels that the ranks happen to start in opposite orders would wait for each other
+        (neither can finish before its last CTA gets an SM) — a fixed order on every rank rules that out."""
+        if world > 1:
+            qh, ih, lh, ph = vq_h(xh)
+            torch.autograd.grad([qh, lh["loss"]], [xh], [gh, ones])
+            ql, il, ll, pl = vq_l(xl)
+            torch.autograd.grad([ql, ll["loss"]], [xl], [gl, ones])
+            return ll["loss"], lh["loss"], il, ih
         cur = torch.cuda.current_stream()
         side_h.wait_stream(cur)
         with torch.cuda.stream(side_h):
@@ -208,20 +221,23 @@ def our_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
+    def timed(fn, steps, local=False):
+        """ms for `steps` calls of fn(i): barrier + synchronize on both sides, max over ranks.  local=True: this rank only
+        (sections that rank 0 runs alone must not enter a collective)."""
+        sync = torch.cuda.synchronize if local else barrier
+        sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
         e1.record()
-        barrier()
+        sync()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
+        if world > 1 and not local:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    def graph_timed(fn, reps):
+    def graph_timed(fn, reps, local=False):
         """ms per call of fn(i), i = 0..reps-1, replayed from ONE CUDA graph (no host launch gaps); None if capture fails."""
         try:
             side = torch.cuda.Stream()
@@ -233,7 +249,7 @@ def our_arm(args):
                         fn(i)
             torch.cuda.current_stream().wait_stream(side)
             kg.replay()
-            return timed(lambda i: kg.replay(), 3) / (3 * reps)
+            return timed(lambda i: kg.replay(), 3, local) / (3 * reps)
         except Exception as exc:
             print(f"[bench] rank {rank}: graph capture failed: {exc}", file=sys.stderr)
             return None
@@ -249,6 +265,7 @@ def our_arm(args):
     clear_grads()
     eager_ms = timed(eager, args.steps)
     clear_grads()
+    note(f"eager: {eager_ms / args.steps * 1e3:.1f} us per step")
 
     # ---- CUDA-graph replay of the same step (launch-bound regime: 4 small kernels per step).  ONE graph holds
     #      several consecutive training steps (rotating over the resident input batches, EMA state carried from
@@ -300,6 +317,7 @@ def our_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     clear_grads()
     value = world * LATENTS_PER_STEP * timed_steps / (main_ms * 1e-3)
+    note(f"timed region ({mode}): {main_ms / timed_steps * 1e3:.1f} us per step")
 
     # ---- e2e: pinned host inputs -> H2D -> step -> D2H of the step's result -------------------------
     #      Double-buffered: the H2D copy of step i+1 runs on a copy stream while step i computes (every step's input is
@@ -344,6 +362,7 @@ def our_arm(args):
     e2e_ms = timed(lambda i: e2e_step(i0 + i), args.steps)
     torch.cuda.synchronize()
     e2e_value = world * LATENTS_PER_STEP * args.steps / (e2e_ms * 1e-3)
+    note(f"e2e: {e2e_ms / args.steps * 1e3:.1f} us per step")
 
     # ---- roofline of the dominant kernel: the HF fused train step (forward + EMA, ONE launch — the kernel the
     #      timed region runs for the HF codebook), timed alone with CUDA events on the launching stream --------
@@ -415,7 +434,7 @@ def our_arm(args):
                 x, o = xt[i % 8], outs[i % 8]
                 assert lib_f.tvq_frontend(x.data_ptr(), B_TRAJ, 4, 200, 4, None, o["enc_in_l"].data_ptr(), o["enc_in_h"].data_ptr(),
                                           o["x_l"].data_ptr(), o["x_h"].data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
-            fe_ms = graph_timed(fe, 40) or timed(fe, 40) / 40
+            fe_ms = graph_timed(fe, 40, local=True) or timed(fe, 40, local=True) / 40
             fe_bytes = B_TRAJ * 4 * (200 * 4 + 2 * (2 * 3 * 201 * 4) + 2 * 200 * 4)
             frontend = {"what": "tvq_frontend: x (1024,4,200) -> enc_in_l, enc_in_h (1024,8,3,201), x_l, x_h (1024,4,200); "
                                 "n_fft=4 (stage1.py:101-113, vq_vae.py:179-180)", "us_per_launch": fe_ms * 1e3,
@@ -489,6 +508,8 @@ def sweep_point(tvq, dev, n, k, d, hbm_gbs, bf16_tf):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=False, file=sys.stderr)     # a hang leaves a Python stack in the log
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -280,6 +280,9 @@ __attribute__((visibility("default"))) int tvq_debug_stream_prof(unsigned long l
 __attribute__((visibility("default"))) int tvq_debug_phases(unsigned long long* out32) {
     return (int)cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(unsigned long long) * 32);
 }
+__attribute__((visibility("default"))) int tvq_debug_phases_all(unsigned long long* out24) {
+    return (int)cudaMemcpyFromSymbol(out24, g_phase_all, sizeof(unsigned long long) * 24);
+}
 __attribute__((visibility("default"))) int tvq_debug_tiles(unsigned long long* out32) {
     return (int)cudaMemcpyFromSymbol(out32, g_tile_clk, sizeof(unsigned long long) * 32);
 }

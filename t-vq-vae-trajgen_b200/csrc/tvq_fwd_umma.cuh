@@ -38,6 +38,7 @@ namespace tvq {
 #ifdef TVQ_PROFILE_PHASES
 // Experiment build only (tools/profile_phases.py): per-phase clock64 totals of CTA 0's epilogue warps.
 __device__ unsigned long long g_phase_clk[2][16];
+__device__ unsigned long long g_phase_all[2][12];  // CTA 0, epilogue groups 0/1, quadrant 0: clock totals of phases 0..9
 __device__ unsigned long long g_tile_clk[8][4];   // CTA 0, warp 2: per tile (first 8): clocks at tile landed / scores ready / scan done / apply done
 __device__ unsigned long long g_gt[4];   // [0] min CTA start (globaltimer ns), [1] max CTA end, [2] max CTA clocks, [3] max main-loop-end clocks
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -666,10 +667,24 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                         ss[u] = fmaf(xv[u].x, xv[u].x, fmaf(xv[u].y, xv[u].y, fmaf(xv[u].z, xv[u].z, xv[u].w * xv[u].w)));
                     }
                     TVQ_PH(5);
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], off);
+                    {   // four warp-wide sums with 10 shuffles instead of 20: the first two butterfly steps also halve the
+                        // number of values a lane carries (lanes with bit 4 set keep rows 2-3, bit 3 picks the row of
+                        // the pair), three plain steps finish, four broadcasts hand every lane all four |x|^2 (the sums
+                        // only feed the error bound, so their order is free)
+                        const bool h4 = lane & 16, h3 = lane & 8;
+                        const float k0 = h4 ? ss[2] : ss[0], k1 = h4 ? ss[3] : ss[1];
+                        const float g0 = h4 ? ss[0] : ss[2], g1 = h4 ? ss[1] : ss[3];
+                        const float r0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 16);
+                        const float r1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 16);
+                        float t = (h3 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, h3 ? r0 : r1, 8);
+                        t += __shfl_xor_sync(0xffffffffu, t, 4);
+                        t += __shfl_xor_sync(0xffffffffu, t, 2);
+                        t += __shfl_xor_sync(0xffffffffu, t, 1);
+                        ss[0] = __shfl_sync(0xffffffffu, t, 0);     // lane (bit4, bit3) = (0,0) -> row 0, (0,1) -> 1, (1,0) -> 2, (1,1) -> 3
+                        ss[1] = __shfl_sync(0xffffffffu, t, 8);
+                        ss[2] = __shfl_sync(0xffffffffu, t, 16);
+                        ss[3] = __shfl_sync(0xffffffffu, t, 24);
+                    }
                     TVQ_PH(6);
                     int cd[4];
 #pragma unroll
@@ -693,6 +708,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                         }
                         cd[u] = code;
                     }
+                    TVQ_PH(9);
                     if (p.q != nullptr || TRAIN) {
                         float4 ev[4];
 #pragma unroll
@@ -739,7 +755,9 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                     TVQ_PH(7);
                     if (TRAIN) {
                         // ONE tensor-memory read-modify-write per row; rows of the batch that share a
-                        // code (a warp-uniform condition) take the sequential form
+                        // code (a warp-uniform condition) take the sequential form.  (Folding such rows into one
+                        // read-modify-write was measured and is slower: the predicated loads / stores cost the
+                        // common path more than the sequential form costs the rare one.)
                         const bool dup = cd[1] == cd[0] || cd[2] == cd[0] || cd[2] == cd[1] || cd[3] == cd[0] ||
                                          cd[3] == cd[1] || cd[3] == cd[2];
                         __syncwarp();
@@ -810,7 +828,10 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         if (TRAIN) tmem_st_wait();
 #ifdef TVQ_PROFILE_PHASES
         if (blockIdx.x == 0 && lane == 0 && quad == 0 && g < 2)
+        {
             for (int i = 0; i < 8; ++i) g_phase_clk[g][i] = (unsigned long long)ph_acc[i];
+            for (int i = 0; i < 10; ++i) g_phase_all[g][i] = (unsigned long long)ph_acc[i];
+        }
 #endif
     }
 

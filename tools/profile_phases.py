@@ -87,6 +87,11 @@ def run_step(n, k=32, d=128, variant='base'):
     names = ["wait_full", "wait_tmem", "scan", "apply_rest", "release", "ap_load+shfl", "ap_butterfly", "ap_decide+out"]
     for g in range(2):
         print(f"  CTA0 group {g} totals:", ", ".join(f"{names[j]}={int(out[g*16+j])}" for j in range(8)))
+    pa = (ctypes.c_ulonglong * 24)()
+    lib.tvq_debug_phases_all(pa)
+    nm = ["wait_full", "wait_tmem", "scan", "apply_rest", "release", "ap_load", "ap_butterfly", "ap_gather+st+store+codes", "ap_tmem_rmw", "ap_decide"]
+    for g in range(2):
+        print(f"  CTA0 group {g} all phases:", ", ".join(f"{nm[j]}={int(pa[g*12+j])}" for j in range(10)))
     tl = (ctypes.c_ulonglong * 32)()
     lib.tvq_debug_tiles(tl)
     print("  CTA0 warp2 per tile [landed, scores, scan done, apply done]:", [[int(tl[4 * t + j]) for j in range(4)] for t in range(4)])
