@@ -197,15 +197,9 @@ def our_arm(args):
         The LF and HF quantisers are independent, so each runs on its own stream (an explicit
         HF-forward-before-LF-forward dependency was tried and is slower: the tail of one forward kernel
         overlaps the head of the other when the hardware is free to schedule them).
-        Data-parallel runs use ONE stream: each fused kernel's last CTA waits for the same codebook's statistics from
-        every peer, and two such kernels that the ranks happen to start in opposite orders would wait for each other
-        (neither can finish before its last CTA gets an SM) — a fixed order on every rank rules that out."""
-        if world > 1:
-            qh, ih, lh, ph = vq_h(xh)
-            torch.autograd.grad([qh, lh["loss"]], [xh], [gh, ones])
-            ql, il, ll, pl = vq_l(xl)
-            torch.autograd.grad([ql, ll["loss"]], [xl], [gl, ones])
-            return ll["loss"], lh["loss"], il, ih
+        Data-parallel runs do the same: each fused kernel's last CTA waits for that codebook's statistics from every
+        peer while the other codebook's kernel proceeds; the data-parallel launch leaves one SM out of its grid, so the
+        two kernels can never starve each other of SMs whatever order the ranks start them in (tvq_api.cu)."""
         cur = torch.cuda.current_stream()
         side_h.wait_stream(cur)
         with torch.cuda.stream(side_h):

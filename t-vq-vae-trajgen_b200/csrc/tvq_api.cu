@@ -144,7 +144,12 @@ int launch_fwd_umma_impl(FwdParams p, const DeviceInfo& di, cudaStream_t stream)
         if (rc != TVQ_OK) return rc;
     }
     p.num_tiles = (int)((p.n + kUM - 1) / kUM);
-    int grid = p.num_tiles < di.sm_count ? p.num_tiles : di.sm_count;
+    // Data-parallel: the last CTA of a launch holds its SM while it waits for the peers' statistics.  One SM is left out
+    // of the grid so that a second exchange kernel running next to it (the other codebook of the step, on another
+    // stream) can always get ALL of its CTAs resident and publish its own statistics — whatever order the ranks
+    // happen to start the two kernels in, nobody waits for an SM held by a waiting CTA.
+    const int cap = di.sm_count - (p.dp_world > 1 && di.sm_count > 1 ? 1 : 0);
+    int grid = p.num_tiles < cap ? p.num_tiles : cap;
     kern<<<grid, kUThreads, pl.total, stream>>>(tm, p, stages);
     return launch_status();
 }
