@@ -793,23 +793,29 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 float e2v[R][4];
                 int nc[R], cc[R][4];
                 bool valid[R];
-#pragma unroll
-                for (int u = 0; u < R; ++u) {
-                    const int lrow = lrow0 + R * b + u;
-                    const int64_t grow = wrow0 + R * b + u;
-                    valid[u] = grow < p.n;
+                // the merged counts and candidate codes of the batch are warp-uniform: lane 4u + j fetches candidate j
+                // of latent u once (one shared-memory round trip for the whole batch) and shuffles hand them out
+                int nc_l, c_l;
+                {
+                    const int lu = (lane >> 2) & (R - 1), lj = lane & 3;
+                    const int lrow = lrow0 + R * b + lu;
                     const int n0r = ncnt[lrow], n1r = ncnt[kSM + lrow];
                     const int n0 = n0r & 0xff, n1 = n1r & 0xff;
                     // 1..4: the merged count, resolved right here; anything else: general path
-                    nc[u] = (n0r < 0 || n1r < 0 || ((n0r | n1r) & 0x100) || n0 + n1 == 0 || n0 + n1 > 4) ? 0 : n0 + n1;
+                    nc_l = (n0r < 0 || n1r < 0 || ((n0r | n1r) & 0x100) || n0 + n1 == 0 || n0 + n1 > 4) ? 0 : n0 + n1;
+                    // candidate j of the merged list: half 0's entries first, then half 1's
+                    const int jj = lj < nc_l ? lj : 0;
+                    const int c = jj < n0 ? cand_c[jj * kSM + lrow] : cand_c[(kSCand + ((jj - n0) & (kSCand - 1))) * kSM + lrow];
+                    c_l = (c >= 0 && c < p.k) ? c : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    const int64_t grow = wrow0 + R * b + u;
+                    valid[u] = grow < p.n;
+                    nc[u] = __shfl_sync(0xffffffffu, nc_l, 4 * u);
                     if (valid[u] && nc[u] == 0) gen_mask |= 1u << (R * b + u);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // candidate j of the merged list: half 0's entries first, then half 1's
-                        const int jj = j < nc[u] ? j : 0;
-                        const int c = jj < n0 ? cand_c[jj * kSM + lrow] : cand_c[(kSCand + ((jj - n0) & (kSCand - 1))) * kSM + lrow];
-                        cc[u][j] = (c >= 0 && c < p.k) ? c : 0;
-                    }
+                    for (int j = 0; j < 4; ++j) cc[u][j] = __shfl_sync(0xffffffffu, c_l, 4 * u + j);
                     const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)(valid[u] ? grow : 0) * p.d);
                     xa[u] = (valid[u] && h0) ? __ldg(xr + lane) : z4;
                     xb[u] = (valid[u] && h1) ? __ldg(xr + lane + 32) : z4;
