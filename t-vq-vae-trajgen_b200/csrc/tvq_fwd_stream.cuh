@@ -702,14 +702,10 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
         const bool h0 = lane < nchunk, h1 = NV > 1 && lane + 32 < nchunk;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float INF = __int_as_float(0x7f800000);
-#ifndef TVQ_APPLY_NCA
-#define TVQ_APPLY_NCA 4
-#endif
-        // apply phase: up to NCA candidates per latent are resolved in the batched pass (longer lists go to the
-        // one-at-a-time second pass), R latents in flight.  NCA = 2 with twice the latents per L2 round trip was measured
-        // and is slower (512 x 64: 6.3 vs 4.4 ms): three- and four-candidate latents are too common for the second pass.
-        constexpr int NCA = TVQ_APPLY_NCA;
-        constexpr int R = (NV > 1 ? 2 : 4) * (4 / NCA);       // latents in flight in the apply phase
+        // latents in flight in the apply phase (up to 4 candidates each are resolved in the batched pass).  Two candidates
+        // per latent with twice the latents per L2 round trip was measured and is slower (512 x 64: 6.3 vs 4.4 ms): three-
+        // and four-candidate latents are too common for the one-at-a-time second pass.
+        constexpr int R = NV > 1 ? 2 : 4;
         SP_DECL;
         int et = 0, it = 0;
         for (int grp = unit0; grp < ngroups; grp += nunits, ++it) {
@@ -796,9 +792,9 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
 #pragma unroll 1
             for (int b = 0; b < 16 / R; ++b) {
                 if (wrow0 + R * b >= p.n) break;              // warp-uniform
-                float4 xa[R], xb[R], ea[R][NCA], eb[R][NCA];
-                float e2v[R][NCA];
-                int nc[R], cc[R][NCA];
+                float4 xa[R], xb[R], ea[R][4], eb[R][4];
+                float e2v[R][4];
+                int nc[R], cc[R][4];
                 bool valid[R];
                 // the merged counts and candidate codes of the batch are warp-uniform: lane 4u + j fetches candidate j
                 // of latent u once (one shared-memory round trip for the whole batch) and shuffles hand them out
@@ -808,8 +804,8 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                     const int lrow = lrow0 + R * b + lu;
                     const int n0r = ncnt[lrow], n1r = ncnt[kSM + lrow];
                     const int n0 = n0r & 0xff, n1 = n1r & 0xff;
-                    // 1..NCA: the merged count, resolved right here; anything else: general path
-                    nc_l = (n0r < 0 || n1r < 0 || ((n0r | n1r) & 0x100) || n0 + n1 == 0 || n0 + n1 > NCA) ? 0 : n0 + n1;
+                    // 1..4: the merged count, resolved right here; anything else: general path
+                    nc_l = (n0r < 0 || n1r < 0 || ((n0r | n1r) & 0x100) || n0 + n1 == 0 || n0 + n1 > 4) ? 0 : n0 + n1;
                     // candidate j of the merged list: half 0's entries first, then half 1's
                     const int jj = lj < nc_l ? lj : 0;
                     const int c = jj < n0 ? cand_c[jj * kSM + lrow] : cand_c[(kSCand + ((jj - n0) & (kSCand - 1))) * kSM + lrow];
@@ -822,12 +818,12 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                     nc[u] = __shfl_sync(0xffffffffu, nc_l, 4 * u);
                     if (valid[u] && nc[u] == 0) gen_mask |= 1u << (R * b + u);
 #pragma unroll
-                    for (int j = 0; j < NCA; ++j) cc[u][j] = __shfl_sync(0xffffffffu, c_l, 4 * u + j);
+                    for (int j = 0; j < 4; ++j) cc[u][j] = __shfl_sync(0xffffffffu, c_l, 4 * u + j);
                     const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)(valid[u] ? grow : 0) * p.d);
                     xa[u] = (valid[u] && h0) ? __ldg(xr + lane) : z4;
                     xb[u] = (valid[u] && h1) ? __ldg(xr + lane + 32) : z4;
 #pragma unroll
-                    for (int j = 0; j < NCA; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         ea[u][j] = z4; eb[u][j] = z4; e2v[u][j] = 0.f;
                         if (j < nc[u]) {
                             const float4* er = reinterpret_cast<const float4*>(p.cb + (size_t)cc[u][j] * p.d);
@@ -843,11 +839,11 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                     if (valid[u] && nc[u] >= 2) {
                         // fp32 re-score of the (<= 4) candidates, all lanes on this latent
                         n_resc += 1u;
-                        float dd[NCA];
+                        float dd[4];
                         float ss = fmaf(xa[u].x, xa[u].x, fmaf(xa[u].y, xa[u].y, fmaf(xa[u].z, xa[u].z, xa[u].w * xa[u].w)));
                         if (NV > 1) ss = fmaf(xb[u].x, xb[u].x, fmaf(xb[u].y, xb[u].y, fmaf(xb[u].z, xb[u].z, fmaf(xb[u].w, xb[u].w, ss))));
 #pragma unroll
-                        for (int j = 0; j < NCA; ++j) {
+                        for (int j = 0; j < 4; ++j) {
                             dd[j] = fmaf(xa[u].x, ea[u][j].x, fmaf(xa[u].y, ea[u][j].y, fmaf(xa[u].z, ea[u][j].z, xa[u].w * ea[u][j].w)));
                             if (NV > 1) dd[j] = fmaf(xb[u].x, eb[u][j].x, fmaf(xb[u].y, eb[u][j].y, fmaf(xb[u].z, eb[u][j].z, fmaf(xb[u].w, eb[u][j].w, dd[j]))));
                         }
@@ -855,13 +851,13 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                         for (int off = 16; off >= 1; off >>= 1) {
                             ss += __shfl_xor_sync(0xffffffffu, ss, off);
 #pragma unroll
-                            for (int j = 0; j < NCA; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], off);
+                            for (int j = 0; j < 4; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], off);
                         }
                         const float bnd = fmaf(sqrtf(ss), 1.0001f, emax);
                         const float thr32 = 1.6e-6f * bnd * bnd;
                         float m1 = INF, m2 = INF;
 #pragma unroll
-                        for (int j = 0; j < NCA; ++j) {
+                        for (int j = 0; j < 4; ++j) {
                             const float sv = j < nc[u] ? fmaf(-2.f, dd[j], e2v[u][j]) : INF;
                             if (sv < m1) { m2 = m1; m1 = sv; sel = j; }
                             else if (sv < m2) m2 = sv;
@@ -877,7 +873,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                             int arg = 0x7fffffff;
                             sel = 0;
 #pragma unroll
-                            for (int j = 0; j < NCA; ++j) {
+                            for (int j = 0; j < 4; ++j) {
                                 if (j < nc[u]) {
                                     double sd = 0.0;
                                     if (h0) sd = dot4(sd, xa[u], ea[u][j]);
@@ -889,11 +885,9 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                         }
                     }
                     if (valid[u] && nc[u] >= 1) {
-                        int code = cc[u][0];
-                        float4 wa = ea[u][0], wb = eb[u][0];
-#pragma unroll
-                        for (int j = 1; j < NCA; ++j)
-                            if (sel == j) { code = cc[u][j]; wa = ea[u][j]; wb = eb[u][j]; }
+                        const int code = sel == 0 ? cc[u][0] : sel == 1 ? cc[u][1] : sel == 2 ? cc[u][2] : cc[u][3];
+                        const float4 wa = sel == 0 ? ea[u][0] : sel == 1 ? ea[u][1] : sel == 2 ? ea[u][2] : ea[u][3];
+                        const float4 wb = sel == 0 ? eb[u][0] : sel == 1 ? eb[u][1] : sel == 2 ? eb[u][2] : eb[u][3];
                         if (p.q != nullptr || TRAIN)
                             apply_row<NV, TRAIN>(p, esum, xa[u], xb[u], wa, wb, code, wrow0 + R * b + u, h0, h1, lane, loss);
                         mycode = (lane == R * b + u) ? code : mycode;
