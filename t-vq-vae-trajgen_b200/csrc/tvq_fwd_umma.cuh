@@ -792,22 +792,47 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                     p.idx[row0 + lane] = (int64_t)mycode;
                 }
                 if (p.q != nullptr && p.q_hw > 0) {
-                    // transposed store of the 16 rows x d channels parked in the tile: lane = (row, channel parity);
-                    // for one channel 16 lanes write 16 consecutive positions of 'b c (h w)' (64-byte runs)
-                    __syncwarp();
-                    const int r = lane & 15, par = lane >> 4;
-                    const int64_t grow = row0 + r;
-                    const int64_t bi = grow / p.q_hw, hw = grow - bi * p.q_hw;
-                    float* qc = p.q + bi * (int64_t)p.d * p.q_hw + hw;
-                    const float* trow = xt + (quad * 16 + r) * 32;             // row inside a 32-float slab
-                    const int rsw = (quad * 16 + r) & 7;
+                    const bool tile_full = (int64_t)tile * kUM + kUM <= p.n;    // (the same for the four warps of the group)
+                    if (tile_full) {
+                        // transposed store by the whole group: once its four warps have parked their rows, each stores a
+                        // quarter of the channels for ALL 64 rows of the tile — lane = latent, so one instruction writes 32
+                        // consecutive positions of 'b c (h w)' (128-byte runs; 64-byte runs per warp cost 20-40 % more time
+                        // at large n: partial sectors)
+                        named_bar_sync(2 + g, 128);
+                        const int cq = (p.d + 3) >> 2;                          // channels per warp
+#pragma unroll
+                        for (int hrow = 0; hrow < 2; ++hrow) {
+                            const int r = 32 * hrow + lane;
+                            const int64_t grow = (int64_t)tile * kUM + r;
+                            const int64_t bi = grow / p.q_hw, hw = grow - bi * p.q_hw;
+                            float* qc = p.q + bi * (int64_t)p.d * p.q_hw + hw;
+                            const float* trow = xt + r * 32;                      // row inside a 32-float slab
+                            const int rsw = r & 7;
+                            const int c1 = (quad + 1) * cq < p.d ? (quad + 1) * cq : p.d;
 #pragma unroll 4
-                    for (int cc = 0; cc < (p.d >> 1); ++cc) {
-                        const int c = 2 * cc + par;
-                        const float v = trow[(c >> 5) * (kUM * 32) + ((((c >> 2) & 7) ^ rsw) << 2) + (c & 3)];
-                        qc[(int64_t)c * p.q_hw] = v;
+                            for (int c = quad * cq; c < c1; ++c) {
+                                const float v = trow[(c >> 5) * (kUM * 32) + ((((c >> 2) & 7) ^ rsw) << 2) + (c & 3)];
+                                qc[(int64_t)c * p.q_hw] = v;
+                            }
+                        }
+                        __syncwarp();
+                    } else {
+                        // (a full quadrant of the last, partial tile) the warp's own 16 rows: lane = (row, channel parity)
+                        __syncwarp();
+                        const int r = lane & 15, par = lane >> 4;
+                        const int64_t grow = row0 + r;
+                        const int64_t bi = grow / p.q_hw, hw = grow - bi * p.q_hw;
+                        float* qc = p.q + bi * (int64_t)p.d * p.q_hw + hw;
+                        const float* trow = xt + (quad * 16 + r) * 32;             // row inside a 32-float slab
+                        const int rsw = (quad * 16 + r) & 7;
+#pragma unroll 4
+                        for (int cc = 0; cc < (p.d >> 1); ++cc) {
+                            const int c = 2 * cc + par;
+                            const float v = trow[(c >> 5) * (kUM * 32) + ((((c >> 2) & 7) ^ rsw) << 2) + (c & 3)];
+                            qc[(int64_t)c * p.q_hw] = v;
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             } else {
                 for (int r = 0; r < nvalid; ++r) {        // last, partial tile: one fully checked row at a time
