@@ -517,6 +517,37 @@ __global__ void __launch_bounds__(256) batched_transpose_kernel(const float* __r
     }
 }
 
+// The same transpose with one batch element per CTA pass: in[b] (r x s floats, contiguous) is read front to back
+// into a padded shared-memory slab (row pitch odd: both the row-wise fill and the column-wise drain are conflict-free)
+// and out[b] (s x r, contiguous) is written front to back — every global access is a full 128-byte line whatever r and
+// s are (the 32 x 32 tiling leaves 44 % of a tile empty at s = 18).  Used for r or s below 32 when the slab fits.
+__global__ void __launch_bounds__(256) slab_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t b,
+                                                              int r, int s) {
+    extern __shared__ float slab[];
+    const int P = s | 1;                                  // row pitch (odd)
+    const int n = r * s, tid = threadIdx.x, nt = blockDim.x;
+    // element tid + i * nt of the input is (c, t) = divmod(., s); of the output (t, c) = divmod(., r): incremental
+    const int ic = nt / s, it = nt - ic * s, oc = nt / r, ot = nt - oc * r;
+    for (int64_t bi = blockIdx.x; bi < b; bi += gridDim.x) {
+        const float* src = in + bi * (int64_t)n;
+        float* dst = out + bi * (int64_t)n;
+        __syncthreads();                                  // the previous element has been drained
+        int c = tid / s, t = tid - c * s;
+        for (int e = tid; e < n; e += nt) {
+            slab[c * P + t] = ld_stream_v1(src + e);
+            c += ic; t += it;
+            if (t >= s) { t -= s; ++c; }
+        }
+        __syncthreads();
+        int t2 = tid / r, c2 = tid - t2 * r;
+        for (int e = tid; e < n; e += nt) {
+            dst[e] = slab[c2 * P + t2];
+            t2 += oc; c2 += ot;
+            if (c2 >= r) { c2 -= r; ++t2; }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Dense -dist matrix for the stochastic branch (vq.py:210-214, fp32 three-term formula).
 // One warp per latent; k is small where this is used (stage 3 / sampler, k = 32).
