@@ -51,6 +51,8 @@ __device__ unsigned long long g_sprof[128];
 #define SP_LAP(i) do { long long _t = clock64(); sp[i] += _t - sp_t; sp_t = _t; } while (0)
 #define SP_RESET() do { sp_t = clock64(); } while (0)
 #define SP_DUMP(base) do { if (blockIdx.x == 0) for (int _i = 0; _i < 8; ++_i) g_sprof[(base) + _i] = (unsigned long long)sp[_i]; } while (0)
+#define SP_MARK(v) long long v = clock64()
+#define SP_ADD(i, v) do { sp[i] += clock64() - v; } while (0)
 #else
 #define SP_DECL do { } while (0)
 #define SP_WAIT(i, bar, par) mbar_wait(bar, par)
@@ -58,6 +60,8 @@ __device__ unsigned long long g_sprof[128];
 #define SP_LAP(i) do { } while (0)
 #define SP_RESET() do { } while (0)
 #define SP_DUMP(base) do { } while (0)
+#define SP_MARK(v) do { } while (0)
+#define SP_ADD(i, v) do { } while (0)
 #endif
 
 constexpr int kSM = 128;                 // latents per row tile
@@ -792,6 +796,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
 #pragma unroll 1
             for (int b = 0; b < 16 / R; ++b) {
                 if (wrow0 + R * b >= p.n) break;              // warp-uniform
+                SP_MARK(sp_b0);
                 float4 xa[R], xb[R], ea[R][4], eb[R][4];
                 float e2v[R][4];
                 int nc[R], cc[R][4];
@@ -833,6 +838,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                         }
                     }
                 }
+                SP_ADD(6, sp_b0);                              // candidate fetch + loads issued (nothing used yet)
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
                     int sel = 0;
@@ -895,6 +901,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 }
             }
             // ---- second pass (rare): long merged lists, spilled candidates, exhaustive scans — one latent at a time
+            SP_MARK(sp_g0);
 #pragma unroll 1
             while (gen_mask) {
                 const int r = __ffs(gen_mask) - 1;
@@ -924,6 +931,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 }
                 mycode = (lane == r) ? code : mycode;
             }
+            SP_ADD(7, sp_g0);                                  // second pass (general resolution, one latent at a time)
             if (lane < 16 && wrow0 + lane < p.n) {
                 p.idx[wrow0 + lane] = (int64_t)mycode;
                 atomicAdd(p.stats + mycode, 1.0f);            // counts (exact integers in fp32)

@@ -5,7 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "t-vq-vae-trajgen_b200", "csrc")
 SO = os.path.join(CSRC, "_prof", "libtvq_sprof.so")
 
-VARIANTS = {"": [], "noslow": ["-DTVQ_ABL_NOSLOW"], "noe2": ["-DTVQ_ABL_NOE2"], "noslow_nold": ["-DTVQ_ABL_NOSLOW", "-DTVQ_ABL_NOLD"], "noslow_nomma": ["-DTVQ_ABL_NOSLOW", "-DTVQ_ABL_NOMMA"],
+VARIANTS = {"": []}
+_OLD_VARIANTS = {"": [], "noslow": ["-DTVQ_ABL_NOSLOW"], "noe2": ["-DTVQ_ABL_NOE2"], "noslow_nold": ["-DTVQ_ABL_NOSLOW", "-DTVQ_ABL_NOLD"], "noslow_nomma": ["-DTVQ_ABL_NOSLOW", "-DTVQ_ABL_NOMMA"],
             "noslow_noe2": ["-DTVQ_ABL_NOSLOW", "-DTVQ_ABL_NOE2"]}
 
 def so_of(v):
@@ -54,7 +55,7 @@ def run(n, k, d, train, variant=""):
         print(f"  {name:9s}", ", ".join(f"{l}={v/per_cta/1000:.1f}k" for l, v in zip(labels, vals) if l), "(clk per row tile)")
     show("producer", 0, ["wait_e_empty", "wait_b_empty", "", "", "", "", "", "total"])
     show("mma", 8, ["wait_a_full", "wait_t_empty", "wait_b_full", "", "", "", "", "total"])
-    show("scan w2", 16, ["wait_rows", "wait_e2", "wait_t_full", "scan", "merge", "apply", "", ""])
+    show("scan w2", 16, ["wait_rows", "wait_e2", "wait_t_full", "scan", "merge", "apply", "apply:fetch+issue", "apply:2nd pass"])
     show("convert", 24, ["wait_a_empty", "wait_r_empty", "work", "", "", "", "", ""])
     for w in range(0):
         show(f"scan w{w+2}", 64 + 8 * w, ["wait_rows", "wait_e2", "wait_t_full", "scan", "merge", "apply", "", ""])
