@@ -260,6 +260,65 @@ __device__ __forceinline__ void small_stats_tile(const FwdParams& p, const float
     __syncthreads();
 }
 
+// Data-parallel statistics exchange, called by every thread of the LAST CTA of a launch (p.dp_world > 1): the one-shot
+// all-reduce over NVLink peer memory of tvq_aux.cuh::ema_dp_kernel (same buffer layout and protocol: push the packed
+// block into this rank's slot on every rank, fence.sys, publish flag = step everywhere, wait for all local flags, add the
+// slots in rank order), with the rank-ordered sum written back into the local statistics p.stats — after it the
+// single-rank update can run unchanged, and every rank holds identical bits.
+__device__ __forceinline__ void dp_reduce_stats(const FwdParams& p, int* misc) {
+    const int tid = threadIdx.x;
+    const int world = p.dp_world;
+    const int kp = (p.k + 3) & ~3;
+    const int64_t len4 = (int64_t)(kp + p.k * p.d) >> 2;
+    unsigned char* mine = reinterpret_cast<unsigned char*>(p.peers[p.dp_rank]);
+    if (tid == 0) {
+        unsigned* counter = reinterpret_cast<unsigned*>(mine);
+        misc[2] = (int)(*counter + 1u);
+        *counter = (unsigned)misc[2];
+    }
+    __syncthreads();
+    const unsigned epoch = (unsigned)misc[2];
+    const int par = (int)(epoch & 1u);
+    const size_t flags_off = 64, slots_off = 64 + (((size_t)2 * world * 4 + 63) & ~(size_t)63);
+    const float4* src = reinterpret_cast<const float4*>(p.stats);
+    for (int r = 0; r < world; ++r) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(p.peers[r]) + slots_off) +
+                      ((size_t)par * world + p.dp_rank) * len4;
+        for (int64_t f = tid; f < len4; f += blockDim.x) dst[f] = __ldcg(src + f);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) {
+        unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(p.peers[tid]) + flags_off) + par * world + p.dp_rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+        const unsigned* lf = reinterpret_cast<const unsigned*>(mine + flags_off) + par * world + tid;
+        unsigned long long t0 = 0;
+        for (unsigned spin = 1;; ++spin) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(lf) : "memory");
+            if (v == epoch) break;
+            if ((spin & 0x3ffu) == 0) {                 // a lost peer becomes an error, not a hang
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 10000000000ull) __trap();
+            }
+        }
+    }
+    __syncthreads();
+    const float4* slots = reinterpret_cast<const float4*>(mine + slots_off) + (size_t)par * world * len4;
+    float4* out = reinterpret_cast<float4*>(p.stats);
+    for (int64_t f = tid; f < len4; f += blockDim.x) {
+        float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < world; ++r) {
+            const float4 v = __ldcg(slots + (size_t)r * len4 + f);
+            sv.x += v.x; sv.y += v.y; sv.z += v.z; sv.w += v.w;
+        }
+        out[f] = sv;
+    }
+    __syncthreads();
+}
+
 // Last-CTA epilogue (threadFenceReduction pattern): the CTA that takes the final ticket turns the
 // global totals into the scalars.  Called by every thread of every CTA after its flush.
 template <bool TRAIN>

@@ -278,7 +278,7 @@ __device__ __forceinline__ void xcf_issue_tile(const FwdParams& p, const uint32_
 template <int KP, bool TRAIN>
 __device__ __forceinline__ void finish_resident(const FwdParams& p, const float* cbs, int* misc) {
     const int tid = threadIdx.x, lane = tid & 31;
-    const bool ema = TRAIN && p.fuse_ema;
+    const bool ema = TRAIN && p.fuse_ema;       // (data-parallel: p.dp_world > 1 implies the fused step)
     constexpr int J = (KP * 32 + kUThreads - 1) / kUThreads;       // float4 cells of the [k, d] buffers per thread
     const int dq = p.d >> 2, cells = p.k * dq, kp = (p.k + 3) & ~3;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -306,7 +306,8 @@ __device__ __forceinline__ void finish_resident(const FwdParams& p, const float*
     const float cnt1 = (KP > 32 && lane + 32 < p.k) ? __ldcg(p.stats + lane + 32) : 0.f;
     float4* esum4 = reinterpret_cast<float4*>(p.stats + kp);
     float4 sv[J];
-    if (ema) {
+    const bool dp = p.dp_world > 1;            // data-parallel: the sums are loaded after the exchange below
+    if (ema && !dp) {
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int f = tid + j * kUThreads;
@@ -345,8 +346,20 @@ __device__ __forceinline__ void finish_resident(const FwdParams& p, const float*
         p.hdr->n_exact = 0u;
     }
     if (!ema) return;
+    float cnt = cnt0;
+    if (dp) {
+        // perplexity and loss above are this rank's own (as in the reference: vq.py:246-249 sits after, and is unaffected
+        // by, the all-reduce); the EMA update uses the statistics of ALL ranks, summed over NVLink peer memory
+        dp_reduce_stats(p, misc);
+        cnt = lane < p.k ? __ldcg(p.stats + lane) : 0.f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int f = tid + j * kUThreads;
+            sv[j] = f < cells ? __ldcg(esum4 + f) : z4;
+        }
+    }
     // ---- EMA update (vq.py:231,236-242): every other CTA has finished reading the codebook and flushing
-    const float cs_new = lane < p.k ? fmaf(cnt0, p.one_minus_decay, __fmul_rn(cs_old, p.decay)) : 0.f;
+    const float cs_new = lane < p.k ? fmaf(cnt, p.one_minus_decay, __fmul_rn(cs_old, p.decay)) : 0.f;
     const float nsum = __double2float_rn(butterfly_sum((double)cs_new));
     const float denom = __fadd_rn(nsum, p.k_eps);
     float4* avg4 = reinterpret_cast<float4*>(p.embed_avg);
@@ -927,8 +940,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         if (tid == 0) atomicAdd(&p.hdr->loss_sum, t);
     }
     TVQ_KT(6);
-    if (p.dp_world > 1) finish_ticket<TRAIN>(p, red, misc);      // data-parallel: statistics exchange over peer memory
-    else finish_resident<KP, TRAIN>(p, cbs, misc);
+    finish_resident<KP, TRAIN>(p, cbs, misc);
     TVQ_KT(7);
 #ifdef TVQ_PROFILE_PHASES
     if (blockIdx.x == 0 && (tid == 0 || tid == 64))
