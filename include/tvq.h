@@ -117,6 +117,11 @@ TVQ_API int tvq_ema_update(const float *stats, float *cluster_size, float *embed
  *   use an all-reduce + tvq_ema_update).  stats (this rank's, from tvq_forward) must be padded to a
  *   multiple of 4 floats (TVQ_STATS_LEN rounded up).                                              */
 TVQ_API size_t tvq_exchange_bytes(int k, int d, int world);
+/* Exchange-buffer header (first 64 bytes of every rank's buffer, local use only): u32 [0] step counter, u32 [1] error word.
+ * A data-parallel kernel waits for every peer's statistics at most `seconds` (default 1800; 0 = for ever).  When a peer does
+ * not show up in time the kernel stores the step number in the error word, gives up the wait and finishes the step with
+ * whatever that peer's slot holds: the CUDA context survives and the HOST decides (read the word; 0 = no error so far). */
+TVQ_API int tvq_set_peer_timeout(double seconds);
 TVQ_API int tvq_ema_update_dp(const float *stats, void *const *peer_bufs, int rank, int world,
                       float *cluster_size, float *embed_avg, float *embed, float *embed_prev, int k,
                       int d, double decay, double eps, void *stream);
@@ -181,6 +186,11 @@ TVQ_API int tvq_backward(const float *g_q, const float *g_commit, const float *g
  *   tokens [b*t] int64; layout 0: out[b, t, d]; layout 1: out[b, d, t] (decoder layout).      */
 TVQ_API int tvq_gather(const int64_t *tokens, const float *codebook, int64_t b, int64_t t, int k, int d,
                int layout, float *out, void *stream);
+/* The same, reporting ids outside [0, k) — F.embedding raises on them (e.g. a mask token, id == k, left over by an
+ * incomplete MaskGIT pass): such a token's output row is NaN and *bad_count (device uint32, caller-zeroed, may be NULL)
+ * is incremented once per offending token.  tvq_gather is this call with bad_count = NULL.                      */
+TVQ_API int tvq_gather_checked(const int64_t *tokens, const float *codebook, int64_t b, int64_t t, int k, int d,
+                       int layout, float *out, unsigned *bad_count, void *stream);
 
 /* Full negative squared-distance matrix dist[n,k] (vq.py:210-214) for the stochastic
  * `svq_temp` branch (vq.py:55-56), whose sampling stays in torch to share its RNG stream.   */

@@ -19,21 +19,42 @@ using namespace tvq;
 
 namespace {
 
+constexpr int kMaxDevices = 64;
 struct DeviceInfo {
     int checked = 0;
     int ok = 0;
+    int index = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
 };
-DeviceInfo g_dev[64];
+DeviceInfo g_dev[kMaxDevices];
+
+// cudaFuncSetAttribute / occupancy are per DEVICE: every host-side cache of them is indexed by the device the call runs on
+// (one process may drive several GPUs).  Benign if raced: the worst case is a repeated, idempotent runtime call.
+struct PerDeviceInt {
+    int v[kMaxDevices];
+    explicit PerDeviceInt(int init) { for (int i = 0; i < kMaxDevices; ++i) v[i] = init; }
+    int& operator[](int dev) { return v[dev]; }
+};
+
+template <typename Kern>
+int ensure_dynamic_smem(Kern kern, PerDeviceInt& cache, int dev, size_t bytes) {
+    if ((long long)bytes > (long long)cache[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        cache[dev] = (int)bytes;
+    }
+    return TVQ_OK;
+}
 
 int device_info(DeviceInfo** out) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
-    if (dev < 0 || dev >= 64) return TVQ_ERR_DEVICE;
+    if (dev < 0 || dev >= kMaxDevices) return TVQ_ERR_DEVICE;
     DeviceInfo& di = g_dev[dev];
     if (!di.checked) {
+        di.index = dev;
         int major = 0;
         if ((e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess) return (int)e;
         cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -44,6 +65,11 @@ int device_info(DeviceInfo** out) {
     *out = &di;
     return di.ok ? TVQ_OK : TVQ_ERR_DEVICE;
 }
+
+// How long a data-parallel kernel waits for a peer's statistics before it reports the step in the exchange buffer's error
+// word and carries on (tvq_set_peer_timeout; default 30 min — longer than torch's NCCL watchdog, so a slow rank is never
+// turned into an error by this library first).  Process-wide, passed by value with every launch.
+unsigned long long g_peer_timeout_ns = 1800ull * 1000000000ull;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -57,21 +83,17 @@ inline int launch_status() {
 template <int DP, bool TRAIN>
 int launch_fwd_simt(const FwdParams& p, const SmemPlan& pl, const DeviceInfo& di, cudaStream_t stream) {
     auto kern = fwd_simt_kernel<DP, TRAIN>;
-    static int configured_smem = -1;   // per instantiation (host-side caches; benign if raced)
-    static int occ_smem = -1, occ_val = 0;
-    if (pl.total > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total);
-        if (e != cudaSuccess) return (int)e;
-        configured_smem = pl.total;
-    }
-    if (occ_smem != pl.total) {
+    static PerDeviceInt configured_smem(-1);   // per instantiation and device
+    static PerDeviceInt occ_smem(-1), occ_val(0);
+    if (int rc = ensure_dynamic_smem(kern, configured_smem, di.index, pl.total)) return rc;
+    if (occ_smem[di.index] != pl.total) {
         int o = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, pl.total);
         if (e != cudaSuccess) return (int)e;
-        occ_val = o;
-        occ_smem = pl.total;
+        occ_val[di.index] = o;
+        occ_smem[di.index] = pl.total;
     }
-    const int occ = occ_val;
+    const int occ = occ_val[di.index];
     if (occ < 1) return TVQ_ERR_UNSUPPORTED;
     long long grid = (long long)occ * di.sm_count;
     if (grid > p.num_tiles) grid = p.num_tiles;
@@ -131,12 +153,8 @@ int launch_fwd_umma_impl(FwdParams p, const DeviceInfo& di, cudaStream_t stream)
     if (stages < 2) return TVQ_ERR_UNSUPPORTED;
     if (TRAIN && stages * (kUM * DP * 4) < 4 * KP * 32 * 16) return TVQ_ERR_UNSUPPORTED;   // end-of-kernel dump area
     const UmmaPlan pl = make_umma_plan(DP, KP, stages);
-    static int configured_smem = -1;
-    if (pl.total > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total);
-        if (e != cudaSuccess) return (int)e;
-        configured_smem = pl.total;
-    }
+    static PerDeviceInt configured_smem(-1);
+    if (int rc = ensure_dynamic_smem(kern, configured_smem, di.index, pl.total)) return rc;
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));                       // channels-first x: loaded with cp.async, no tensor map
     if (!XCF) {
@@ -207,12 +225,8 @@ int launch_fwd_stream_impl(FwdParams p, const void* cbh, const DeviceInfo& di, c
     if (stages > kSMaxStages) stages = kSMaxStages;
     if (stages < 2) return TVQ_ERR_UNSUPPORTED;
     const StreamPlan pl = make_stream_plan(DP, NT, stages, CG);
-    static int configured_smem = -1;
-    if (pl.total > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total);
-        if (e != cudaSuccess) return (int)e;
-        configured_smem = pl.total;
-    }
+    static PerDeviceInt configured_smem(-1);
+    if (int rc = ensure_dynamic_smem(kern, configured_smem, di.index, pl.total)) return rc;
     CUtensorMap tm;
     int rc = make_cb_tensor_map(&tm, cbh, p.k, DP, NT / CG);
     if (rc != TVQ_OK) return rc;
@@ -300,7 +314,13 @@ __attribute__((visibility("default"))) int tvq_debug_gt(unsigned long long* out4
 }
 #endif
 
-int tvq_abi_version(void) { return 1; }
+int tvq_abi_version(void) { return 2; }
+
+int tvq_set_peer_timeout(double seconds) {
+    if (!(seconds >= 0.0) || seconds > 1e9) return TVQ_ERR_BAD_ARG;
+    g_peer_timeout_ns = (unsigned long long)(seconds * 1e9);
+    return TVQ_OK;
+}
 
 const char* tvq_error_string(int code) {
     switch (code) {
@@ -370,7 +390,7 @@ int forward_impl(const float* x, const float* codebook, int64_t n, int k, int d,
     p.idx = idx; p.q = (flags & TVQ_F_WRITE_Q) ? q : nullptr; p.stats = stats; p.scalars = scalars;
     p.hdr = hdr; p.e2 = e2; p.commitment_weight = commitment_weight;
     p.commit_out = nullptr; p.weighted_out = nullptr; p.fuse_ema = 0;
-    p.peers = nullptr; p.dp_rank = 0; p.dp_world = 1; p.q_hw = q_hw; p.x_hw = x_hw;
+    p.peers = nullptr; p.dp_rank = 0; p.dp_world = 1; p.dp_timeout_ns = 0; p.q_hw = q_hw; p.x_hw = x_hw;
     p.cluster_size = nullptr; p.embed_avg = nullptr; p.embed = nullptr; p.embed_prev = nullptr;
     p.decay = p.one_minus_decay = p.eps = p.k_eps = 0.f;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
@@ -434,7 +454,7 @@ int train_step_impl(const float* x, float* embed, float* cluster_size, float* em
     p.commit_out = commit_out; p.weighted_out = weighted_out;
     p.cluster_size = cluster_size; p.embed_avg = embed_avg; p.embed = embed; p.embed_prev = embed_prev;
     p.decay = (float)decay; p.one_minus_decay = (float)(1.0 - decay); p.eps = (float)eps; p.k_eps = (float)((double)k * eps);
-    p.peers = peers; p.dp_rank = dp_rank; p.dp_world = dp_world; p.q_hw = q_hw; p.x_hw = x_hw;
+    p.peers = peers; p.dp_rank = dp_rank; p.dp_world = dp_world; p.dp_timeout_ns = g_peer_timeout_ns; p.q_hw = q_hw; p.x_hw = x_hw;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
     p.exact = 0; p.given_idx = 0; p.use_hist = k <= 2048;
     if (umma) {
@@ -517,7 +537,7 @@ int tvq_backward_cfx(const float* g_zq, const float* g_commit, const float* g_we
     int rc = device_info(&di);
     if (rc != TVQ_OK) return rc;
     auto launch = [&](auto kern) -> int {
-        if (smem > 48 * 1024) {
+        if (smem > 48 * 1024) {      // idempotent and cheap next to the launch; no cache, so nothing to key by device
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
         }
@@ -549,12 +569,8 @@ int tvq_backward_cf(const float* g_zq, const float* g_commit, const float* g_wei
     const float scale = (float)(2.0 / ((double)b * (double)hw * (double)d));
     const size_t slab = ((size_t)hw * (d + 1) + (size_t)k * (d + 1) + (size_t)hw) * sizeof(float);
     if (k >= 1 && (d & 3) == 0 && aligned16(x) && aligned16(codebook) && slab <= 100 * 1024) {
-        static size_t configured = 48 * 1024;
-        if (slab > configured) {
-            cudaError_t e = cudaFuncSetAttribute(backward_cf_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab);
-            if (e != cudaSuccess) return (int)e;
-            configured = slab;
-        }
+        static PerDeviceInt configured(48 * 1024);
+        if ((rc = ensure_dynamic_smem(backward_cf_slab_kernel, configured, di->index, slab)) != TVQ_OK) return rc;
         int64_t grid = b < 8LL * di->sm_count ? b : 8LL * di->sm_count;
         backward_cf_slab_kernel<<<(unsigned)grid, 256, slab, stream>>>(g_zq, g_commit, g_weighted, x, idx, codebook, b, hw, k, d,
                                                                       commitment_weight, scale, g_z);
@@ -635,6 +651,7 @@ int tvq_ema_update_dp(const float* stats, void* const* peer_bufs, int rank, int 
     p.e.hdr = nullptr;
     p.peers = peer_bufs; p.rank = rank; p.world = world;
     p.len4 = (TVQ_STATS_LEN(k, d) + 3) / 4;
+    p.timeout_ns = g_peer_timeout_ns;
     ema_dp_kernel<<<1, 1024, 0, stream>>>(p);
     return launch_status();
 }
@@ -660,6 +677,11 @@ int tvq_backward(const float* g_q, const float* g_commit, const float* g_weighte
 
 int tvq_gather(const int64_t* tokens, const float* codebook, int64_t b, int64_t t, int k, int d, int layout,
                float* out, void* stream_) {
+    return tvq_gather_checked(tokens, codebook, b, t, k, d, layout, out, nullptr, stream_);
+}
+
+int tvq_gather_checked(const int64_t* tokens, const float* codebook, int64_t b, int64_t t, int k, int d, int layout,
+                       float* out, unsigned* bad_count, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 1 || b < 0 || t < 0 || (layout != 0 && layout != 1)) return TVQ_ERR_UNSUPPORTED;
     if (b * t == 0) return TVQ_OK;
@@ -671,11 +693,11 @@ int tvq_gather(const int64_t* tokens, const float* codebook, int64_t b, int64_t 
         if ((d & 3) || !aligned16(codebook) || !aligned16(out)) return TVQ_ERR_UNSUPPORTED;
         int64_t blocks = (b * t + 7) / 8;
         if (blocks > 16LL * di->sm_count) blocks = 16LL * di->sm_count;
-        gather_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tokens, codebook, b * t, k, d, out);
+        gather_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tokens, codebook, b * t, k, d, out, bad_count);
     } else {
         int64_t tiles = b * ((t + 31) / 32) * ((d + 31) / 32);
         if (tiles > 16LL * di->sm_count) tiles = 16LL * di->sm_count;
-        gather_transposed_kernel<<<(unsigned)tiles, 256, 0, stream>>>(tokens, codebook, b, t, k, d, out);
+        gather_transposed_kernel<<<(unsigned)tiles, 256, 0, stream>>>(tokens, codebook, b, t, k, d, out, bad_count);
     }
     return launch_status();
 }
@@ -705,12 +727,8 @@ int tvq_frontend(const float* x, int64_t b, int c, int l, int n_fft, float* xf, 
     if (rc != TVQ_OK) return rc;
     const size_t smem = frontend_smem_bytes(l, n_fft);
     if (smem > (size_t)di->max_smem_optin) return TVQ_ERR_UNSUPPORTED;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
+    static PerDeviceInt configured(48 * 1024);
+    if ((rc = ensure_dynamic_smem(frontend_kernel, configured, di->index, smem)) != TVQ_OK) return rc;
     FrontendParams p;
     p.x = x; p.rows = b * c; p.c = c; p.l = l; p.n_fft = n_fft;
     p.xf = xf; p.enc_in_l = enc_in_l; p.enc_in_h = enc_in_h; p.x_l = x_l; p.x_h = x_h;
@@ -733,12 +751,8 @@ int launch_band_istft(const BandIstftParams& p, int64_t b, int c, cudaStream_t s
     if (rc != TVQ_OK) return rc;
     const size_t smem = band_istft_smem_bytes(p.l, p.n_fft);
     if (smem > (size_t)di->max_smem_optin) return TVQ_ERR_UNSUPPORTED;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(band_istft_kernel<BACKWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
+    static PerDeviceInt configured(48 * 1024);
+    if ((rc = ensure_dynamic_smem(band_istft_kernel<BACKWARD>, configured, di->index, smem)) != TVQ_OK) return rc;
     int64_t grid = p.rows;
     if (grid > 64LL * di->sm_count) grid = 64LL * di->sm_count;
     band_istft_kernel<BACKWARD><<<(unsigned)grid, 128, smem, stream>>>(p);

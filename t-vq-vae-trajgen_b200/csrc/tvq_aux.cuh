@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) ema_kernel(const EmaParams p) {
 // Data-parallel EMA update in ONE kernel: a one-shot all-reduce of the packed statistics over NVLink
 // peer memory, fused with the EMA update (the reference's two dormant all_reduce hooks, vq.py:229 and
 // :234, followed by :231 and :236-242).  Every rank owns an exchange buffer that all peers have mapped:
-//   header (64 B, local only: launch counter) | flags [2 parities][world] u32 | slots [2][world][len4] fp32
+//   header (64 B, local only: u32 launch counter, u32 error word = last step a peer timed out in) | flags [2 parities][world] u32 | slots [2][world][len4] fp32
 // Step e (parity e & 1): push my statistics into slot [parity][rank] of EVERY rank's buffer (posted
 // remote stores), fence, publish flag = e on every rank, wait until all `world` local flags show e, then
 // add the slots in rank order — the same order on every rank, so the replicas stay bit-identical — and
@@ -141,6 +141,7 @@ struct EmaDpParams {
     void* const* peers;          // device array [world]: every rank's exchange buffer
     int rank, world;
     int64_t len4;                // statistics length in float4 (padded)
+    unsigned long long timeout_ns;   // give up waiting for a peer after this long (0 = never); see wait_flag_sys
 };
 
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
@@ -179,17 +180,9 @@ __global__ void __launch_bounds__(1024) ema_dp_kernel(const EmaDpParams p) {
     if (tid < p.world) {
         unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(p.peers[tid]) + flags_off) + par * p.world + p.rank;
         st_release_sys_u32(flag, epoch);
-        // ---- wait for every rank's contribution to MY buffer (bounded: a lost peer becomes an error, not a hang)
+        // ---- wait for every rank's contribution to MY buffer (bounded: a lost peer becomes a reported error, not a hang)
         const unsigned* lf = reinterpret_cast<const unsigned*>(mine + flags_off) + par * p.world + tid;
-        unsigned long long t0 = 0;
-        for (unsigned spin = 1; ld_acquire_sys_u32(lf) != epoch; ++spin) {
-            if ((spin & 0x3ffu) == 0) {
-                unsigned long long t;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                if (t0 == 0) t0 = t;
-                else if (t - t0 > 10000000000ull) __trap();
-            }
-        }
+        wait_flag_sys(lf, epoch, p.timeout_ns, reinterpret_cast<unsigned*>(mine) + 1);
     }
     __syncthreads();
     // ---- reduce (rank order) + EMA update
@@ -269,12 +262,20 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
 // De-tokenising gather (models/maskgit.py:465-470).
 // layout 0: out[b, t, :] = cb[tok[b, t]]       — one warp per token, 16-byte lanes
 __global__ void __launch_bounds__(256) gather_rows_kernel(const int64_t* __restrict__ tok, const float* __restrict__ cb,
-                                                           int64_t ntok, int k, int d, float* __restrict__ out) {
+                                                           int64_t ntok, int k, int d, float* __restrict__ out,
+                                                           unsigned* __restrict__ bad) {
+    // An id outside [0, k) (e.g. a leaked mask token, id == k) is an error F.embedding raises on: its row is written as
+    // NaN and counted in *bad (if given) — never silently decoded as a neighbouring code.
     const int lane = threadIdx.x & 31;
     const int dq = d >> 2;
+    const float nan = __int_as_float(0x7fc00000);
     for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntok; t += ((int64_t)gridDim.x * blockDim.x) >> 5) {
-        int64_t code = __ldg(tok + t);
-        code = code < 0 ? 0 : (code >= k ? k - 1 : code);
+        const int64_t code = __ldg(tok + t);
+        if (code < 0 || code >= k) {
+            if (lane == 0 && bad) atomicAdd(bad, 1u);
+            for (int c = lane; c < dq; c += 32) st_stream_v4(out + (size_t)t * d + 4 * c, make_float4(nan, nan, nan, nan));
+            continue;
+        }
         const float4* er = reinterpret_cast<const float4*>(cb + (size_t)code * d);
         for (int c = lane; c < dq; c += 32) st_stream_v4(out + (size_t)t * d + 4 * c, __ldg(er + c));
     }
@@ -283,7 +284,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const int64_t* __restr
 // are transposed through shared memory so that both the code-word reads and the output writes
 // are coalesced.
 __global__ void __launch_bounds__(256) gather_transposed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ cb,
-                                                                 int64_t b, int64_t t, int k, int d, float* __restrict__ out) {
+                                                                 int64_t b, int64_t t, int k, int d, float* __restrict__ out,
+                                                                 unsigned* __restrict__ bad) {
     __shared__ float tile[32][33];
     __shared__ int codes[32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps
@@ -297,11 +299,13 @@ __global__ void __launch_bounds__(256) gather_transposed_kernel(const int64_t* _
         if (threadIdx.x < 32) {
             int64_t tt = t0 + threadIdx.x;
             int64_t code = tt < t ? __ldg(tok + bi * t + tt) : 0;
-            codes[threadIdx.x] = (int)(code < 0 ? 0 : (code >= k ? k - 1 : code));
+            const bool oob = code < 0 || code >= k;          // -> NaN column + error count (see gather_rows_kernel)
+            if (oob && bad && d0 == 0) atomicAdd(bad, 1u);
+            codes[threadIdx.x] = oob ? -1 : (int)code;
         }
         __syncthreads();
         for (int r = ty; r < 32; r += 8)   // r: token within tile, tx: channel
-            tile[r][tx] = (d0 + tx < d) ? __ldg(cb + (size_t)codes[r] * d + d0 + tx) : 0.f;
+            tile[r][tx] = (d0 + tx < d) ? (codes[r] < 0 ? __int_as_float(0x7fc00000) : __ldg(cb + (size_t)codes[r] * d + d0 + tx)) : 0.f;
         __syncthreads();
         for (int r = ty; r < 32; r += 8)   // r: channel within tile, tx: token
             if (d0 + r < d && t0 + tx < t) out[(bi * d + d0 + r) * t + t0 + tx] = tile[tx][r];

@@ -106,6 +106,25 @@ __device__ __forceinline__ double canon_dot_global(const float* a, const float* 
     return butterfly_sum(p);
 }
 
+// Data-parallel exchange: spin until the local flag *lf shows `epoch` (written by a peer over NVLink with st.release.sys).
+// A peer that does not show up within timeout_ns (0 = wait for ever) is REPORTED, not fatal: the step counter is stored in
+// *err (the error word of this rank's exchange buffer, read by the host: PeerExchange.check()) and the wait gives up, so
+// the CUDA context survives — what NCCL's watchdog does with a lost rank is the host's decision here too.
+__device__ __forceinline__ void wait_flag_sys(const unsigned* lf, unsigned epoch, unsigned long long timeout_ns, unsigned* err) {
+    unsigned long long t0 = 0;
+    for (unsigned spin = 1;; ++spin) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(lf) : "memory");
+        if (v == epoch) return;
+        if ((spin & 0x3ffu) == 0 && timeout_ns != 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > timeout_ns) { atomicMax(err, epoch); return; }
+        }
+    }
+}
+
 // Block-wide sum of one double per thread (kThreads threads); result valid in thread 0.
 __device__ __forceinline__ double block_sum(double v, double* scratch /* >= kWarps doubles */) {
 #pragma unroll

@@ -52,6 +52,7 @@ struct FwdParams {
     // data-parallel fused step: exchange buffers of every rank (tvq_aux.cuh::ema_dp_kernel layout); world <= 1: local
     void* const* peers;
     int dp_rank, dp_world;
+    unsigned long long dp_timeout_ns;   // give up waiting for a peer after this long (0 = never); tvq_common.cuh::wait_flag_sys
     // q layout: 0 = [n, d] row-major; hw > 0 = channels-first [n / hw, d, hw] (the 'b c (h w)' layout of the caller,
     // utils/train_utils.py:349): resident-codebook tcgen05 kernel only
     int q_hw;
@@ -292,18 +293,7 @@ __device__ __forceinline__ void dp_reduce_stats(const FwdParams& p, int* misc) {
         unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(p.peers[tid]) + flags_off) + par * world + p.dp_rank;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
         const unsigned* lf = reinterpret_cast<const unsigned*>(mine + flags_off) + par * world + tid;
-        unsigned long long t0 = 0;
-        for (unsigned spin = 1;; ++spin) {
-            unsigned v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(lf) : "memory");
-            if (v == epoch) break;
-            if ((spin & 0x3ffu) == 0) {                 // a lost peer becomes an error, not a hang
-                unsigned long long t;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                if (t0 == 0) t0 = t;
-                else if (t - t0 > 10000000000ull) __trap();
-            }
-        }
+        wait_flag_sys(lf, epoch, p.dp_timeout_ns, reinterpret_cast<unsigned*>(mine) + 1);
     }
     __syncthreads();
     const float4* slots = reinterpret_cast<const float4*>(mine + slots_off) + (size_t)par * world * len4;
@@ -396,18 +386,7 @@ __device__ __forceinline__ void finish_ticket(const FwdParams& p, double* red, i
                     unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(p.peers[tid]) + flags_off) + par * world + p.dp_rank;
                     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
                     const unsigned* lf = reinterpret_cast<const unsigned*>(mine + flags_off) + par * world + tid;
-                    unsigned long long t0 = 0;
-                    for (unsigned spin = 1;; ++spin) {
-                        unsigned v;
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(lf) : "memory");
-                        if (v == epoch) break;
-                        if ((spin & 0x3ffu) == 0) {
-                            unsigned long long t;
-                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                            if (t0 == 0) t0 = t;
-                            else if (t - t0 > 10000000000ull) __trap();
-                        }
-                    }
+                    wait_flag_sys(lf, epoch, p.dp_timeout_ns, reinterpret_cast<unsigned*>(mine) + 1);
                 }
                 __syncthreads();
                 slots = reinterpret_cast<const float4*>(mine + slots_off) + (size_t)par * world * len4;

@@ -25,8 +25,43 @@ def stats_len(k: int, d: int) -> int:
     return stats_offset(k) + k * d
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None) -> int:
+    """Raw cudaStream_t of torch's current stream on `device` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on_device_of:
+    """Make `t`'s device the current CUDA device for the enclosed C-ABI call.  The ABI works on the CURRENT device
+    (include/tvq.h), so a module living on cuda:1 must not launch on cuda:0 just because nobody called set_device."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, t: torch.Tensor):
+        self.idx = t.device.index
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _launch(name: str, anchor: torch.Tensor, *args) -> None:
+    """lib.<name>(*args, stream) on the anchor tensor's device and torch's current stream there; raises on a non-zero
+    status.  Every pointer argument must live on that device (checked by the callers through _same_device)."""
+    with _on_device_of(anchor):
+        rc = getattr(_lib.load(), name)(*args, torch.cuda.current_stream(anchor.device).cuda_stream)
+    _lib.check(rc, name)
+
+
+def _same_device(anchor: torch.Tensor, *others) -> None:
+    for t in others:
+        if t is not None and t.device != anchor.device:
+            raise RuntimeError(f"tensors on different devices: {anchor.device} and {t.device}")
 
 
 def _need(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
@@ -64,6 +99,7 @@ def vq_forward_raw(x: torch.Tensor, codebook: torch.Tensor, ws: Workspace, *, tr
     """
     _need(x, "x")
     _need(codebook, "codebook")
+    _same_device(x, codebook, ws.buf, idx)
     n, d = x.shape
     k = codebook.shape[0]
     if codebook.shape[1] != d:
@@ -80,10 +116,9 @@ def vq_forward_raw(x: torch.Tensor, codebook: torch.Tensor, ws: Workspace, *, tr
         scalars.fill_(float("nan"))
         ws.stats.zero_()
         return idx, q, scalars
-    rc = _lib.load().tvq_forward(x.data_ptr(), codebook.data_ptr(), n, k, d, f, float(commitment_weight), idx.data_ptr(),
+    _launch("tvq_forward", x, x.data_ptr(), codebook.data_ptr(), n, k, d, f, float(commitment_weight), idx.data_ptr(),
                                  q.data_ptr() if write_q else None, ws.stats.data_ptr(), scalars.data_ptr(),
-                                 ws.buf.data_ptr(), ws.nbytes, _stream())
-    _lib.check(rc, "tvq_forward")
+                                 ws.buf.data_ptr(), ws.nbytes)
     return idx, q, scalars
 
 
@@ -91,10 +126,9 @@ def vq_ema_update(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg: to
                   embed_prev: Optional[torch.Tensor], decay: float, eps: float, ws: Workspace) -> None:
     _need(stats, "stats"); _need(cluster_size, "cluster_size"); _need(embed_avg, "embed_avg"); _need(embed, "embed")
     k, d = embed.shape
-    rc = _lib.load().tvq_ema_update(stats.data_ptr(), cluster_size.data_ptr(), embed_avg.data_ptr(), embed.data_ptr(),
+    _launch("tvq_ema_update", stats, stats.data_ptr(), cluster_size.data_ptr(), embed_avg.data_ptr(), embed.data_ptr(),
                                     embed_prev.data_ptr() if embed_prev is not None else None, k, d, float(decay),
-                                    float(eps), ws.buf.data_ptr(), ws.nbytes, _stream())
-    _lib.check(rc, "tvq_ema_update")
+                                    float(eps), ws.buf.data_ptr(), ws.nbytes)
 
 
 class PeerExchange:
@@ -126,17 +160,23 @@ class PeerExchange:
     def matches(self, k: int, d: int, device: torch.device) -> bool:
         return self.k == k and self.d == d and self.device == device
 
+    def check(self) -> None:
+        """Raise if a kernel ever gave up waiting for a peer (error word of the exchange header, include/tvq.h)."""
+        step = int(self.buf[4:8].view(torch.int32).item())
+        if step != 0:
+            raise RuntimeError(f"tvq_b200: rank {self.rank} timed out waiting for a peer's codebook statistics in "
+                               f"data-parallel step {step}; the replicas' codebooks may have diverged")
+
 
 def vq_ema_update_dp(stats: torch.Tensor, ex: PeerExchange, cluster_size: torch.Tensor, embed_avg: torch.Tensor,
                      embed: torch.Tensor, embed_prev: Optional[torch.Tensor], decay: float, eps: float) -> None:
     """tvq_ema_update_dp: all-reduce of the packed statistics over NVLink peer memory + EMA update, one kernel."""
     _need(stats, "stats"); _need(cluster_size, "cluster_size"); _need(embed_avg, "embed_avg"); _need(embed, "embed")
     k, d = embed.shape
-    rc = _lib.load().tvq_ema_update_dp(stats.data_ptr(), ex.peers.data_ptr(), ex.rank, ex.world, cluster_size.data_ptr(),
+    _launch("tvq_ema_update_dp", stats, stats.data_ptr(), ex.peers.data_ptr(), ex.rank, ex.world, cluster_size.data_ptr(),
                                        embed_avg.data_ptr(), embed.data_ptr(),
                                        embed_prev.data_ptr() if embed_prev is not None else None, k, d, float(decay),
-                                       float(eps), _stream())
-    _lib.check(rc, "tvq_ema_update_dp")
+                                       float(eps))
 
 
 def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: float, embed_prev: Optional[torch.Tensor],
@@ -148,6 +188,7 @@ def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: flo
     """
     _need(x, "x")
     embed = cb._embed_data()
+    _same_device(x, embed, ws.buf, embed_prev)
     n, d = x.shape
     k = embed.shape[0]
     idx = torch.empty(n, dtype=torch.int64, device=x.device)
@@ -158,19 +199,17 @@ def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: flo
     if n == 0:
         scalars.fill_(float("nan")); commit.fill_(float("nan")); weighted.fill_(float("nan"))
     if px is not None:       # data-parallel: the kernel's last CTA sums the statistics of all ranks over NVLink peer memory
-        rc = _lib.load().tvq_train_step_dp(x.data_ptr(), embed.data_ptr(), cb.cluster_size.data_ptr(), cb.embed_avg.data_ptr(),
+        _launch("tvq_train_step_dp", x, x.data_ptr(), embed.data_ptr(), cb.cluster_size.data_ptr(), cb.embed_avg.data_ptr(),
                                            embed_prev.data_ptr() if embed_prev is not None else None, n, k, d,
                                            float(commitment_weight), float(cb.decay), float(cb.eps), idx.data_ptr(),
                                            q.data_ptr(), scalars.data_ptr(), commit.data_ptr(), weighted.data_ptr(),
-                                           ws.buf.data_ptr(), ws.nbytes, px.peers.data_ptr(), px.rank, px.world, _stream())
-        _lib.check(rc, "tvq_train_step_dp")
+                                           ws.buf.data_ptr(), ws.nbytes, px.peers.data_ptr(), px.rank, px.world)
         return idx, q, scalars, commit, weighted
-    rc = _lib.load().tvq_train_step(x.data_ptr() if n else None, embed.data_ptr(), cb.cluster_size.data_ptr(),
+    _launch("tvq_train_step", embed, x.data_ptr() if n else None, embed.data_ptr(), cb.cluster_size.data_ptr(),
                                     cb.embed_avg.data_ptr(), embed_prev.data_ptr() if embed_prev is not None else None,
                                     n, k, d, float(commitment_weight), float(cb.decay), float(cb.eps),
                                     idx.data_ptr() if n else None, q.data_ptr() if n else None, scalars.data_ptr(),
-                                    commit.data_ptr(), weighted.data_ptr(), ws.buf.data_ptr(), ws.nbytes, _stream())
-    _lib.check(rc, "tvq_train_step")
+                                    commit.data_ptr(), weighted.data_ptr(), ws.buf.data_ptr(), ws.nbytes)
     return idx, q, scalars, commit, weighted
 
 
@@ -181,28 +220,35 @@ def vq_backward(g_q: Optional[torch.Tensor], g_commit: Optional[torch.Tensor], g
     for t, name in ((g_q, "g_q"), (g_commit, "g_commit"), (g_weighted, "g_weighted")):
         if t is not None:
             _need(t, name)
+    _same_device(x, idx, codebook, g_q, g_commit, g_weighted)
     n, d = x.shape
     g_x = torch.empty_like(x)
     ptr = lambda t: t.data_ptr() if t is not None else None
-    rc = _lib.load().tvq_backward(ptr(g_q), ptr(g_commit), ptr(g_weighted), x.data_ptr(), idx.data_ptr(),
-                                  codebook.data_ptr(), n, codebook.shape[0], d, float(commitment_weight), g_x.data_ptr(),
-                                  _stream())
-    _lib.check(rc, "tvq_backward")
+    _launch("tvq_backward", x, ptr(g_q), ptr(g_commit), ptr(g_weighted), x.data_ptr(), idx.data_ptr(),
+                                  codebook.data_ptr(), n, codebook.shape[0], d, float(commitment_weight), g_x.data_ptr())
     return g_x
 
 
-def vq_gather(tokens: torch.Tensor, codebook: torch.Tensor, channels_first: bool = False) -> torch.Tensor:
-    """tokens (b, t) int64 -> (b, t, d), or (b, d, t) when channels_first (models/maskgit.py:465-470)."""
+def vq_gather(tokens: torch.Tensor, codebook: torch.Tensor, channels_first: bool = False, *, strict: bool = True
+              ) -> torch.Tensor:
+    """tokens (b, t) int64 -> (b, t, d), or (b, d, t) when channels_first (models/maskgit.py:465-470).
+
+    An id outside [0, k) — e.g. a mask token (id == k) left by an incomplete MaskGIT pass — is an error, as it is for the
+    reference's F.embedding: the kernel writes NaN for that token and counts it; strict=True (default) reads the count
+    (one 4-byte device-to-host read) and raises IndexError, strict=False leaves the NaNs to speak for themselves."""
     _need(tokens, "tokens", torch.int64)
     _need(codebook, "codebook")
+    _same_device(tokens, codebook)
     if tokens.dim() != 2:
         raise ValueError("tokens must be (b, t)")
     b, t = tokens.shape
     k, d = codebook.shape
     out = torch.empty((b, d, t) if channels_first else (b, t, d), dtype=torch.float32, device=tokens.device)
-    rc = _lib.load().tvq_gather(tokens.data_ptr(), codebook.data_ptr(), b, t, k, d, 1 if channels_first else 0,
-                                out.data_ptr(), _stream())
-    _lib.check(rc, "tvq_gather")
+    bad = torch.zeros(1, dtype=torch.int32, device=tokens.device) if strict else None
+    _launch("tvq_gather_checked", tokens, tokens.data_ptr(), codebook.data_ptr(), b, t, k, d, 1 if channels_first else 0,
+            out.data_ptr(), bad.data_ptr() if strict else None)
+    if strict and int(bad.item()) != 0:
+        raise IndexError(f"vq_gather: {int(bad.item())} token id(s) outside [0, {k}) (a leaked mask token?)")
     return out
 
 
@@ -212,8 +258,7 @@ def vq_neg_dist(x: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
     n, d = x.shape
     k = codebook.shape[0]
     dist = torch.empty((n, k), dtype=torch.float32, device=x.device)
-    rc = _lib.load().tvq_neg_dist(x.data_ptr(), codebook.data_ptr(), n, k, d, dist.data_ptr(), _stream())
-    _lib.check(rc, "tvq_neg_dist")
+    _launch("tvq_neg_dist", x, x.data_ptr(), codebook.data_ptr(), n, k, d, dist.data_ptr())
     return dist
 
 
@@ -221,9 +266,8 @@ def vq_reseed(x: torch.Tensor, rows: torch.Tensor, cluster_size: torch.Tensor, t
               embed: torch.Tensor) -> None:
     _need(x, "x"); _need(rows, "rows", torch.int64); _need(cluster_size, "cluster_size"); _need(embed, "embed")
     n, d = x.shape
-    rc = _lib.load().tvq_reseed(x.data_ptr(), rows.data_ptr(), cluster_size.data_ptr(), float(threshold),
-                                embed.data_ptr(), n, embed.shape[0], d, _stream())
-    _lib.check(rc, "tvq_reseed")
+    _launch("tvq_reseed", x, x.data_ptr(), rows.data_ptr(), cluster_size.data_ptr(), float(threshold),
+                                embed.data_ptr(), n, embed.shape[0], d)
 
 
 class VQTrainStep(torch.autograd.Function):
@@ -282,7 +326,7 @@ def transpose12(x: torch.Tensor) -> torch.Tensor:
     _need(x, "x")
     b, r, s = x.shape
     out = torch.empty(b, s, r, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().tvq_transpose(x.data_ptr(), b, r, s, out.data_ptr(), _stream()), "tvq_transpose")
+    _launch("tvq_transpose", x, x.data_ptr(), b, r, s, out.data_ptr())
     return out
 
 
@@ -296,10 +340,8 @@ def vq_forward_qcf(x: torch.Tensor, codebook: torch.Tensor, ws: Workspace, hw: i
     q = torch.empty(n // hw, d, hw, dtype=torch.float32, device=x.device)
     scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32, device=x.device)
     f = (_lib.F_TRAIN if train else 0) | _lib.F_WRITE_Q
-    rc = _lib.load().tvq_forward_qcf(x.data_ptr(), codebook.data_ptr(), n, k, d, f, float(commitment_weight), idx.data_ptr(),
-                                     q.data_ptr(), ws.stats.data_ptr(), scalars.data_ptr(), ws.buf.data_ptr(), ws.nbytes, int(hw),
-                                     _stream())
-    _lib.check(rc, "tvq_forward_qcf")
+    _launch("tvq_forward_qcf", x, x.data_ptr(), codebook.data_ptr(), n, k, d, f, float(commitment_weight), idx.data_ptr(),
+                                     q.data_ptr(), ws.stats.data_ptr(), scalars.data_ptr(), ws.buf.data_ptr(), ws.nbytes, int(hw))
     return idx, q, scalars
 
 
@@ -313,10 +355,9 @@ def vq_forward_cf(z: torch.Tensor, codebook: torch.Tensor, ws: Workspace, *, tra
     q = torch.empty(b, d, hw, dtype=torch.float32, device=z.device) if write_q else None
     scalars = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32, device=z.device)
     f = (_lib.F_TRAIN if train else 0) | (_lib.F_WRITE_Q if write_q else 0)
-    rc = _lib.load().tvq_forward_cf(z.data_ptr(), codebook.data_ptr(), b, hw, k, d, f, float(commitment_weight), idx.data_ptr(),
+    _launch("tvq_forward_cf", z, z.data_ptr(), codebook.data_ptr(), b, hw, k, d, f, float(commitment_weight), idx.data_ptr(),
                                     q.data_ptr() if q is not None else None, ws.stats.data_ptr(), scalars.data_ptr(),
-                                    ws.buf.data_ptr(), ws.nbytes, _stream())
-    _lib.check(rc, "tvq_forward_cf")
+                                    ws.buf.data_ptr(), ws.nbytes)
     return idx, q, scalars
 
 
@@ -354,11 +395,10 @@ class VQTrainStepCF(torch.autograd.Function):
         outs = (float(commitment_weight), float(cb.decay), float(cb.eps), idx.data_ptr(), q.data_ptr(), scalars.data_ptr(),
                 commit.data_ptr(), weighted.data_ptr(), ws.buf.data_ptr(), ws.nbytes)
         if VQTrainStepCF.IN_PLACE:
-            rc = _lib.load().tvq_train_step_cf(z.data_ptr(), *head, b, int(hw), k, d, *outs, *tail, _stream())
+            _launch("tvq_train_step_cf", z, z.data_ptr(), *head, b, int(hw), k, d, *outs, *tail)
         else:
             xr = transpose12(z)                           # [b, hw, d]: dropped right after the launch
-            rc = _lib.load().tvq_train_step_qcf(xr.data_ptr(), *head, n, k, d, *outs, *tail, int(hw), _stream())
-        _lib.check(rc, "tvq_train_step_cf")
+            _launch("tvq_train_step_qcf", z, xr.data_ptr(), *head, n, k, d, *outs, *tail, int(hw))
         ctx.save_for_backward(x, idx, prev)
         ctx.meta = (b, hw, float(commitment_weight))
         ctx.mark_non_differentiable(idx, scalars)
@@ -376,7 +416,6 @@ class VQTrainStepCF(torch.autograd.Function):
         g_weighted = g_weighted.contiguous() if g_weighted is not None else None
         g_z = torch.empty(b, d, hw, dtype=torch.float32, device=x.device)
         ptr = lambda t: t.data_ptr() if t is not None else None
-        rc = _lib.load().tvq_backward_cfx(ptr(g_q), ptr(g_commit), ptr(g_weighted), x.data_ptr(), idx.data_ptr(), prev.data_ptr(),
-                                          b, hw, prev.shape[0], d, w, g_z.data_ptr(), _stream())
-        _lib.check(rc, "tvq_backward_cfx")
+        _launch("tvq_backward_cfx", x, ptr(g_q), ptr(g_commit), ptr(g_weighted), x.data_ptr(), idx.data_ptr(), prev.data_ptr(),
+                                          b, hw, prev.shape[0], d, w, g_z.data_ptr())
         return g_z, None, None

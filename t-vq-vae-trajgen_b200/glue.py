@@ -24,7 +24,7 @@ class _Transpose(torch.autograd.Function):
     def forward(ctx, x):
         b, r, s = x.shape
         out = torch.empty(b, s, r, dtype=torch.float32, device=x.device)
-        TF._lib.check(TF._lib.load().tvq_transpose(x.data_ptr(), b, r, s, out.data_ptr(), TF._stream()), "tvq_transpose")
+        TF._launch("tvq_transpose", x, x.data_ptr(), b, r, s, out.data_ptr())
         return out
 
     @staticmethod
@@ -46,6 +46,9 @@ def quantize(z, vq_model, transpose_channel_length_axes: bool = False, svq_temp:
     z_q comes back contiguous in the input's layout."""
     input_dim = z.dim() - 2
     fused = getattr(vq_model, "_channels_first_ok", None)
+    cb = getattr(vq_model, "_codebook", None)
+    if fused is not None and vq_model.training and cb._ddp_active() and cb._px is None and z.is_cuda:
+        cb.setup_data_parallel(z.device)        # collective, once: every rank's first data-parallel training call
     if fused is not None and (input_dim == 2 or (input_dim == 1 and transpose_channel_length_axes)) and fused(z, svq_temp):
         # the module takes 'b c (h w)' directly: one transpose in, z_q written channels-first, one-kernel backward
         return vq_model.forward_channels_first(z)
@@ -66,18 +69,19 @@ def quantize(z, vq_model, transpose_channel_length_axes: bool = False, svq_temp:
 
 
 @torch.no_grad()
-def decode_tokens(s: torch.Tensor, vq_model, h: int, w: int) -> torch.Tensor:
+def decode_tokens(s: torch.Tensor, vq_model, h: int, w: int, *, strict: bool = True) -> torch.Tensor:
     """Token ids (b, n) -> decoder input (b, c, h, w): gather + project_out + 'b n c -> b c h w'.
 
     Without a projection the gather kernel writes the decoder layout directly (one pass instead
-    of the reference's gather + two rearranges).
+    of the reference's gather + two rearranges).  Ids outside [0, K) raise IndexError (strict, one 4-byte read-back) or
+    come out as NaN (strict=False: no synchronisation), as F.embedding would refuse them — never a neighbouring code.
     """
     embed = vq_model._codebook._embed_data()
     s = s.contiguous()
     if isinstance(vq_model.project_out, torch.nn.Identity):
-        zq = TF.vq_gather(s, embed, channels_first=True)             # (b, c, n)
+        zq = TF.vq_gather(s, embed, channels_first=True, strict=strict)             # (b, c, n)
     else:
-        zq = vq_model.project_out(TF.vq_gather(s, embed)).transpose(1, 2)
+        zq = vq_model.project_out(TF.vq_gather(s, embed, strict=strict)).transpose(1, 2)
     b, c, n = zq.shape
     return zq.reshape(b, c, h, w)
 
@@ -106,10 +110,7 @@ def lf_hf_frontend(x: torch.Tensor, n_fft: int, *, want=("xf", "enc_in_l", "enc_
         shape = (b, c, l) if name in ("x_l", "x_h") else (b, 2 * c, k, t)
         out[name] = torch.empty(shape, dtype=torch.float32, device=x.device)
     ptr = lambda name: out[name].data_ptr() if name in out else None
-    lib = TF._lib.load()
-    rc = lib.tvq_frontend(x.data_ptr(), b, c, l, n_fft, ptr("xf"), ptr("enc_in_l"), ptr("enc_in_h"), ptr("x_l"), ptr("x_h"),
-                          TF._stream())
-    TF._lib.check(rc, "tvq_frontend")
+    TF._launch("tvq_frontend", x, x.data_ptr(), b, c, l, n_fft, ptr("xf"), ptr("enc_in_l"), ptr("enc_in_h"), ptr("x_l"), ptr("x_h"))
     return out
 
 
@@ -131,8 +132,7 @@ class _BandISTFT(torch.autograd.Function):
         b, c2, k, t = u.shape
         c = c2 // 2
         y = torch.empty(b, c, length, dtype=torch.float32, device=u.device)
-        rc = TF._lib.load().tvq_band_istft(u.data_ptr(), b, c, length, n_fft, band, y.data_ptr(), TF._stream())
-        TF._lib.check(rc, "tvq_band_istft")
+        TF._launch("tvq_band_istft", u, u.data_ptr(), b, c, length, n_fft, band, y.data_ptr())
         ctx.meta = (b, c, k, t, n_fft, band, length)
         return y
 
@@ -141,8 +141,7 @@ class _BandISTFT(torch.autograd.Function):
         b, c, k, t, n_fft, band, length = ctx.meta
         g_y = g_y.contiguous()
         g_u = torch.empty(b, 2 * c, k, t, dtype=torch.float32, device=g_y.device)
-        rc = TF._lib.load().tvq_band_istft_backward(g_y.data_ptr(), b, c, length, n_fft, band, g_u.data_ptr(), TF._stream())
-        TF._lib.check(rc, "tvq_band_istft_backward")
+        TF._launch("tvq_band_istft_backward", g_y, g_y.data_ptr(), b, c, length, n_fft, band, g_u.data_ptr())
         return g_u, None, None, None
 
 
@@ -192,9 +191,8 @@ def maskgit_step(logits: torch.Tensor, s: torch.Tensor, mask_token_id: int, mask
     s_new = torch.empty_like(s)
     sampled = torch.empty_like(s) if return_details else None
     masking = torch.empty(b, n, dtype=torch.uint8, device=s.device) if return_details else None
-    rc = TF._lib.load().tvq_maskgit_step(logits.data_ptr(), s.data_ptr(), q.data_ptr(), u.data_ptr(), b, n, k, int(mask_token_id),
+    TF._launch("tvq_maskgit_step", logits, logits.data_ptr(), s.data_ptr(), q.data_ptr(), u.data_ptr(), b, n, k, int(mask_token_id),
                                          int(mask_len), float(temperature), s_new.data_ptr(),
                                          sampled.data_ptr() if return_details else None,
-                                         masking.data_ptr() if return_details else None, TF._stream())
-    TF._lib.check(rc, "tvq_maskgit_step")
+                                         masking.data_ptr() if return_details else None)
     return (s_new, sampled, masking.bool()) if return_details else s_new

@@ -34,13 +34,23 @@ def _default(val, d):
 
 
 def sample_vectors(samples: torch.Tensor, num: int) -> torch.Tensor:
-    """Rows for k-means seeding / dead-code replacement; same RNG calls as vq.py:67-75."""
+    """Row indices for k-means seeding / dead-code replacement; same RNG calls as vq.py:67-75."""
     n, device = samples.shape[0], samples.device
     if n >= num:
         indices = torch.randperm(n, device=device)[:num]
     else:
         indices = torch.randint(0, n, (num,), device=device)
     return indices
+
+
+def sample_rows(samples: torch.Tensor, num: int, ddp: bool) -> torch.Tensor:
+    """`num` rows of `samples` (vq.py:67-75).  Data-parallel: rank 0's draw FROM RANK 0's BATCH is broadcast, so the
+    replicas re-seed / initialise with identical vectors — the reference draws rank-locally and its replicas would
+    diverge (SURVEY section 8 e, caveats).  Every rank consumes its RNG exactly as the reference does."""
+    rows = samples[sample_vectors(samples, num)].contiguous()
+    if ddp:
+        distributed.broadcast(rows, src=0)
+    return rows
 
 
 def orthogonal_loss_fn(t: torch.Tensor) -> torch.Tensor:
@@ -104,21 +114,53 @@ class EuclideanCodebook(nn.Module):
         if self._ddp_active():
             distributed.all_reduce(stats)
 
-    def _peer_exchange(self, device: torch.device):
-        """Exchange buffers of the fused NVLink all-reduce + EMA kernel, or None (then: all_reduce + EMA kernel).
-        Set up once per codebook, on the first data-parallel training step (a collective: every rank gets here)."""
-        if self._px is False:
-            return None
-        if self._px is None or not self._px.matches(self.codebook_size, self.dim, device):
+    def setup_data_parallel(self, device: torch.device):
+        """COLLECTIVE: set up the exchange buffers of the fused NVLink all-reduce + EMA kernels, and agree across the ranks
+        on whether they are used.  Every rank of the process group must call it at the same point (the module does, on its
+        first data-parallel training step); the outcome is the same on every rank — a rank where symmetric memory is not
+        available, or that sets TVQ_NO_PEER_EXCHANGE, takes ALL ranks to the all_reduce + EMA-kernel path, so no rank ever
+        spins in the peer kernel while another sits in NCCL.  Returns the PeerExchange or None."""
+        if self._px is not None and (self._px is False or self._px.matches(self.codebook_size, self.dim, device)):
+            return self._px or None
+        def agreed(flag: bool) -> bool:                                      # MIN over the ranks; every rank calls it
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+            distributed.all_reduce(t, op=distributed.ReduceOp.MIN)
+            return int(t.item()) == 1
+
+        px, why = None, ""
+        # (1) the local preconditions, agreed on BEFORE anyone enters the rendezvous (itself a collective)
+        if distributed.get_backend() != "nccl":
+            why = "peer exchange needs CUDA peers (nccl process group)"
+        elif os.environ.get("TVQ_NO_PEER_EXCHANGE"):
+            why = "TVQ_NO_PEER_EXCHANGE is set"
+        elif TF.stats_len(self.codebook_size, self.dim) > (1 << 16):
+            why = "statistics too large for the one-shot exchange"
+        go = agreed(not why) if distributed.get_backend() == "nccl" else False
+        # (2) allocation + rendezvous, then agree on the outcome
+        if go:
             try:
-                if distributed.get_backend() != "nccl" or os.environ.get("TVQ_NO_PEER_EXCHANGE"):
-                    raise RuntimeError("peer exchange needs CUDA peers (nccl process group)")
-                self._px = TF.PeerExchange(self.codebook_size, self.dim, device)
-            except Exception as exc:          # say so once; the NCCL all-reduce path computes the same update
-                warnings.warn(f"tvq_b200: NVLink peer exchange unavailable ({exc}); using all_reduce + EMA kernel")
-                self._px = False
-                return None
-        return self._px
+                px = TF.PeerExchange(self.codebook_size, self.dim, device)
+            except Exception as exc:
+                why = str(exc)
+            if not agreed(px is not None):
+                px = None
+        if px is None and distributed.get_rank() == 0:
+            warnings.warn("tvq_b200: NVLink peer exchange not used" + (f" ({why})" if why else " (unavailable on a peer)")
+                          + "; all ranks use all_reduce + EMA kernel")
+        self._px = px if px is not None else False
+        return px
+
+    def _peer_exchange(self, device: torch.device):
+        """The exchange buffers, or None (then: all_reduce + EMA kernel).  The first call is the collective setup."""
+        if self._px is None or (self._px is not False and not self._px.matches(self.codebook_size, self.dim, device)):
+            return self.setup_data_parallel(device)
+        return self._px or None
+
+    def check_peer_errors(self) -> None:
+        """Raise if a data-parallel kernel of this codebook ever gave up waiting for a peer (include/tvq.h:
+        tvq_set_peer_timeout).  Reads one word from the device (a synchronisation): call it off the hot path."""
+        if self._px:
+            self._px.check()
 
     def _sync_and_update(self, ws, prev) -> None:
         """EMA update from this call's statistics (ws.stats); data-parallel: summed over the ranks first."""
@@ -150,19 +192,37 @@ class EuclideanCodebook(nn.Module):
 
     # -- optional branches that consume torch's RNG ---------------------------------------------
     @torch.no_grad()
-    def init_embed_(self, data: torch.Tensor) -> None:
-        """k-means initialisation (vq.py:171-179, :78-106): Lloyd iterations on the kernels."""
+    def init_embed_(self, data: torch.Tensor, seed_rows: Optional[torch.Tensor] = None) -> None:
+        """k-means initialisation (vq.py:171-179, :78-106): Lloyd iterations on the kernels (assign + per-code sums in one
+        launch per iteration; the reference's (N, K, D) broadcast difference is never built).
+
+        seed_rows (k int64 row indices into data): the initial means, instead of a draw from torch's generator — so a
+        caller (or a parity test: tests/golden/kmeans_init_train.npz) can fix them.
+        Data-parallel (sync_codebook on an initialised group): rank 0's seed vectors are broadcast and the per-iteration
+        statistics are summed over the ranks — one global k-means, identical replicas (the reference would run R
+        independent k-means on the local batches and diverge).
+        Deviation: codes are assigned by the canonical three-term rule of DESIGN section 4, the reference's k-means uses
+        the direct difference sum((x - m)^2) (vq.py:87-90); they can differ only on a row whose two nearest means are
+        within a few ulps — the parity test counts such rows."""
         if self._initted_host is None:
             self._initted_host = bool(self.initted.item())     # one sync, then cached
         if self._initted_host:
             return
         k = self.codebook_size
+        ddp = self._ddp_active()
         ws = self._workspace(data.device)
-        means = data[sample_vectors(data, k)].contiguous()
+        if seed_rows is not None:
+            means = data[seed_rows.to(data.device)].contiguous()
+            if ddp:
+                distributed.broadcast(means, src=0)
+        else:
+            means = sample_rows(data, k, ddp)
         off = TF.stats_offset(k)
         bins = None
         for _ in range(self.kmeans_iters):
             TF.vq_forward_raw(data, means, ws, train=True, write_q=False)      # counts + per-code sums
+            if ddp:
+                distributed.all_reduce(ws.stats)
             bins = ws.stats[:k].clone()
             sums = ws.stats[off:off + k * self.dim].view(k, self.dim)
             empty = bins == 0
@@ -176,15 +236,21 @@ class EuclideanCodebook(nn.Module):
 
     @torch.no_grad()
     def expire_codes_(self, batch_samples: torch.Tensor) -> None:
-        """Dead-code re-seed (vq.py:187-195); only `embed` is replaced, as in the reference."""
+        """Dead-code re-seed (vq.py:187-195); only `embed` is replaced, as in the reference.  Data-parallel: cluster_size
+        is identical on every rank, so all ranks take the branch together and re-seed with rank 0's rows."""
         if self.threshold_ema_dead_code == 0:
             return
         expired = self.cluster_size < self.threshold_ema_dead_code
         if not torch.any(expired):                       # same sync (and same RNG use) as the reference
             return
-        flat = batch_samples.reshape(-1, batch_samples.shape[-1])
-        rows = sample_vectors(flat, self.codebook_size)
-        TF.vq_reseed(flat.contiguous(), rows, self.cluster_size, self.threshold_ema_dead_code, self._embed_data())
+        flat = batch_samples.reshape(-1, batch_samples.shape[-1]).contiguous()
+        k = self.codebook_size
+        if self._ddp_active():
+            rows = sample_rows(flat, k, True)            # [k, d] vectors, rank 0's
+            TF.vq_reseed(rows, torch.arange(k, device=rows.device), self.cluster_size, self.threshold_ema_dead_code,
+                         self._embed_data())
+            return
+        TF.vq_reseed(flat, sample_vectors(flat, k), self.cluster_size, self.threshold_ema_dead_code, self._embed_data())
 
     # -- the step -----------------------------------------------------------------------------
     def _assign(self, flat: torch.Tensor, svq_temp):
@@ -349,7 +415,11 @@ class VectorQuantize(nn.Module):
                 and cb.threshold_ema_dead_code == 0 and cb._initted_host is True and cb.dim <= 128
                 and cb.codebook_size <= (32 if self.training else 64) and z.shape[1] == cb.dim
                 and z.numel() > 0 and z.shape[0] * z[0, 0].numel() < 2 ** 31 - 64
-                and (not (self.training and cb._ddp_active()) or cb._peer_exchange(z.device) is not None))
+                # tvq_backward_cfx keeps the codebook (k x (d+1)) and one index row (hw) in <= 100 KB of shared memory
+                and (not self.training or (cb.codebook_size * (cb.dim + 1) + z[0, 0].numel()) * 4 <= 100 * 1024)
+                # data-parallel: only with the peer exchange already agreed on (setup_data_parallel: a collective the
+                # caller runs first — quantize() does — never a side effect of this predicate)
+                and (not (self.training and cb._ddp_active()) or bool(cb._px)))
 
     def forward_channels_first(self, z: torch.Tensor):
         """z (b, c, h, w) or (b, c, l) -> (z_q in the same layout, embed_ind (b, h*w), vq_loss, perplexity): what

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(tvq):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/tvq.h but not exported"
     assert set(declared) == set(tvq._lib.EXPORTS)
-    assert lib.tvq_abi_version() == 1
+    assert lib.tvq_abi_version() == 2
     assert b"unsupported" in lib.tvq_error_string(-1)
     assert lib.tvq_workspace_bytes(0, 32, 128) >= 64 + 32 * 4
 
