@@ -214,6 +214,13 @@ TVQ_API int tvq_frontend(const float *x, int64_t b, int c, int l, int n_fft, flo
  * with pad_func = identity (band 0), zero_pad_high_freq (band 1: keep bin 0) or zero_pad_low_freq (band 2: keep
  * bins 1..), in ONE kernel; the backward (adjoint) writes g_u, zero in the bands pad_func removed.            */
 TVQ_API int tvq_band_istft(const float *u, int64_t b, int c, int l, int n_fft, int band, float *y, void *stream);
+/* The general form: u [b, 2c, n_fft/2+1, t] with ANY number of frames t >= 2 (the shipped decoders emit t = 384 (LF) / 400
+ * (HF) frames for l = 200): the ISTFT yields hop * (t - 1) samples, F.interpolate(mode="linear", align_corners=False) maps
+ * them onto l.  tvq_band_istft(_backward) is this call with t = l / hop + 1.                                    */
+TVQ_API int tvq_band_istft_frames(const float *u, int64_t b, int c, int t, int l, int n_fft, int band, float *y,
+                          void *stream);
+TVQ_API int tvq_band_istft_frames_backward(const float *g_y, int64_t b, int c, int t, int l, int n_fft, int band,
+                                   float *g_u, void *stream);
 TVQ_API int tvq_band_istft_backward(const float *g_y, int64_t b, int c, int l, int n_fft, int band, float *g_u,
                             void *stream);
 

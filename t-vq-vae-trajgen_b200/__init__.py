@@ -12,7 +12,9 @@ from .functional import (PeerExchange, VQTrainStep, Workspace, stats_len, stats_
 from .glue import (band_timefreq_to_time, decode_tokens, lf_hf_frontend, maskgit_step, quantize, time_to_timefreq,
                    timefreq_to_time)
 from .vq import EuclideanCodebook, VectorQuantize
+from . import stage1
+from .stage1 import Stage1, Stage1Trainer
 
-__all__ = ["VectorQuantize", "EuclideanCodebook", "quantize", "decode_tokens", "lf_hf_frontend", "time_to_timefreq", "timefreq_to_time", "band_timefreq_to_time", "maskgit_step", "vq_forward_raw", "vq_ema_update", "vq_ema_update_dp", "PeerExchange",
+__all__ = ["Stage1", "Stage1Trainer", "stage1", "VectorQuantize", "EuclideanCodebook", "quantize", "decode_tokens", "lf_hf_frontend", "time_to_timefreq", "timefreq_to_time", "band_timefreq_to_time", "maskgit_step", "vq_forward_raw", "vq_ema_update", "vq_ema_update_dp", "PeerExchange",
            "vq_train_step_raw", "vq_backward", "vq_gather", "vq_neg_dist", "vq_reseed", "Workspace", "VQTrainStep", "stats_len",
            "stats_offset", "_lib"]

@@ -743,13 +743,13 @@ int tvq_frontend(const float* x, int64_t b, int c, int l, int n_fft, float* xf, 
 namespace {
 template <bool BACKWARD>
 int launch_band_istft(const BandIstftParams& p, int64_t b, int c, cudaStream_t stream) {
-    if (b < 0 || c < 1 || p.n_fft < 4 || p.n_fft > 64 || (p.n_fft & 3) || p.l <= p.n_fft / 2 || p.band < 0 || p.band > 2)
+    if (b < 0 || c < 1 || p.n_fft < 4 || p.n_fft > 64 || (p.n_fft & 3) || p.l < 1 || p.t < 2 || p.band < 0 || p.band > 2)
         return TVQ_ERR_UNSUPPORTED;
     if (b == 0) return TVQ_OK;
     DeviceInfo* di = nullptr;
     int rc = device_info(&di);
     if (rc != TVQ_OK) return rc;
-    const size_t smem = band_istft_smem_bytes(p.l, p.n_fft);
+    const size_t smem = band_istft_smem_bytes(p.t, p.n_fft);
     if (smem > (size_t)di->max_smem_optin) return TVQ_ERR_UNSUPPORTED;
     static PerDeviceInt configured(48 * 1024);
     if ((rc = ensure_dynamic_smem(band_istft_kernel<BACKWARD>, configured, di->index, smem)) != TVQ_OK) return rc;
@@ -762,18 +762,28 @@ int launch_band_istft(const BandIstftParams& p, int64_t b, int c, cudaStream_t s
 
 extern "C" {
 
-int tvq_band_istft(const float* u, int64_t b, int c, int l, int n_fft, int band, float* y, void* stream_) {
+int tvq_band_istft_frames(const float* u, int64_t b, int c, int t, int l, int n_fft, int band, float* y, void* stream_) {
     if (b > 0 && (!u || !y)) return TVQ_ERR_BAD_ARG;
     BandIstftParams p;
-    p.u = u; p.g_y = nullptr; p.y = y; p.g_u = nullptr; p.rows = b * c; p.l = l; p.n_fft = n_fft; p.band = band;
+    p.u = u; p.g_y = nullptr; p.y = y; p.g_u = nullptr; p.rows = b * c; p.l = l; p.n_fft = n_fft; p.band = band; p.t = t;
     return launch_band_istft<false>(p, b, c, (cudaStream_t)stream_);
 }
 
-int tvq_band_istft_backward(const float* g_y, int64_t b, int c, int l, int n_fft, int band, float* g_u, void* stream_) {
+int tvq_band_istft_frames_backward(const float* g_y, int64_t b, int c, int t, int l, int n_fft, int band, float* g_u, void* stream_) {
     if (b > 0 && (!g_y || !g_u)) return TVQ_ERR_BAD_ARG;
     BandIstftParams p;
-    p.u = nullptr; p.g_y = g_y; p.y = nullptr; p.g_u = g_u; p.rows = b * c; p.l = l; p.n_fft = n_fft; p.band = band;
+    p.u = nullptr; p.g_y = g_y; p.y = nullptr; p.g_u = g_u; p.rows = b * c; p.l = l; p.n_fft = n_fft; p.band = band; p.t = t;
     return launch_band_istft<true>(p, b, c, (cudaStream_t)stream_);
+}
+
+int tvq_band_istft(const float* u, int64_t b, int c, int l, int n_fft, int band, float* y, void* stream_) {
+    if (n_fft < 4 || l <= n_fft / 2) return TVQ_ERR_UNSUPPORTED;
+    return tvq_band_istft_frames(u, b, c, l / (n_fft / 4) + 1, l, n_fft, band, y, stream_);
+}
+
+int tvq_band_istft_backward(const float* g_y, int64_t b, int c, int l, int n_fft, int band, float* g_u, void* stream_) {
+    if (n_fft < 4 || l <= n_fft / 2) return TVQ_ERR_UNSUPPORTED;
+    return tvq_band_istft_frames_backward(g_y, b, c, l / (n_fft / 4) + 1, l, n_fft, band, g_u, stream_);
 }
 
 int tvq_maskgit_step(const float* logits, const int64_t* s, const float* q, const float* u, int64_t b, int n, int k,

@@ -180,6 +180,9 @@ inline size_t frontend_smem_bytes(int l, int n_fft) {
 // 0, zero_pad_low_freq keeps bins 1..).  Forward and backward (the op is linear, the backward is its adjoint: an
 // STFT-like analysis of g / envelope) as one kernel each; the zeroed bands never leave the kernel, their gradient is
 // written as zeros.  band: 0 = all bins (plain timefreq_to_time), 1 = LF (bin 0), 2 = HF (bins >= 1).
+// T (frames of u) and L (output length) are independent: the ISTFT yields hop (T - 1) samples, the linear interpolation
+// (align_corners = False, no anti-aliasing, ATen's one-rounding source coordinate) maps them onto L — up- or down-sampling
+// (the shipped decoders emit T = 384 / 400 frames for L = 200).
 namespace tvq {
 
 struct BandIstftParams {
@@ -189,6 +192,7 @@ struct BandIstftParams {
     float* g_u;            // backward: [b, 2c, K, T] out
     int64_t rows;          // b * c
     int l, n_fft, band;
+    int t;                 // frames of u (the decoder's own width: 384 / 400 at configs/config.yaml, NOT l / hop + 1)
 };
 
 // window envelope sum_t w^2[j + N/2 - t hop] over the frames that exist (torch.istft's normalisation)
@@ -210,7 +214,7 @@ template <bool BACKWARD>
 __global__ void __launch_bounds__(128) band_istft_kernel(const BandIstftParams p) {
     extern __shared__ float fsm[];
     const int N = p.n_fft, half = N >> 1, hop = N >> 2, K = half + 1;
-    const int L = p.l, T = 1 + L / hop, Ly = hop * (T - 1);
+    const int L = p.l, T = p.t, Ly = hop * (T - 1);   // torch.istft(center=True) returns hop * (T - 1) samples
     float* xr = fsm;                        // [K][T]
     float* xi = xr + K * T;                 // [K][T]
     float* ys = xi + K * T;                 // [Ly]   signal before the interpolation (forward) / its gradient / envelope (backward)
@@ -316,8 +320,8 @@ __global__ void __launch_bounds__(128) band_istft_kernel(const BandIstftParams p
     }
 }
 
-inline size_t band_istft_smem_bytes(int l, int n_fft) {
-    const int half = n_fft / 2, hop = n_fft / 4, K = half + 1, T = 1 + l / hop, Ly = hop * (T - 1);
+inline size_t band_istft_smem_bytes(int t, int n_fft) {
+    const int half = n_fft / 2, hop = n_fft / 4, K = half + 1, T = t, Ly = hop * (T - 1);
     return (size_t)(2 * K * T + ((Ly + 3) & ~3) + n_fft + 2 * K * n_fft) * sizeof(float);
 }
 

@@ -132,7 +132,7 @@ class _BandISTFT(torch.autograd.Function):
         b, c2, k, t = u.shape
         c = c2 // 2
         y = torch.empty(b, c, length, dtype=torch.float32, device=u.device)
-        TF._launch("tvq_band_istft", u, u.data_ptr(), b, c, length, n_fft, band, y.data_ptr())
+        TF._launch("tvq_band_istft_frames", u, u.data_ptr(), b, c, t, length, n_fft, band, y.data_ptr())
         ctx.meta = (b, c, k, t, n_fft, band, length)
         return y
 
@@ -141,7 +141,7 @@ class _BandISTFT(torch.autograd.Function):
         b, c, k, t, n_fft, band, length = ctx.meta
         g_y = g_y.contiguous()
         g_u = torch.empty(b, 2 * c, k, t, dtype=torch.float32, device=g_y.device)
-        TF._launch("tvq_band_istft_backward", g_y, g_y.data_ptr(), b, c, length, n_fft, band, g_u.data_ptr())
+        TF._launch("tvq_band_istft_frames_backward", g_y, g_y.data_ptr(), b, c, t, length, n_fft, band, g_u.data_ptr())
         return g_u, None, None, None
 
 
@@ -153,14 +153,15 @@ def band_timefreq_to_time(u: torch.Tensor, n_fft: int, C: int, band="all", lengt
 
     band "lf": zero_pad_high_freq(u) first (keep bin 0); "hf": zero_pad_low_freq(u) (keep bins 1..); "all": none.
     Equals F.interpolate(timefreq_to_time(pad_func(u), n_fft, C), length, mode="linear") of the reference
-    (models/vq_vae.py:259-262); length defaults to the ISTFT's own length, hop * (T - 1)."""
+    (models/vq_vae.py:259-262) for ANY frame count T (the shipped decoders emit 384 / 400 frames for length 200);
+    length defaults to the ISTFT's own length, hop * (T - 1)."""
     if u.dim() != 4 or u.shape[1] != 2 * C or u.shape[2] != n_fft // 2 + 1:
         raise ValueError(f"u must be (B, {2 * C}, {n_fft // 2 + 1}, T), got {tuple(u.shape)}")
     hop = n_fft // 4
     ly = hop * (u.shape[3] - 1)
     length = ly if length is None else int(length)
-    if length // hop + 1 != u.shape[3]:
-        raise NotImplementedError("the kernel derives T from the output length: need length // hop + 1 == T")
+    if u.shape[3] < 2 or length < 1:
+        raise ValueError("need at least two frames and a positive output length")
     return _BandISTFT.apply(u.contiguous().float(), n_fft, _BANDS[band], length)
 
 

@@ -71,7 +71,9 @@ def test_full_batch_properties(tvq):
 
 # ------------------------------------------------------------------ decoder side: pad_func + ISTFT + interpolate
 
-ISTFT_CASES = ["istft_cfg1", "istft_nfft8", "istft_interp"]
+# istft_dec_*: the decoders' real output widths (384 / 400 frames -> 200 samples, down-sampling interpolation) and an
+# up-sampling case, from oracle/gen_golden_stage1.py
+ISTFT_CASES = ["istft_cfg1", "istft_nfft8", "istft_interp", "istft_dec_lf", "istft_dec_hf", "istft_dec_up"]
 
 
 @pytest.mark.parametrize("name", ISTFT_CASES)
