@@ -250,7 +250,9 @@ class Stage1Trainer:
         self.flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
         off = 0
         for p in params:                      # every .grad is a view of the flat bucket: one all-reduce, no copies
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            # same sizes AND strides as the parameter (a channels_last weight is a dense permutation), as autograd's
+            # gradient-layout contract and the fused optimizer want
+            p.grad = self.flat_grad[off:off + p.numel()].as_strided(p.size(), p.stride())
             off += p.numel()
         self.lr = torch.tensor(self.base_lr * warmup_cosine_factor(1, self.max_steps, self.warmup_rate, self.base_lr),
                                dtype=torch.float32, device=dev)

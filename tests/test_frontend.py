@@ -101,7 +101,7 @@ def test_band_istft_kernel_matches_reference_golden(tvq, name):
         ry, rg = torch.from_numpy(g["y_" + band]), torch.from_numpy(g["g_u_" + band])
         torch.testing.assert_close(y.detach().cpu(), ry, rtol=0, atol=1e-5 * max(1.0, float(ry.abs().max())), msg=lambda m: f"y {band}: {m}")
         torch.testing.assert_close(u.grad.cpu(), rg, rtol=0, atol=1e-5 * max(1.0, float(rg.abs().max())), msg=lambda m: f"g_u {band}: {m}")
-    if l % (n_fft // 4) == 0:
+    if l % (n_fft // 4) == 0 and g["u"].shape[3] == l // (n_fft // 4) + 1:     # no interpolation: the plain ISTFT
         u = torch.from_numpy(g["u"]).cuda()
         torch.testing.assert_close(tvq.timefreq_to_time(u, n_fft, c).cpu(), torch.from_numpy(g["y_all"]), rtol=0, atol=1e-5 * 4)
 
