@@ -204,6 +204,25 @@ inline size_t ws_bf16_offset(int k, int d) {
     return (o + 255) & ~(size_t)255;
 }
 
+inline size_t ws_e2h_offset(int k, int d) {
+    const size_t o = ws_bf16_offset(k, d) + (size_t)k * (size_t)stream_dp(d) * 2;
+    return (o + 255) & ~(size_t)255;
+}
+
+// |e|^2 / 2 pieces [roundup(k, 256), 16] bf16: one box = 16 elements (32 bytes, the SWIZZLE_32B span) x nt codes
+int make_e2_tensor_map(CUtensorMap* tm, const void* e2h, int k, int nt) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return TVQ_ERR_DEVICE;
+    cuuint64_t gdim[2] = {16u, (cuuint64_t)e2_len(k)};
+    cuuint64_t gstride[1] = {32u};
+    cuuint32_t box[2] = {16u, (cuuint32_t)nt};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(e2h), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? TVQ_OK : TVQ_ERR_BAD_ARG;
+}
+
 int make_cb_tensor_map(CUtensorMap* tm, const void* cbh, int k, int dp, int nt) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return TVQ_ERR_DEVICE;
@@ -218,7 +237,7 @@ int make_cb_tensor_map(CUtensorMap* tm, const void* cbh, int k, int dp, int nt) 
 }
 
 template <int DP, int NT, bool TRAIN, int CG>
-int launch_fwd_stream_impl(FwdParams p, const void* cbh, const DeviceInfo& di, cudaStream_t stream) {
+int launch_fwd_stream_impl(FwdParams p, const void* cbh, const void* e2h, const DeviceInfo& di, cudaStream_t stream) {
     auto kern = fwd_stream_kernel<DP, NT, TRAIN, CG>;
     const StreamPlan fixed = make_stream_plan(DP, NT, 0, CG);
     int stages = (di.max_smem_optin - fixed.total) / ((NT / CG) * 128);
@@ -227,14 +246,15 @@ int launch_fwd_stream_impl(FwdParams p, const void* cbh, const DeviceInfo& di, c
     const StreamPlan pl = make_stream_plan(DP, NT, stages, CG);
     static PerDeviceInt configured_smem(-1);
     if (int rc = ensure_dynamic_smem(kern, configured_smem, di.index, pl.total)) return rc;
-    CUtensorMap tm;
+    CUtensorMap tm, tm2;
     int rc = make_cb_tensor_map(&tm, cbh, p.k, DP, NT / CG);
     if (rc != TVQ_OK) return rc;
+    if ((rc = make_e2_tensor_map(&tm2, e2h, p.k, NT / CG)) != TVQ_OK) return rc;
     p.num_tiles = (int)((p.n + kSM - 1) / kSM);
     const int groups = (p.num_tiles + CG - 1) / CG, units = di.sm_count / CG;
     const int grid = CG * (groups < units ? groups : units);
     if (CG == 1) {
-        kern<<<grid, kSThreads, pl.total, stream>>>(tm, p, stages);
+        kern<<<grid, kSThreads, pl.total, stream>>>(tm, tm2, p, stages);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
@@ -246,7 +266,7 @@ int launch_fwd_stream_impl(FwdParams p, const void* cbh, const DeviceInfo& di, c
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, p, stages);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, tm2, p, stages);
         if (e != cudaSuccess) return (int)e;
     }
     return launch_status();
@@ -265,24 +285,25 @@ inline int stream_cg(const FwdParams& p) {
 }
 
 template <bool TRAIN>
-int dispatch_fwd_stream(const FwdParams& p, const void* cbh, const DeviceInfo& di, cudaStream_t s) {
+int dispatch_fwd_stream(const FwdParams& p, const void* cbh, const void* e2h, const DeviceInfo& di, cudaStream_t s) {
     const int cg = stream_cg(p);
     switch (stream_dp(p.d)) {
-        case 64: return cg == 2 ? launch_fwd_stream_impl<64, 256, TRAIN, 2>(p, cbh, di, s) : launch_fwd_stream_impl<64, 256, TRAIN, 1>(p, cbh, di, s);
-        case 128: return cg == 2 ? launch_fwd_stream_impl<128, 256, TRAIN, 2>(p, cbh, di, s) : launch_fwd_stream_impl<128, 256, TRAIN, 1>(p, cbh, di, s);
-        case 256: return cg == 2 ? launch_fwd_stream_impl<256, 256, TRAIN, 2>(p, cbh, di, s) : launch_fwd_stream_impl<256, 128, TRAIN, 1>(p, cbh, di, s);
+        case 64: return cg == 2 ? launch_fwd_stream_impl<64, 256, TRAIN, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<64, 256, TRAIN, 1>(p, cbh, e2h, di, s);
+        case 128: return cg == 2 ? launch_fwd_stream_impl<128, 256, TRAIN, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<128, 256, TRAIN, 1>(p, cbh, e2h, di, s);
+        case 256: return cg == 2 ? launch_fwd_stream_impl<256, 256, TRAIN, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<256, 128, TRAIN, 1>(p, cbh, e2h, di, s);
     }
     return TVQ_ERR_UNSUPPORTED;
 }
 
 int launch_prep(const float* cb, int k, int d, float* e2, WsHeader* hdr, float* stats, int64_t stats_len, void* cbh, int dp,
-                const DeviceInfo& di, cudaStream_t stream) {
-    int64_t work = stats_len / 4 > (int64_t)k * 32 ? stats_len / 4 : (int64_t)k * 32;
+                void* e2h, const DeviceInfo& di, cudaStream_t stream) {
+    int64_t work = stats_len / 4 > (int64_t)e2_len(k) * 32 ? stats_len / 4 : (int64_t)e2_len(k) * 32;
     if (cbh && (int64_t)k * (dp / 4) > work) work = (int64_t)k * (dp / 4);
     int blocks = (int)((work + 255) / 256);
     if (blocks > 4 * di.sm_count) blocks = 4 * di.sm_count;
     if (blocks < 1) blocks = 1;
-    prep_kernel<<<blocks, 256, 0, stream>>>(cb, k, d, e2, hdr, stats, stats_len, reinterpret_cast<__nv_bfloat16*>(cbh), dp);
+    prep_kernel<<<blocks, 256, 0, stream>>>(cb, k, d, e2, hdr, stats, stats_len, reinterpret_cast<__nv_bfloat16*>(cbh), dp,
+                                            reinterpret_cast<__nv_bfloat16*>(e2h));
     return launch_status();
 }
 
@@ -346,7 +367,8 @@ size_t tvq_workspace_bytes(int64_t n, int k, int d) {
     const size_t kk = k > 0 ? (size_t)k : 0, dd = d > 0 ? (size_t)d : 0;
     // header | |e|^2 table | private statistics scratch of tvq_train_step | bf16 codebook copy (streamed tcgen05 path)
     if (kk == 0 || dd == 0) return sizeof(WsHeader) + 256;
-    return ws_bf16_offset((int)kk, (int)dd) + kk * (size_t)stream_dp((int)dd) * 2 + 256;
+    // ... | bf16 codebook copy | |e|^2 / 2 pieces (both operands of the streamed tcgen05 path)
+    return ws_e2h_offset((int)kk, (int)dd) + e2_len((int)kk) * 32 + 256;
 }
 
 }  // extern "C"
@@ -381,8 +403,9 @@ int forward_impl(const float* x, const float* codebook, int64_t n, int k, int d,
     const bool use_stream = !(flags & (TVQ_F_EXACT | TVQ_F_GIVEN_IDX | TVQ_F_NO_UMMA)) && !resident && n > 0 &&
                             n < (int64_t(1) << 31) - 256;
     void* cbh = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_bf16_offset(k, d) : nullptr;
-    // per-call preparation: |e|^2, zero statistics / loss (+ bf16 codebook copy)
-    if ((rc = launch_prep(codebook, k, d, e2, hdr, stats, stats_len, cbh, stream_dp(d), *di, stream)) != TVQ_OK) return rc;
+    void* e2h = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_e2h_offset(k, d) : nullptr;
+    // per-call preparation: |e|^2, zero statistics / loss (+ the bf16 operands of the streamed path)
+    if ((rc = launch_prep(codebook, k, d, e2, hdr, stats, stats_len, cbh, stream_dp(d), e2h, *di, stream)) != TVQ_OK) return rc;
     if (n == 0) return TVQ_OK;   // nothing to assign; scalars are left to the caller (reference yields NaN)
 
     FwdParams p;
@@ -409,7 +432,7 @@ int forward_impl(const float* x, const float* codebook, int64_t n, int k, int d,
     if (use_stream) {
         p.use_hist = 0;
         p.stats_mode = train ? kStatsLarge : kStatsNone;
-        return train ? dispatch_fwd_stream<true>(p, cbh, *di, stream) : dispatch_fwd_stream<false>(p, cbh, *di, stream);
+        return train ? dispatch_fwd_stream<true>(p, cbh, e2h, *di, stream) : dispatch_fwd_stream<false>(p, cbh, e2h, *di, stream);
     }
     const int dp = pad_dim(d);
     p.use_hist = k <= 2048;
@@ -443,9 +466,10 @@ int train_step_impl(const float* x, float* embed, float* cluster_size, float* em
     if (x_hw > 0 && (!umma || x_hw != q_hw)) return TVQ_ERR_UNSUPPORTED;    // and the channels-first x load
     const bool use_stream = !umma && n > 0 && n < (int64_t(1) << 31) - 256;
     void* cbh = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_bf16_offset(k, d) : nullptr;
+    void* e2h = use_stream ? reinterpret_cast<unsigned char*>(workspace) + ws_e2h_offset(k, d) : nullptr;
     if (!umma) {
         // generic composition: zero + |e|^2 (+ bf16 copy), streamed tcgen05 forward, EMA kernel (three launches)
-        if ((rc = launch_prep(embed, k, d, e2, hdr, scratch, TVQ_STATS_LEN(k, d), cbh, stream_dp(d), *di, stream)) != TVQ_OK) return rc;
+        if ((rc = launch_prep(embed, k, d, e2, hdr, scratch, TVQ_STATS_LEN(k, d), cbh, stream_dp(d), e2h, *di, stream)) != TVQ_OK) return rc;
     }
     FwdParams p;
     p.x = x; p.cb = embed; p.n = n; p.k = k; p.d = d;
@@ -467,7 +491,7 @@ int train_step_impl(const float* x, float* embed, float* cluster_size, float* em
     if (use_stream) {
         p.use_hist = 0;
         p.stats_mode = kStatsLarge;
-        if ((rc = dispatch_fwd_stream<true>(p, cbh, *di, stream)) != TVQ_OK) return rc;
+        if ((rc = dispatch_fwd_stream<true>(p, cbh, e2h, *di, stream)) != TVQ_OK) return rc;
     } else if (n > 0) {
         const int dp = pad_dim(d);
         p.stats_mode = ((int64_t)k * dp <= 8192 && k <= 512) ? kStatsSmall : kStatsLarge;

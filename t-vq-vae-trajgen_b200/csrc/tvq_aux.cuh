@@ -10,20 +10,34 @@ namespace tvq {
 
 // ------------------------------------------------------------------------------------------
 // Per-call preparation: canonical |e_k|^2 (one warp per code), zero the statistics buffer and
-// the loss / diagnostic fields of the workspace header; optionally the bf16 copy of the codebook
-// ([k, dp] row-major, zero padded to dp columns) that the streamed tcgen05 path feeds to TMA.
+// the loss / diagnostic fields of the workspace header; optionally the operands the streamed tcgen05 path feeds to TMA:
+//   cbh  [k, dp] bf16 row-major, zero padded to dp columns: the NEGATED codebook, -e
+//   e2h  [roundup(k, 256), 16] bf16: |e_k|^2 / 2 split into three bf16 pieces (hi, mid, lo: 24 bits, i.e. the fp32 value
+//        exactly) followed by zeros — one extra K step of the distance GEMM against constant rows (1, 1, 1, 0...), so the
+//        accumulator comes out as the half-score |e|^2 / 2 - x.e; rows >= k hold a huge value and can never be nominated
 __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ cb, int k, int d, float* __restrict__ e2,
                                                    WsHeader* hdr, float* __restrict__ stats, int64_t stats_len,
-                                                   __nv_bfloat16* __restrict__ cbh, int dp) {
+                                                   __nv_bfloat16* __restrict__ cbh, int dp, __nv_bfloat16* __restrict__ e2h) {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int c = gwarp; c < k; c += nwarps) {
-        const float* er = cb + (size_t)c * d;
-        double s = canon_dot_global(er, er, d >> 2, lane);
-        if (lane == 0) e2[c] = __double2float_rn(s);
+    const int kpad = (k + 255) & ~255;
+    for (int c = gwarp; c < kpad; c += nwarps) {
+        float e2c = 1e30f;                                               // pad: never the minimum
+        if (c < k) {
+            const float* er = cb + (size_t)c * d;
+            e2c = __double2float_rn(canon_dot_global(er, er, d >> 2, lane));
+        }
+        if (lane == 0) e2[c] = e2c;
+        if (e2h != nullptr && lane < 16) {
+            const float v = 0.5f * e2c;                                  // exact
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const float r1 = v - __bfloat162float(h);                    // exact (Sterbenz-like: h is v rounded to 8 bits)
+            const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+            e2h[(size_t)c * 16 + lane] = lane == 0 ? h : lane == 1 ? m : lane == 2 ? l : __float2bfloat16_rn(0.f);
+        }
     }
-    for (int c = k + gwarp * 32 + lane; c < ((k + 255) & ~255); c += nwarps * 32) e2[c] = 1e30f;   // pad: never the minimum
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
     if (stats != nullptr) {
@@ -39,7 +53,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ cb,
             const int c4 = (int)(f - row * dq);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c4 < nchunk) v = __ldg(reinterpret_cast<const float4*>(cb + (size_t)row * d) + c4);
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(-v.x, -v.y), hi = __floats2bfloat162_rn(-v.z, -v.w);
             uint2 o;
             o.x = *reinterpret_cast<const uint32_t*>(&lo);
             o.y = *reinterpret_cast<const uint32_t*>(&hi);

@@ -69,7 +69,6 @@ constexpr int kSThreads = 384;           // 12 warps: 168 registers per thread (
 constexpr int kSCvtWarps = 2;            // converter warps (64 latents each)
 constexpr int kSScanWarps = 8;           // two per TMEM lane quadrant
 constexpr int kSCand = 12;               // candidate slots per latent and scan half
-constexpr int kSESlots = 8;              // |e|^2 slices in flight
 constexpr int kSBrowRing = 4;            // row-bound buffers (converter runs up to 2 tiles ahead of the scan)
 constexpr int kSMaxStages = 8;
 constexpr int kSOvf = 32;                // spill entries per quadrant and row tile (beyond that: exhaustive scan)
@@ -77,7 +76,7 @@ constexpr int kSScratch = 2 * kSCand + kSOvf;   // merged candidate list of one 
 
 struct StreamPlan {
     int stages, stage_bytes, a_bytes;
-    int a, b, e2s, brow, cs, cc, drop, mfin, ncnt, ovf, scratch, red, misc, bars, tmem, total;
+    int a, b, aone, brow, cs, cc, drop, mfin, ncnt, ovf, scratch, red, misc, bars, tmem, total;
 };
 __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages, int cg = 1) {
     StreamPlan u;
@@ -87,7 +86,7 @@ __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stage
     int o = 0;
     u.a = o;     o += 2 * u.a_bytes;
     u.b = o;     o += stages * u.stage_bytes;
-    u.e2s = o;   o += kSESlots * nt * 4;
+    u.aone = o;  o += kSM * 32;          // constant A block of the |e|^2 step: 128 rows x 16 bf16, SWIZZLE_32B (256-byte aligned)
     u.brow = o;  o += kSBrowRing * kSM * 4;
     u.cs = o;    o += 2 * kSCand * kSM * 4;
     u.cc = o;    o += 2 * kSCand * kSM * 4;
@@ -98,7 +97,7 @@ __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stage
     u.scratch = o; o += kSScratch * 8 * 4;   // per scan warp
     u.red = o;   o += 32 * 8;
     u.misc = o;  o += 16 * 4;
-    u.bars = o;  o += (2 * kSMaxStages + 4 + 8 + 2 * kSESlots + 2 * kSBrowRing) * 8;
+    u.bars = o;  o += (2 * kSMaxStages + 4 + 8 + 2 * kSBrowRing) * 8;
     u.tmem = o;  o += 16;
     u.total = o;
     return u;
@@ -201,10 +200,28 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                  ::"r"(bar), "h"((uint16_t)3)
                  : "memory");
 }
+// Shared-memory matrix descriptor, K-major operand, SWIZZLE_32B: rows of 32 bytes (16 bf16 = one UMMA K step), 8-row
+// groups 256 bytes apart — what a TMA box of {16 bf16, rows} with CU_TENSOR_MAP_SWIZZLE_32B writes.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(256 >> 4) << 32;           // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)6 << 61;                    // SWIZZLE_32B
+    return d;
+}
 __device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
 }
 }  // namespace sm100
+
+// Bound on |(s_a - s_b) - (d_a - d_b) / 2| for one latent, s = the tensor-core half-scores |e|^2 / 2 - x.e (bf16 operands,
+// fp32 accumulation incl. the |e|^2 / 2 step), d = the canonical distances: half of DESIGN section 4's bf16 bound, the
+// second term widened (2e-6 -> 3e-6) for the one more accumulation the tensor core now does.
+__device__ __forceinline__ float stream_bound(const float xn, const float emax, const float sum) {
+    return 0.5f * fmaf(0.0172f * xn, emax, 3e-6f * sum * sum);
+}
 
 // Spill buffer of one TMEM lane quadrant for the current row tile (shared memory).
 struct OvfBuf {
@@ -251,22 +268,14 @@ __device__ __noinline__ int cand_make_room(const float thr, float* ls, int* lc, 
     return kept;
 }
 
-// One chunk of 32 scores of ONE latent (this thread's TMEM lane).
-__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const float4* e2c, const int code0, const float brow,
+// One chunk of 32 scores of ONE latent (this thread's TMEM lane).  The accumulator already IS the score (halved): the
+// GEMM runs on the negated codebook and carries |e|^2 / 2 as one extra K step, s = |e|^2 / 2 - x.e (see the kernel).
+__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const int code0, const float brow,
                                            ScanState& st, float* ls, int* lc, float* sd, const OvfBuf& ob, const int trow) {
     using namespace sm100;
     float s[32];
-#ifdef TVQ_ABL_NOE2      // ablation builds (tools/profile_stream.py): wrong results, timing only
 #pragma unroll
     for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
-    if (false)
-#endif
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float4 e = e2c[i];     // the same address for every lane: shared-memory broadcast
-        fma2(s[4 * i], s[4 * i + 1], __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), -2.f, -2.f, e.x, e.y);
-        fma2(s[4 * i + 2], s[4 * i + 3], __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]), -2.f, -2.f, e.z, e.w);
-    }
     float g[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = fminf(fmin3(s[4 * i], s[4 * i + 1], s[4 * i + 2]), s[4 * i + 3]);
@@ -442,7 +451,8 @@ __device__ __forceinline__ int gather_cands(int* list, const int n0, const int n
 // CTA from that CTA's shared memory.  Per SM this halves the TMA fill and the L2 traffic of the code stream and
 // takes a third off the shared-memory operand reads.
 template <int DP, int NT, bool TRAIN, int CG>
-__global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_cb, const FwdParams p,
+__global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_cb,
+                                                                 const __grid_constant__ CUtensorMap tmap_e2, const FwdParams p,
                                                                  const int stages) {
     using namespace sm100;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -456,7 +466,6 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     static_assert(NT == 128 || NT == 256, "code tile of 128 or 256");
 
     const StreamPlan pl = make_stream_plan(DP, NT, stages, CG);
-    float* e2s = reinterpret_cast<float*>(smem + pl.e2s);
     float* brow_ring = reinterpret_cast<float*>(smem + pl.brow);
     float* cand_s = reinterpret_cast<float*>(smem + pl.cs);     // [half][slot][latent]
     int* cand_c = reinterpret_cast<int*>(smem + pl.cc);
@@ -471,9 +480,8 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     const uint32_t bar_bfull = bar0, bar_bempty = bar_bfull + 8 * kSMaxStages;
     const uint32_t bar_afull = bar_bempty + 8 * kSMaxStages, bar_aempty = bar_afull + 16;
     const uint32_t bar_tfull = bar_aempty + 16, bar_tempty = bar_tfull + 32;
-    const uint32_t bar_efull = bar_tempty + 32, bar_eempty = bar_efull + 8 * kSESlots;
-    const uint32_t bar_rfull = bar_eempty + 8 * kSESlots, bar_rempty = bar_rfull + 8 * kSBrowRing;
-    const uint32_t a_base = smem_u32(smem + pl.a), b_base = smem_u32(smem + pl.b);
+    const uint32_t bar_rfull = bar_tempty + 32, bar_rempty = bar_rfull + 8 * kSBrowRing;
+    const uint32_t a_base = smem_u32(smem + pl.a), b_base = smem_u32(smem + pl.b), aone_base = smem_u32(smem + pl.aone);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunk = p.d >> 2;
@@ -491,13 +499,21 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
         for (int s = 0; s < kSMaxStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, CG * kSCvtWarps); mbar_init(bar_aempty + 8 * s, 1); }
         for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, CG * kSScanWarps); }
-        for (int s = 0; s < kSESlots; ++s) { mbar_init(bar_efull + 8 * s, 1); mbar_init(bar_eempty + 8 * s, kSScanWarps); }
         for (int s = 0; s < kSBrowRing; ++s) { mbar_init(bar_rfull + 8 * s, kSCvtWarps); mbar_init(bar_rempty + 8 * s, kSScanWarps); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_cb);
+        tma_prefetch_desc(&tmap_e2);
         for (int i = 4; i < 12; ++i) misc[i] = 0;           // spill counters [parity][quadrant]
     }
     if (warp == 1) { if (CG == 2) tmem_alloc2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
+    // constant A block of the |e|^2 step: every row is (1, 1, 1, 0, ..., 0) in bf16; 16-byte chunk c of row r sits at
+    // chunk (c ^ ((r >> 2) & 1)) of the row's 32 bytes (SWIZZLE_32B)
+    for (int i = tid; i < kSM * 2; i += kSThreads) {
+        const int r = i >> 1, c = i & 1;
+        const uint4 v = c == 0 ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(smem + pl.aone + r * 32 + ((c ^ ((r >> 2) & 1)) << 4)) = v;
+    }
+    if (CG == 2) fence_proxy_async_all(); else fence_proxy_async_smem();
     // max |e| (error-bound constant): every CTA scans the |e|^2 table (k floats, L2 resident)
     float emax2 = 0.f;
     for (int c = tid; c < p.k; c += kSThreads) emax2 = fmaxf(emax2, __ldg(p.e2 + c));
@@ -520,28 +536,26 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
 
     if (warp == 0) {
         // ============================================================ producer: code slabs (TMA) + |e|^2 slices
-        // (the |e|^2 table in the workspace is padded with BIG to a multiple of 256, so every slice is a
-        //  plain NT*4-byte bulk copy and codes >= k can never be nominated)
+        // per code tile: KSLABS slabs of the (negated) bf16 codebook, then the |e|^2 / 2 slab [NT x 16 bf16] (its table in the
+        // workspace is padded with BIG to a multiple of 256 codes, so codes >= k can never be nominated)
         if (lane == 0) {
             SP_DECL;
-            int ib = 0, et = 0;
+            int ib = 0;
             for (int grp = unit0; grp < ngroups; grp += nunits) {
-                for (int ct = 0; ct < n_ct; ++ct, ++et) {
-                    const int es = et % kSESlots;
-                    SP_WAIT(0, bar_eempty + 8 * es, (((uint32_t)(et / kSESlots)) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(bar_efull + 8 * es, (uint32_t)(NT * 4));
-                    bulk_load_1d(smem_u32(e2s + es * NT), p.e2 + (size_t)ct * NT, (uint32_t)(NT * 4), bar_efull + 8 * es);
-                    for (int j = 0; j < KSLABS; ++j, ++ib) {
+                for (int ct = 0; ct < n_ct; ++ct) {
+                    for (int j = 0; j <= KSLABS; ++j, ++ib) {
                         const int s = ib % stages;
+                        const uint32_t bytes = j < KSLABS ? (uint32_t)(NT * 128) : (uint32_t)(NT * 32);
+                        const CUtensorMap* tm = j < KSLABS ? &tmap_cb : &tmap_e2;
+                        const int c0 = j < KSLABS ? j * 64 : 0;
                         SP_WAIT(1, bar_bempty + 8 * s, (((uint32_t)(ib / stages)) & 1u) ^ 1u);
                         if (CG == 2) {
                             // the even CTA's barrier counts the bytes of both halves; each CTA fetches its half
-                            if (crank == 0) mbar_arrive_expect_tx(bar_bfull + 8 * s, (uint32_t)(NT * 128));
-                            tma_load_2d_pair(b_base + s * pl.stage_bytes, &tmap_cb, bar_bfull + 8 * s, j * 64,
-                                             ct * NT + crank * (NT / 2));
+                            if (crank == 0) mbar_arrive_expect_tx(bar_bfull + 8 * s, bytes);
+                            tma_load_2d_pair(b_base + s * pl.stage_bytes, tm, bar_bfull + 8 * s, c0, ct * NT + crank * (NT / 2));
                         } else {
-                            mbar_arrive_expect_tx(bar_bfull + 8 * s, (uint32_t)(NT * 128));
-                            tma_load_2d(b_base + s * pl.stage_bytes, &tmap_cb, bar_bfull + 8 * s, j * 64, ct * NT);
+                            mbar_arrive_expect_tx(bar_bfull + 8 * s, bytes);
+                            tma_load_2d(b_base + s * pl.stage_bytes, tm, bar_bfull + 8 * s, c0, ct * NT);
                         }
                     }
                 }
@@ -565,22 +579,28 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                     SP_WAIT(1, bar_tempty + 8 * slot, (((uint32_t)(tt / SLOTS)) & 1u) ^ 1u);
                     tc_fence_after();
 #pragma unroll 1
-                    for (int j = 0; j < KSLABS; ++j, ++ib) {
+                    for (int j = 0; j <= KSLABS; ++j, ++ib) {
                         const int s = ib % stages;
                         SP_WAIT(2, bar_bfull + 8 * s, ((uint32_t)(ib / stages)) & 1u);
                         tc_fence_after();
                         const uint32_t b0 = b_base + s * pl.stage_bytes;
+                        if (j < KSLABS) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
+                            for (int kk = 0; kk < 4; ++kk) {
 #ifdef TVQ_ABL_NOMMA     // ablation build: no MMA issued (timing of the scan without tensor-pipe / operand traffic)
-                            continue;
+                                continue;
 #endif
-                            if (CG == 2)
-                                umma_bf16_pair(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
-                                               umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
-                            else
-                                umma_bf16(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
-                                          umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
+                                if (CG == 2)
+                                    umma_bf16_pair(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
+                                                   umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
+                                else
+                                    umma_bf16(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
+                                              umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
+                            }
+                        } else {
+                            // + |e|^2 / 2: ONE more K step, constant A rows (1, 1, 1, 0...) x the three bf16 pieces of |e_c|^2 / 2
+                            if (CG == 2) umma_bf16_pair(tmem_base + slot * NT, umma_desc_sw32(aone_base), umma_desc_sw32(b0), idesc, 1u);
+                            else umma_bf16(tmem_base + slot * NT, umma_desc_sw32(aone_base), umma_desc_sw32(b0), idesc, 1u);
                         }
                         // stage free (in both CTAs of a pair) once these MMAs have read it
                         if (CG == 2) umma_commit_pair(bar_bempty + 8 * s); else umma_commit(bar_bempty + 8 * s);
@@ -654,7 +674,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                         for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
                         if (lane == 0) {
                             const float xn = sqrtf(t) * 1.0001f, sum = xn + emax;
-                            brow[rowbase + (i0 + u) / 2] = fmaf(0.0172f * xn, emax, 2e-6f * sum * sum);
+                            brow[rowbase + (i0 + u) / 2] = stream_bound(xn, emax, sum);
                         }
                     }
                 } else if constexpr (F == 32) {
@@ -665,7 +685,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                         for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
                         if (lane == 0) {
                             const float xn = sqrtf(t) * 1.0001f, sum = xn + emax;
-                            brow[rowbase + i0 + u] = fmaf(0.0172f * xn, emax, 2e-6f * sum * sum);
+                            brow[rowbase + i0 + u] = stream_bound(xn, emax, sum);
                         }
                     }
                 } else {
@@ -676,7 +696,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                         for (int off = 8; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
                         if ((lane & 15) == 0) {
                             const float xn = sqrtf(t) * 1.0001f, sum = xn + emax;
-                            brow[rowbase + 2 * (i0 + u) + (lane >> 4)] = fmaf(0.0172f * xn, emax, 2e-6f * sum * sum);
+                            brow[rowbase + 2 * (i0 + u) + (lane >> 4)] = stream_bound(xn, emax, sum);
                         }
                     }
                 }
@@ -732,13 +752,11 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
             }
             // ---- scan: this warp's half of the columns of every code tile
             for (int ct = 0; ct < n_ct; ++ct, ++et) {
-                const int slot = et % SLOTS, es = et % kSESlots;
-                SP_WAIT(1, bar_efull + 8 * es, ((uint32_t)(et / kSESlots)) & 1u);
+                const int slot = et % SLOTS;
                 SP_WAIT(2, bar_tfull + 8 * slot, ((uint32_t)(et / SLOTS)) & 1u);
                 tc_fence_after();
                 SP_RESET();
                 const uint32_t taddr = lane_addr + (uint32_t)(slot * NT);
-                const float4* e2c = reinterpret_cast<const float4*>(e2s + es * NT + half * (NT / 2));
                 const int code0 = ct * NT + half * (NT / 2);
                 uint32_t ra[32], rb[32];
                 tmem_ld_x32(taddr, ra);
@@ -746,16 +764,15 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 for (int c = 0; c < NCH; c += 2) {          // the next chunk's tcgen05.ld is in flight while this one is scanned
                     tmem_ld_wait();
                     tmem_ld_x32(taddr + (uint32_t)(c + 1) * 32u, rb);
-                    scan_chunk(ra, e2c + c * 8, code0 + c * 32, brow, st, ls, lc, sd, ob, trow);
+                    scan_chunk(ra, code0 + c * 32, brow, st, ls, lc, sd, ob, trow);
                     tmem_ld_wait();
                     if (c + 2 < NCH) tmem_ld_x32(taddr + (uint32_t)(c + 2) * 32u, ra);
-                    scan_chunk(rb, e2c + (c + 1) * 8, code0 + (c + 1) * 32, brow, st, ls, lc, sd, ob, trow);
+                    scan_chunk(rb, code0 + (c + 1) * 32, brow, st, ls, lc, sd, ob, trow);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     if (CG == 2) mbar_arrive_leader(bar_tempty + 8 * slot); else mbar_arrive(bar_tempty + 8 * slot);
-                    mbar_arrive(bar_eempty + 8 * es);
                 }
                 SP_LAP(3);
             }
