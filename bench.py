@@ -299,8 +299,13 @@ def our_arm(args):
     torch.set_float32_matmul_precision("high")                   # harness convolutions only; the VQ kernels decide in fp32/fp64
 
     torch.manual_seed(0)                                        # identical replicas
-    vq_l = tvq.VectorQuantize(DIM, K_CODES, sync_codebook=world > 1).to(dev).train()
-    vq_h = tvq.VectorQuantize(DIM, K_CODES, sync_codebook=world > 1).to(dev).train()
+    defer = args.defer if world > 1 else 0
+    vq_l = tvq.VectorQuantize(DIM, K_CODES, sync_codebook=world > 1, defer_exchange=defer).to(dev).train()
+    vq_h = tvq.VectorQuantize(DIM, K_CODES, sync_codebook=world > 1, defer_exchange=defer).to(dev).train()
+    if not args.no_sm_split:
+        # the two quantisers run on two streams: share the SMs out in proportion to their latents so that the two persistent
+        # forward launches (one whole SM's shared memory per CTA) are resident together instead of one after the other
+        vq_l._codebook.sm_share, vq_h._codebook.sm_share = 0.25, 0.75       # measured best (tools/time_split.py): 72 -> 65 us
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
     sets = []
     for _ in range(N_INPUT_SETS):
@@ -319,8 +324,10 @@ def our_arm(args):
         with torch.cuda.stream(side_h):
             qh, ih, lh, ph = vq_h(xh)
             torch.autograd.grad([qh, lh["loss"]], [xh], [gh, ones])
+            vq_h._codebook.join_pending()                 # (deferred exchange: the finalize kernel rejoins its stream)
         ql, il, ll, pl = vq_l(xl)
         torch.autograd.grad([ql, ll["loss"]], [xl], [gl, ones])
+        vq_l._codebook.join_pending()
         cur.wait_stream(side_h)
         return ll["loss"], lh["loss"], il, ih
 
@@ -667,6 +674,7 @@ def stage1_bench(c, tvq, args, vq_us_per_step):
         torch.manual_seed(0); np.random.seed(0)
         cfg = tvq.stage1.default_config()
         cfg["VQ-VAE"]["sync_codebook"] = world > 1
+        cfg["VQ-VAE"]["defer_exchange"] = args.defer if world > 1 else 0
         model = tvq.Stage1(200, 4, cfg).to(dev).to(memory_format=torch.channels_last)    # NHWC convolutions: 30 -> 20 ms per step
         tr = tvq.Stage1Trainer(model, (batch, 4, 200), use_graph=not args.no_graph)
         tr.warmup_and_capture(3)
@@ -976,6 +984,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-stage1", action="store_true")
+    ap.add_argument("--defer", type=int, default=2, choices=[0, 1, 2],
+                    help="N > 1: 0 = statistics exchange inside the forward kernel's last CTA (round 1); 1 / 2 = deferred to "
+                         "tvq_ema_finalize_dp on a side stream (include/tvq.h: tvq_hint_defer_exchange)")
+    ap.add_argument("--no-sm-split", action="store_true", help="LF and HF forward launches each take the whole GPU (round-1 behaviour)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

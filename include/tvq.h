@@ -58,6 +58,13 @@ TVQ_API const char *tvq_error_string(int code);
 /* 0 if `device` is compute capability 10.x; fills sm_count (may be NULL). */
 TVQ_API int tvq_device_check(int device, int *sm_count);
 
+/* One-shot launch hint of the calling thread: the next resident-codebook forward (tvq_forward / tvq_train_step* with
+ * k <= 32 train / 64 eval, d <= 128) launched from this thread uses at most max_ctas CTAs; cleared by that launch (0 clears
+ * it).  Results do not depend on the grid size (persistent kernel, dynamic tile scheduler).  For callers that run two
+ * independent quantisers on two streams: with the SMs shared out (e.g. in proportion to the latents) the two launches are
+ * resident together instead of one after the other.                                                              */
+TVQ_API int tvq_hint_max_ctas(int max_ctas);
+
 /* Bytes of scratch for (n, k, d): header + per-code constants (|e|^2 padded to a multiple of 256)
  * + tvq_train_step's statistics + the bf16 copy of the codebook that the streamed-codebook tcgen05
  * path feeds to TMA (k x roundup(d, 64..256) x 2 bytes, rewritten by every call).
@@ -135,6 +142,21 @@ TVQ_API int tvq_train_step_dp(const float *x, float *embed, float *cluster_size,
                       double eps, int64_t *idx, float *q, float *scalars, float *commit_out,
                       float *weighted_out, void *workspace, size_t workspace_bytes,
                       void *const *peer_bufs, int rank, int world, void *stream);
+
+/* Deferred exchange: the data-parallel step split in two so that the exchange latency and the skew between the ranks
+ * are off the critical path.  tvq_hint_defer_exchange(mode) is a one-shot hint of the calling thread for the NEXT fused
+ * data-parallel train step (tvq_train_step_dp / _qcf / _cf with world > 1) launched from this thread: the step fills idx, q,
+ * scalars and embed_prev as usual but neither waits for the peers nor updates cluster_size / embed_avg / embed;
+ *   mode 1: its last CTA still PUBLISHES this rank's statistics to the peers (remote stores + flags);
+ *   mode 2: it leaves them in the workspace scratch — its tail is then exactly the single-GPU one.
+ * tvq_ema_finalize_dp(published = (mode == 1), ...) completes the step: (mode 2: publish,) wait for every rank's
+ * statistics of that step, add them in rank order, apply the EMA update.  It must be enqueued after the step it completes,
+ * on any stream ordered after it, and before the next step on the same workspace / exchange buffers; every rank makes the
+ * same sequence of calls.  The caller orders later readers of the three buffers after it.                       */
+TVQ_API int tvq_hint_defer_exchange(int mode);
+TVQ_API int tvq_ema_finalize_dp(int published, void *workspace, size_t workspace_bytes, void *const *peer_bufs, int rank,
+                        int world, float *cluster_size, float *embed_avg, float *embed, int k, int d, double decay,
+                        double eps, void *stream);
 
 /* tvq_forward / tvq_train_step(_dp) writing q CHANNELS-FIRST: q [n / q_hw, d, q_hw] — the 'b c (h w)' layout of the
  * caller (utils/train_utils.py:349), so that quantize() needs no transpose after the VQ.  x stays [n, d]; idx stays

@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -18,6 +19,16 @@
 using namespace tvq;
 
 namespace {
+
+// NVTX range around every launching ABI call (the tracing equivalent of the reference's MLflow step
+// logging): an Nsight Systems / ncu --nvtx timeline shows which call of the reference-shaped API each kernel belongs to.
+// nvtx3 is header-only and resolves the profiler's injection library lazily: without a profiler a push/pop is a load and
+// a predictable branch.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define TVQ_RANGE(name) NvtxRange tvq_nvtx_range_(name)
 
 constexpr int kMaxDevices = 64;
 struct DeviceInfo {
@@ -70,6 +81,16 @@ int device_info(DeviceInfo** out) {
 // word and carries on (tvq_set_peer_timeout; default 30 min — longer than torch's NCCL watchdog, so a slow rank is never
 // turned into an error by this library first).  Process-wide, passed by value with every launch.
 unsigned long long g_peer_timeout_ns = 1800ull * 1000000000ull;
+
+// One-shot launch hint of the calling thread (tvq_hint_max_ctas): the NEXT resident-codebook forward launched from this
+// thread uses at most that many CTAs, then the hint is cleared.  The kernel is persistent with a dynamic tile scheduler, so
+// any grid size computes the same result; a caller that runs two independent quantisers on two streams (the LF and HF
+// codebooks of a stage-1 step) gives each a share of the SMs so that the two launches are resident TOGETHER instead of one
+// after the other (each CTA needs a whole SM's shared memory).
+thread_local int t_hint_max_ctas = 0;
+// One-shot hint (tvq_hint_defer_exchange): the next data-parallel fused train step of this thread only publishes its
+// statistics; the caller completes the step with tvq_ema_finalize_dp.
+thread_local int t_hint_defer_exchange = 0;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -166,7 +187,9 @@ int launch_fwd_umma_impl(FwdParams p, const DeviceInfo& di, cudaStream_t stream)
     // of the grid so that a second exchange kernel running next to it (the other codebook of the step, on another
     // stream) can always get ALL of its CTAs resident and publish its own statistics — whatever order the ranks
     // happen to start the two kernels in, nobody waits for an SM held by a waiting CTA.
-    const int cap = di.sm_count - (p.dp_world > 1 && di.sm_count > 1 ? 1 : 0);
+    int cap = di.sm_count - (p.dp_world > 1 && di.sm_count > 1 ? 1 : 0);
+    if (t_hint_max_ctas > 0 && t_hint_max_ctas < cap) cap = t_hint_max_ctas;
+    t_hint_max_ctas = 0;
     int grid = p.num_tiles < cap ? p.num_tiles : cap;
     kern<<<grid, kUThreads, pl.total, stream>>>(tm, p, stages);
     return launch_status();
@@ -337,6 +360,16 @@ __attribute__((visibility("default"))) int tvq_debug_gt(unsigned long long* out4
 
 int tvq_abi_version(void) { return 2; }
 
+int tvq_hint_max_ctas(int max_ctas) {
+    t_hint_max_ctas = max_ctas > 0 ? max_ctas : 0;
+    return TVQ_OK;
+}
+
+int tvq_hint_defer_exchange(int defer) {
+    t_hint_defer_exchange = (defer == 1 || defer == 2) ? defer : 0;
+    return TVQ_OK;
+}
+
 int tvq_set_peer_timeout(double seconds) {
     if (!(seconds >= 0.0) || seconds > 1e9) return TVQ_ERR_BAD_ARG;
     g_peer_timeout_ns = (unsigned long long)(seconds * 1e9);
@@ -413,7 +446,7 @@ int forward_impl(const float* x, const float* codebook, int64_t n, int k, int d,
     p.idx = idx; p.q = (flags & TVQ_F_WRITE_Q) ? q : nullptr; p.stats = stats; p.scalars = scalars;
     p.hdr = hdr; p.e2 = e2; p.commitment_weight = commitment_weight;
     p.commit_out = nullptr; p.weighted_out = nullptr; p.fuse_ema = 0;
-    p.peers = nullptr; p.dp_rank = 0; p.dp_world = 1; p.dp_timeout_ns = 0; p.q_hw = q_hw; p.x_hw = x_hw;
+    p.peers = nullptr; p.dp_rank = 0; p.dp_world = 1; p.dp_defer = 0; p.dp_timeout_ns = 0; p.q_hw = q_hw; p.x_hw = x_hw;
     p.cluster_size = nullptr; p.embed_avg = nullptr; p.embed = nullptr; p.embed_prev = nullptr;
     p.decay = p.one_minus_decay = p.eps = p.k_eps = 0.f;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
@@ -479,6 +512,8 @@ int train_step_impl(const float* x, float* embed, float* cluster_size, float* em
     p.cluster_size = cluster_size; p.embed_avg = embed_avg; p.embed = embed; p.embed_prev = embed_prev;
     p.decay = (float)decay; p.one_minus_decay = (float)(1.0 - decay); p.eps = (float)eps; p.k_eps = (float)((double)k * eps);
     p.peers = peers; p.dp_rank = dp_rank; p.dp_world = dp_world; p.dp_timeout_ns = g_peer_timeout_ns; p.q_hw = q_hw; p.x_hw = x_hw;
+    p.dp_defer = dp_world > 1 ? t_hint_defer_exchange : 0;
+    t_hint_defer_exchange = 0;
     p.num_tiles = (int)((n + kBM - 1) / kBM);
     p.exact = 0; p.given_idx = 0; p.use_hist = k <= 2048;
     if (umma) {
@@ -508,12 +543,14 @@ extern "C" {
 int tvq_forward(const float* x, const float* codebook, int64_t n, int k, int d, unsigned flags,
                 float commitment_weight, int64_t* idx, float* q, float* stats, float* scalars, void* workspace,
                 size_t workspace_bytes, void* stream_) {
+    TVQ_RANGE("tvq_forward");
     return forward_impl(x, codebook, n, k, d, flags, commitment_weight, idx, q, stats, scalars, workspace, workspace_bytes, stream_, 0);
 }
 
 int tvq_forward_qcf(const float* x, const float* codebook, int64_t n, int k, int d, unsigned flags,
                     float commitment_weight, int64_t* idx, float* q, float* stats, float* scalars, void* workspace,
                     size_t workspace_bytes, int q_hw, void* stream_) {
+    TVQ_RANGE("tvq_forward_qcf");
     if (q_hw < 1 || !q || !(flags & TVQ_F_WRITE_Q)) return TVQ_ERR_BAD_ARG;
     return forward_impl(x, codebook, n, k, d, flags, commitment_weight, idx, q, stats, scalars, workspace, workspace_bytes, stream_, q_hw);
 }
@@ -522,6 +559,7 @@ int tvq_train_step_qcf(const float* x, float* embed, float* cluster_size, float*
                        int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
                        float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* const* peer_bufs,
                        int rank, int world, int q_hw, void* stream_) {
+    TVQ_RANGE("tvq_train_step_qcf");
     if (q_hw < 1 || n < 1 || world < 1 || world > 64 || rank < 0 || rank >= world || (world > 1 && !peer_bufs)) return TVQ_ERR_BAD_ARG;
     return train_step_impl(x, embed, cluster_size, embed_avg, embed_prev, n, k, d, commitment_weight, decay, eps, idx, q, scalars,
                            commit_out, weighted_out, workspace, workspace_bytes, stream_, world > 1 ? peer_bufs : nullptr, rank, world,
@@ -530,6 +568,7 @@ int tvq_train_step_qcf(const float* x, float* embed, float* cluster_size, float*
 
 int tvq_forward_cf(const float* z, const float* codebook, int64_t b, int hw, int k, int d, unsigned flags, float commitment_weight,
                    int64_t* idx, float* q, float* stats, float* scalars, void* workspace, size_t workspace_bytes, void* stream_) {
+    TVQ_RANGE("tvq_forward_cf");
     if (hw < 1 || b < 1 || b * (int64_t)hw >= (int64_t(1) << 31) - 64) return TVQ_ERR_BAD_ARG;
     if (((flags & TVQ_F_WRITE_Q) != 0) != (q != nullptr)) return TVQ_ERR_BAD_ARG;
     return forward_impl(z, codebook, b * hw, k, d, flags, commitment_weight, idx, q, stats, scalars, workspace, workspace_bytes, stream_,
@@ -540,6 +579,7 @@ int tvq_train_step_cf(const float* z, float* embed, float* cluster_size, float* 
                       int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
                       float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* const* peer_bufs,
                       int rank, int world, void* stream_) {
+    TVQ_RANGE("tvq_train_step_cf");
     if (hw < 1 || b < 1 || b * (int64_t)hw >= (int64_t(1) << 31) - 64 || world < 1 || world > 64 || rank < 0 || rank >= world ||
         (world > 1 && !peer_bufs))
         return TVQ_ERR_BAD_ARG;
@@ -550,6 +590,7 @@ int tvq_train_step_cf(const float* z, float* embed, float* cluster_size, float* 
 
 int tvq_backward_cfx(const float* g_zq, const float* g_commit, const float* g_weighted, const float* z, const int64_t* idx,
                      const float* codebook, int64_t b, int hw, int k, int d, float commitment_weight, float* g_z, void* stream_) {
+    TVQ_RANGE("tvq_backward_cfx");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (d < 1 || hw < 1 || b < 0 || k < 1) return TVQ_ERR_UNSUPPORTED;
     if (b == 0) return TVQ_OK;
@@ -583,6 +624,7 @@ int tvq_backward_cfx(const float* g_zq, const float* g_commit, const float* g_we
 
 int tvq_backward_cf(const float* g_zq, const float* g_commit, const float* g_weighted, const float* x, const int64_t* idx,
                     const float* codebook, int64_t b, int hw, int k, int d, float commitment_weight, float* g_z, void* stream_) {
+    TVQ_RANGE("tvq_backward_cf");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (d < 1 || hw < 1 || b < 0) return TVQ_ERR_UNSUPPORTED;
     if (b == 0) return TVQ_OK;
@@ -610,6 +652,7 @@ int tvq_backward_cf(const float* g_zq, const float* g_commit, const float* g_wei
 int tvq_train_step(const float* x, float* embed, float* cluster_size, float* embed_avg, float* embed_prev, int64_t n, int k,
                    int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
                    float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* stream_) {
+    TVQ_RANGE("tvq_train_step");
     return train_step_impl(x, embed, cluster_size, embed_avg, embed_prev, n, k, d, commitment_weight, decay, eps, idx, q, scalars,
                            commit_out, weighted_out, workspace, workspace_bytes, stream_, nullptr, 0, 1);
 }
@@ -618,6 +661,7 @@ int tvq_train_step_dp(const float* x, float* embed, float* cluster_size, float* 
                       int d, float commitment_weight, double decay, double eps, int64_t* idx, float* q, float* scalars,
                       float* commit_out, float* weighted_out, void* workspace, size_t workspace_bytes, void* const* peer_bufs,
                       int rank, int world, void* stream_) {
+    TVQ_RANGE("tvq_train_step_dp");
     if (world < 1 || world > 64 || rank < 0 || rank >= world || (world > 1 && !peer_bufs)) return TVQ_ERR_BAD_ARG;
     if (n < 1) return TVQ_ERR_UNSUPPORTED;      // every rank must launch (the exchange is collective)
     return train_step_impl(x, embed, cluster_size, embed_avg, embed_prev, n, k, d, commitment_weight, decay, eps, idx, q, scalars,
@@ -626,6 +670,7 @@ int tvq_train_step_dp(const float* x, float* embed, float* cluster_size, float* 
 
 int tvq_ema_update(const float* stats, float* cluster_size, float* embed_avg, float* embed, float* embed_prev,
                    int k, int d, double decay, double eps, void* workspace, size_t workspace_bytes, void* stream_) {
+    TVQ_RANGE("tvq_ema_update");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 4 || (d & 3)) return TVQ_ERR_UNSUPPORTED;
     if (!stats || !cluster_size || !embed_avg || !embed || !workspace || workspace_bytes < sizeof(WsHeader)) return TVQ_ERR_BAD_ARG;
@@ -655,13 +700,15 @@ size_t tvq_exchange_bytes(int k, int d, int world) {
     return 64 + (((size_t)2 * world * 4 + 63) & ~(size_t)63) + (size_t)2 * world * len4 * 16;
 }
 
-int tvq_ema_update_dp(const float* stats, void* const* peer_bufs, int rank, int world, float* cluster_size, float* embed_avg,
-                      float* embed, float* embed_prev, int k, int d, double decay, double eps, void* stream_) {
+namespace {
+int ema_dp_launch(const float* stats, void* const* peer_bufs, int rank, int world, float* cluster_size, float* embed_avg,
+                  float* embed, float* embed_prev, int k, int d, double decay, double eps, int finalize, float* consume,
+                  void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 4 || (d & 3) || world < 1 || world > 64 || rank < 0 || rank >= world) return TVQ_ERR_UNSUPPORTED;
     if (TVQ_STATS_LEN(k, d) > (int64_t(1) << 16)) return TVQ_ERR_UNSUPPORTED;   // one CTA: small statistics only
-    if (!stats || !peer_bufs || !cluster_size || !embed_avg || !embed) return TVQ_ERR_BAD_ARG;
-    if (!aligned16(stats) || !aligned16(embed_avg) || !aligned16(embed) || (embed_prev && !aligned16(embed_prev))) return TVQ_ERR_BAD_ARG;
+    if ((!finalize && !stats) || !peer_bufs || !cluster_size || !embed_avg || !embed) return TVQ_ERR_BAD_ARG;
+    if ((stats && !aligned16(stats)) || !aligned16(embed_avg) || !aligned16(embed) || (embed_prev && !aligned16(embed_prev))) return TVQ_ERR_BAD_ARG;
     DeviceInfo* di = nullptr;
     int rc = device_info(&di);
     if (rc != TVQ_OK) return rc;
@@ -676,12 +723,33 @@ int tvq_ema_update_dp(const float* stats, void* const* peer_bufs, int rank, int 
     p.peers = peer_bufs; p.rank = rank; p.world = world;
     p.len4 = (TVQ_STATS_LEN(k, d) + 3) / 4;
     p.timeout_ns = g_peer_timeout_ns;
+    p.finalize = finalize;
+    p.consume = consume;
     ema_dp_kernel<<<1, 1024, 0, stream>>>(p);
     return launch_status();
+}
+}  // namespace
+
+int tvq_ema_update_dp(const float* stats, void* const* peer_bufs, int rank, int world, float* cluster_size, float* embed_avg,
+                      float* embed, float* embed_prev, int k, int d, double decay, double eps, void* stream_) {
+    TVQ_RANGE("tvq_ema_update_dp");
+    return ema_dp_launch(stats, peer_bufs, rank, world, cluster_size, embed_avg, embed, embed_prev, k, d, decay, eps, 0, nullptr, stream_);
+}
+
+int tvq_ema_finalize_dp(int published, void* workspace, size_t workspace_bytes, void* const* peer_bufs, int rank, int world,
+                        float* cluster_size, float* embed_avg, float* embed, int k, int d, double decay, double eps, void* stream_) {
+    TVQ_RANGE("tvq_ema_finalize_dp");
+    if (published)
+        return ema_dp_launch(nullptr, peer_bufs, rank, world, cluster_size, embed_avg, embed, nullptr, k, d, decay, eps, 1, nullptr, stream_);
+    // the step left its statistics in the private scratch of the workspace (zero on entry, zero again after this call)
+    if (!workspace || !aligned16(workspace) || k < 1 || d < 4 || workspace_bytes < tvq_workspace_bytes(0, k, d)) return TVQ_ERR_BAD_ARG;
+    float* scratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + sizeof(WsHeader)) + e2_len(k);
+    return ema_dp_launch(scratch, peer_bufs, rank, world, cluster_size, embed_avg, embed, nullptr, k, d, decay, eps, 0, scratch, stream_);
 }
 
 int tvq_backward(const float* g_q, const float* g_commit, const float* g_weighted, const float* x, const int64_t* idx,
                  const float* codebook, int64_t n, int k, int d, float commitment_weight, float* g_x, void* stream_) {
+    TVQ_RANGE("tvq_backward");
     cudaStream_t stream = (cudaStream_t)stream_;
     (void)k;
     if (d < 4 || (d & 3) || n < 0) return TVQ_ERR_UNSUPPORTED;
@@ -706,6 +774,7 @@ int tvq_gather(const int64_t* tokens, const float* codebook, int64_t b, int64_t 
 
 int tvq_gather_checked(const int64_t* tokens, const float* codebook, int64_t b, int64_t t, int k, int d, int layout,
                        float* out, unsigned* bad_count, void* stream_) {
+    TVQ_RANGE("tvq_gather_checked");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 1 || b < 0 || t < 0 || (layout != 0 && layout != 1)) return TVQ_ERR_UNSUPPORTED;
     if (b * t == 0) return TVQ_OK;
@@ -727,6 +796,7 @@ int tvq_gather_checked(const int64_t* tokens, const float* codebook, int64_t b, 
 }
 
 int tvq_neg_dist(const float* x, const float* codebook, int64_t n, int k, int d, float* dist, void* stream_) {
+    TVQ_RANGE("tvq_neg_dist");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 4 || (d & 3) || n < 0) return TVQ_ERR_UNSUPPORTED;
     if (n == 0) return TVQ_OK;
@@ -742,6 +812,7 @@ int tvq_neg_dist(const float* x, const float* codebook, int64_t n, int k, int d,
 
 int tvq_frontend(const float* x, int64_t b, int c, int l, int n_fft, float* xf, float* enc_in_l, float* enc_in_h, float* x_l,
                  float* x_h, void* stream_) {
+    TVQ_RANGE("tvq_frontend");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (b < 0 || c < 1 || n_fft < 4 || n_fft > 64 || (n_fft & 3) || l <= n_fft / 2 || l / (n_fft / 4) < 1) return TVQ_ERR_UNSUPPORTED;
     if (b == 0) return TVQ_OK;
@@ -787,6 +858,7 @@ int launch_band_istft(const BandIstftParams& p, int64_t b, int c, cudaStream_t s
 extern "C" {
 
 int tvq_band_istft_frames(const float* u, int64_t b, int c, int t, int l, int n_fft, int band, float* y, void* stream_) {
+    TVQ_RANGE("tvq_band_istft_frames");
     if (b > 0 && (!u || !y)) return TVQ_ERR_BAD_ARG;
     BandIstftParams p;
     p.u = u; p.g_y = nullptr; p.y = y; p.g_u = nullptr; p.rows = b * c; p.l = l; p.n_fft = n_fft; p.band = band; p.t = t;
@@ -794,6 +866,7 @@ int tvq_band_istft_frames(const float* u, int64_t b, int c, int t, int l, int n_
 }
 
 int tvq_band_istft_frames_backward(const float* g_y, int64_t b, int c, int t, int l, int n_fft, int band, float* g_u, void* stream_) {
+    TVQ_RANGE("tvq_band_istft_frames_backward");
     if (b > 0 && (!g_y || !g_u)) return TVQ_ERR_BAD_ARG;
     BandIstftParams p;
     p.u = nullptr; p.g_y = g_y; p.y = nullptr; p.g_u = g_u; p.rows = b * c; p.l = l; p.n_fft = n_fft; p.band = band; p.t = t;
@@ -813,6 +886,7 @@ int tvq_band_istft_backward(const float* g_y, int64_t b, int c, int l, int n_fft
 int tvq_maskgit_step(const float* logits, const int64_t* s, const float* q, const float* u, int64_t b, int n, int k,
                      int64_t mask_token_id, int mask_len, float temperature, int64_t* s_new, int64_t* sampled, uint8_t* masking,
                      void* stream_) {
+    TVQ_RANGE("tvq_maskgit_step");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (b < 0 || n < 1 || k < 1 || n > 8192 || mask_len < 0) return TVQ_ERR_UNSUPPORTED;
     if (b == 0) return TVQ_OK;
@@ -830,6 +904,7 @@ int tvq_maskgit_step(const float* logits, const int64_t* s, const float* q, cons
 }
 
 int tvq_transpose(const float* in, int64_t b, int r, int s, float* out, void* stream_) {
+    TVQ_RANGE("tvq_transpose");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (b < 0 || r < 1 || s < 1) return TVQ_ERR_UNSUPPORTED;
     if (b == 0) return TVQ_OK;
@@ -857,6 +932,7 @@ int tvq_transpose(const float* in, int64_t b, int r, int s, float* out, void* st
 
 int tvq_reseed(const float* x, const int64_t* rows, const float* cluster_size, float threshold, float* embed,
                int64_t n, int k, int d, void* stream_) {
+    TVQ_RANGE("tvq_reseed");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k < 1 || d < 4 || (d & 3) || n < 1) return TVQ_ERR_UNSUPPORTED;
     if (!x || !rows || !cluster_size || !embed || !aligned16(x) || !aligned16(embed)) return TVQ_ERR_BAD_ARG;

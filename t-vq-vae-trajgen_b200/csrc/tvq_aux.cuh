@@ -156,6 +156,9 @@ struct EmaDpParams {
     int rank, world;
     int64_t len4;                // statistics length in float4 (padded)
     unsigned long long timeout_ns;   // give up waiting for a peer after this long (0 = never); see wait_flag_sys
+    int finalize;                // 1: the statistics of this step were already published by the forward kernel
+                                 // (tvq_fwd_simt.cuh::dp_publish_stats): no push, the step counter is read, not advanced
+    float* consume;              // optional: e.stats is the workspace scratch of the fused step: zero it once it is pushed
 };
 
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
@@ -175,25 +178,31 @@ __global__ void __launch_bounds__(1024) ema_dp_kernel(const EmaDpParams p) {
     unsigned char* mine = reinterpret_cast<unsigned char*>(p.peers[p.rank]);
     if (tid == 0) {
         unsigned* counter = reinterpret_cast<unsigned*>(mine);
-        s_epoch = *counter + 1u;
-        *counter = s_epoch;
+        s_epoch = *reinterpret_cast<volatile unsigned*>(counter) + (p.finalize ? 0u : 1u);
+        if (!p.finalize) *counter = s_epoch;
     }
     __syncthreads();
     const unsigned epoch = s_epoch;
     const int par = (int)(epoch & 1u);
     const size_t flags_off = 64, slots_off = 64 + (((size_t)2 * p.world * 4 + 63) & ~(size_t)63);
     // ---- push
-    const float4* src = reinterpret_cast<const float4*>(p.e.stats);
-    for (int r = 0; r < p.world; ++r) {
-        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(p.peers[r]) + slots_off) +
-                      ((size_t)par * p.world + p.rank) * p.len4;
-        for (int64_t f = tid; f < p.len4; f += blockDim.x) dst[f] = src[f];
+    if (!p.finalize) {
+        const float4* src = reinterpret_cast<const float4*>(p.e.stats);
+        for (int r = 0; r < p.world; ++r) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(p.peers[r]) + slots_off) +
+                          ((size_t)par * p.world + p.rank) * p.len4;
+            for (int64_t f = tid; f < p.len4; f += blockDim.x) dst[f] = src[f];
+        }
+        __threadfence_system();
+        if (p.consume) {         // (every thread zeroes exactly the cells it has just read)
+            float4* z = reinterpret_cast<float4*>(p.consume);
+            for (int64_t f = tid; f < p.len4; f += blockDim.x) z[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
-    __threadfence_system();
     __syncthreads();
     if (tid < p.world) {
         unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(p.peers[tid]) + flags_off) + par * p.world + p.rank;
-        st_release_sys_u32(flag, epoch);
+        if (!p.finalize) st_release_sys_u32(flag, epoch);
         // ---- wait for every rank's contribution to MY buffer (bounded: a lost peer becomes a reported error, not a hang)
         const unsigned* lf = reinterpret_cast<const unsigned*>(mine + flags_off) + par * p.world + tid;
         wait_flag_sys(lf, epoch, p.timeout_ns, reinterpret_cast<unsigned*>(mine) + 1);

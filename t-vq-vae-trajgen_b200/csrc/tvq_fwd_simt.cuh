@@ -52,6 +52,8 @@ struct FwdParams {
     // data-parallel fused step: exchange buffers of every rank (tvq_aux.cuh::ema_dp_kernel layout); world <= 1: local
     void* const* peers;
     int dp_rank, dp_world;
+    int dp_defer;         // data-parallel: the last CTA only PUBLISHES this rank's statistics (no wait, no EMA update); the update
+                          // runs later in tvq_ema_finalize_dp, off the critical path (tvq_hint_defer_exchange)
     unsigned long long dp_timeout_ns;   // give up waiting for a peer after this long (0 = never); tvq_common.cuh::wait_flag_sys
     // q layout: 0 = [n, d] row-major; hw > 0 = channels-first [n / hw, d, hw] (the 'b c (h w)' layout of the caller,
     // utils/train_utils.py:349): resident-codebook tcgen05 kernel only
@@ -305,6 +307,41 @@ __device__ __forceinline__ void dp_reduce_stats(const FwdParams& p, int* misc) {
             sv.x += v.x; sv.y += v.y; sv.z += v.z; sv.w += v.w;
         }
         out[f] = sv;
+    }
+    __syncthreads();
+}
+
+// The first half of dp_reduce_stats only: push this rank's packed statistics into its slot on every rank and publish the
+// flags — no wait.  The matching second half (wait for all flags of the step, rank-ordered sum, EMA update) is
+// tvq_aux.cuh::ema_dp_kernel in its finalize form, launched by the caller on a stream of its choice: the exchange latency
+// and the inter-rank skew then overlap whatever the caller runs next (the backward kernels) instead of holding this
+// kernel's last CTA.  Called by every thread of the LAST CTA.
+__device__ __forceinline__ void dp_publish_stats(const FwdParams& p, int* misc) {
+    const int tid = threadIdx.x;
+    const int world = p.dp_world;
+    const int kp = (p.k + 3) & ~3;
+    const int64_t len4 = (int64_t)(kp + p.k * p.d) >> 2;
+    unsigned char* mine = reinterpret_cast<unsigned char*>(p.peers[p.dp_rank]);
+    if (tid == 0) {
+        unsigned* counter = reinterpret_cast<unsigned*>(mine);
+        misc[2] = (int)(*counter + 1u);
+        *counter = (unsigned)misc[2];
+    }
+    __syncthreads();
+    const unsigned epoch = (unsigned)misc[2];
+    const int par = (int)(epoch & 1u);
+    const size_t flags_off = 64, slots_off = 64 + (((size_t)2 * world * 4 + 63) & ~(size_t)63);
+    const float4* src = reinterpret_cast<const float4*>(p.stats);
+    for (int r = 0; r < world; ++r) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(p.peers[r]) + slots_off) +
+                      ((size_t)par * world + p.dp_rank) * len4;
+        for (int64_t f = tid; f < len4; f += blockDim.x) dst[f] = __ldcg(src + f);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) {
+        unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(p.peers[tid]) + flags_off) + par * world + p.dp_rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
     }
     __syncthreads();
 }

@@ -171,6 +171,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
+// The same for a hand-off that publishes NO generic-proxy data (a score slot going back to the MMA issuer: the only
+// thing ordered is this warp's tcgen05.ld, already complete and fenced by tcgen05.fence::before_thread_sync): the default
+// arrive, as CUTLASS's ClusterBarrier::arrive(cta_id) issues it.  The cluster-scope release above made every scan warp
+// wait for its candidate-list stores to drain once per code tile (9 % of the kernel's stall samples at 4096 x 128).
+__device__ __forceinline__ void mbar_arrive_leader_nodata(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {   // one full warp in EACH CTA of the pair
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -772,7 +779,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (CG == 2) mbar_arrive_leader(bar_tempty + 8 * slot); else mbar_arrive(bar_tempty + 8 * slot);
+                    if (CG == 2) mbar_arrive_leader_nodata(bar_tempty + 8 * slot); else mbar_arrive(bar_tempty + 8 * slot);
                 }
                 SP_LAP(3);
             }

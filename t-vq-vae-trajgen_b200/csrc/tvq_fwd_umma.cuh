@@ -347,6 +347,27 @@ __device__ __forceinline__ void finish_resident(const FwdParams& p, const float*
     }
     if (!ema) return;
     float cnt = cnt0;
+    if (dp && p.dp_defer) {
+        // deferred exchange: publish this rank's statistics and leave — the wait, the rank-ordered sum and the EMA update
+        // run in tvq_ema_finalize_dp.  What only this kernel knows is saved here: the pre-update codebook for the backward;
+        // the statistics scratch is zero again for the next call.
+        // (dp_defer == 2: not even the publication happens here — the statistics stay in the workspace scratch, and
+        // tvq_ema_finalize_dp pushes them itself and zeroes the scratch; this kernel's tail is then the single-GPU one)
+        const bool publish = p.dp_defer == 1;
+        if (publish) dp_publish_stats(p, misc);
+        float4* prev4 = reinterpret_cast<float4*>(p.embed_prev);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int f = tid + j * kUThreads;
+            if (f < cells) {
+                const int c = f / dq;
+                if (prev4) prev4[f] = *reinterpret_cast<const float4*>(cbs + tile_off<KP>(c, f - c * dq));
+                if (publish) esum4[f] = z4;
+            }
+        }
+        if (publish && tid < kp) p.stats[tid] = 0.f;
+        return;
+    }
     if (dp) {
         // perplexity and loss above are this rank's own (as in the reference: vq.py:246-249 sits after, and is unaffected
         // by, the all-reduce); the EMA update uses the statistics of ALL ranks, summed over NVLink peer memory

@@ -179,6 +179,50 @@ def vq_ema_update_dp(stats: torch.Tensor, ex: PeerExchange, cluster_size: torch.
                                        float(eps))
 
 
+_SM_COUNT = {}
+
+
+def _hint_sm_share(cb, device) -> None:
+    """EuclideanCodebook.sm_share -> tvq_hint_max_ctas for the launch that follows (same thread)."""
+    share = getattr(cb, "sm_share", None)
+    if share:
+        sms = _SM_COUNT.get(device.index)
+        if sms is None:
+            sms = _SM_COUNT[device.index] = torch.cuda.get_device_properties(device).multi_processor_count
+        _lib.load().tvq_hint_max_ctas(max(1, int(round(float(share) * sms))))
+
+
+def _defer_begin(cb, px) -> int:
+    """Deferred data-parallel exchange (EuclideanCodebook.defer_exchange): one-shot hint for the launch that follows."""
+    mode = int(getattr(cb, "defer_exchange", 0) or 0) if px is not None else 0
+    if mode:
+        mode = 2 if mode is True or mode == 2 else 1        # True: everything after the scalars leaves the forward kernel
+        _lib.load().tvq_hint_defer_exchange(mode)
+    return mode
+
+
+def _defer_finish(cb, px, anchor: torch.Tensor, mode: int, ws: "Workspace") -> None:
+    """Enqueue tvq_ema_finalize_dp on the codebook's side stream, ordered after the train step just launched on the current
+    stream; the event it records is what every later reader of embed / embed_avg / cluster_size waits for
+    (EuclideanCodebook.join_pending — the module's buffer accessors do it)."""
+    dev = anchor.device
+    cur = torch.cuda.current_stream(dev)
+    if cb._side is None:
+        cb._side = torch.cuda.Stream(dev)
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    cb._side.wait_event(ev)
+    embed = cb._embed_data()
+    k, d = embed.shape
+    with torch.cuda.stream(cb._side):
+        _launch("tvq_ema_finalize_dp", anchor, 1 if mode == 1 else 0, ws.buf.data_ptr(), ws.nbytes, px.peers.data_ptr(), px.rank,
+                px.world, cb._buffers["cluster_size"].data_ptr(),
+                cb._buffers["embed_avg"].data_ptr(), embed.data_ptr(), k, d, float(cb.decay), float(cb.eps))
+        done = torch.cuda.Event()
+        done.record(cb._side)
+    cb.__dict__["_pending"] = done
+
+
 def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: float, embed_prev: Optional[torch.Tensor],
                       px: Optional["PeerExchange"] = None):
     """tvq_train_step on a codebook module's buffers: fused forward + EMA (one kernel for k <= 32, d <= 128).
@@ -189,6 +233,7 @@ def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: flo
     _need(x, "x")
     embed = cb._embed_data()
     _same_device(x, embed, ws.buf, embed_prev)
+    _hint_sm_share(cb, x.device)
     n, d = x.shape
     k = embed.shape[0]
     idx = torch.empty(n, dtype=torch.int64, device=x.device)
@@ -199,11 +244,14 @@ def vq_train_step_raw(x: torch.Tensor, cb, ws: Workspace, commitment_weight: flo
     if n == 0:
         scalars.fill_(float("nan")); commit.fill_(float("nan")); weighted.fill_(float("nan"))
     if px is not None:       # data-parallel: the kernel's last CTA sums the statistics of all ranks over NVLink peer memory
+        deferred = _defer_begin(cb, px)
         _launch("tvq_train_step_dp", x, x.data_ptr(), embed.data_ptr(), cb.cluster_size.data_ptr(), cb.embed_avg.data_ptr(),
                                            embed_prev.data_ptr() if embed_prev is not None else None, n, k, d,
                                            float(commitment_weight), float(cb.decay), float(cb.eps), idx.data_ptr(),
                                            q.data_ptr(), scalars.data_ptr(), commit.data_ptr(), weighted.data_ptr(),
                                            ws.buf.data_ptr(), ws.nbytes, px.peers.data_ptr(), px.rank, px.world)
+        if deferred:
+            _defer_finish(cb, px, x, deferred, ws)
         return idx, q, scalars, commit, weighted
     _launch("tvq_train_step", embed, x.data_ptr() if n else None, embed.data_ptr(), cb.cluster_size.data_ptr(),
                                     cb.embed_avg.data_ptr(), embed_prev.data_ptr() if embed_prev is not None else None,
@@ -394,11 +442,15 @@ class VQTrainStepCF(torch.autograd.Function):
         head = (embed.data_ptr(), cb.cluster_size.data_ptr(), cb.embed_avg.data_ptr(), prev.data_ptr() if prev is not None else None)
         outs = (float(commitment_weight), float(cb.decay), float(cb.eps), idx.data_ptr(), q.data_ptr(), scalars.data_ptr(),
                 commit.data_ptr(), weighted.data_ptr(), ws.buf.data_ptr(), ws.nbytes)
+        _hint_sm_share(cb, z.device)
+        deferred = _defer_begin(cb, px)
         if VQTrainStepCF.IN_PLACE:
             _launch("tvq_train_step_cf", z, z.data_ptr(), *head, b, int(hw), k, d, *outs, *tail)
         else:
             xr = transpose12(z)                           # [b, hw, d]: dropped right after the launch
             _launch("tvq_train_step_qcf", z, xr.data_ptr(), *head, n, k, d, *outs, *tail, int(hw))
+        if deferred:
+            _defer_finish(cb, px, z, deferred, ws)
         ctx.save_for_backward(x, idx, prev)
         ctx.meta = (b, hw, float(commitment_weight))
         ctx.mark_non_differentiable(idx, scalars)

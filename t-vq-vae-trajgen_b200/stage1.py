@@ -267,6 +267,8 @@ class Stage1Trainer:
         self.flat_grad.zero_()
         out = self.model.total_loss((self.x, None))
         out["loss"].sum().backward()
+        for vq in (self.model.vq_model_l, self.model.vq_model_h):      # deferred EMA exchange (if enabled): rejoin this stream
+            vq._codebook.join_pending()
         if self.world > 1:
             dist.all_reduce(self.flat_grad, group=self.group)
             self.flat_grad.mul_(1.0 / self.world)

@@ -93,11 +93,46 @@ class EuclideanCodebook(nn.Module):
 
         self.perplexity = None
         self._last_ind = None
+        # Fraction of the SMs the fused training-step launch of THIS codebook may use (None: all).  Two independent
+        # quantisers stepped on two streams (stage 1's LF and HF codebooks) set complementary shares, e.g. in proportion to
+        # their latents, so that the two persistent launches are resident together (include/tvq.h: tvq_hint_max_ctas).
+        self.sm_share: Optional[float] = None
+        # Data-parallel fused step with the exchange OFF the critical path (include/tvq.h: tvq_hint_defer_exchange): the
+        # forward kernel only publishes this rank's statistics; the wait for the peers, the rank-ordered sum and the EMA
+        # update run in tvq_ema_finalize_dp on a side stream, overlapping whatever follows the forward (decoder, backward).
+        # Readers of embed / embed_avg / cluster_size are ordered after it automatically (__getattr__ -> join_pending).
+        self.defer_exchange = False            # False | True | 1 | 2 (mode of tvq_hint_defer_exchange; True = 2)
+        self.__dict__["_pending"] = None       # torch.cuda.Event recorded after the outstanding finalize kernel, or None
+        self._side = None                      # the side stream of the finalize kernels
         self._ws: Optional[TF.Workspace] = None
         self._px = None            # TF.PeerExchange, or False once it is known to be unavailable
         # host mirror of `initted` so the hot path never reads a device flag (the reference syncs
         # on `if self.initted:` every call, vq.py:172)
         self._initted_host: Optional[bool] = not kmeans_init
+
+    _STATE = frozenset(("embed", "embed_avg", "cluster_size"))
+
+    def __getattr__(self, name):
+        # buffers live in self._buffers, so every `cb.embed` (module code, MaskGIT's `_codebook.embed`, state_dict users)
+        # comes through here: order the reader's stream after an outstanding deferred EMA update first
+        if name in EuclideanCodebook._STATE and self.__dict__.get("_pending") is not None:
+            self.join_pending()
+        return super().__getattr__(name)
+
+    def join_pending(self) -> None:
+        """Make the current stream wait for the outstanding tvq_ema_finalize_dp of this codebook (no host synchronisation)."""
+        ev = self.__dict__.get("_pending")
+        if ev is not None:
+            self.__dict__["_pending"] = None
+            torch.cuda.current_stream(self._buffers["embed_avg"].device).wait_event(ev)
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        self.join_pending()                    # (nn.Module reads self._buffers directly here)
+        return super()._save_to_state_dict(destination, prefix, keep_vars)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.join_pending()
+        return super()._apply(fn, *args, **kwargs)
 
     # -- plumbing ---------------------------------------------------------------------------
     def _workspace(self, device: torch.device) -> TF.Workspace:
@@ -322,7 +357,7 @@ class VectorQuantize(nn.Module):
                  kmeans_iters=10, use_cosine_sim=False, threshold_ema_dead_code=0, channel_last=True,
                  accept_image_fmap=False, commitment_weight=1.0, orthogonal_reg_weight=0.0,
                  orthogonal_reg_active_codes_only=False, orthogonal_reg_max_codes=None, sample_codebook_temp=0.0,
-                 sync_codebook=False, emb_dropout=0.0, **kwargs):
+                 sync_codebook=False, emb_dropout=0.0, defer_exchange=False, **kwargs):
         super().__init__()
         self.heads = heads
         codebook_dim = _default(codebook_dim, dim)
@@ -344,6 +379,9 @@ class VectorQuantize(nn.Module):
             decay=decay, eps=eps, threshold_ema_dead_code=threshold_ema_dead_code, use_ddp=sync_codebook,
             learnable_codebook=has_codebook_orthogonal_loss, sample_codebook_temp=sample_codebook_temp,
             emb_dropout=emb_dropout)
+        # (not a reference keyword) data-parallel only: take the statistics exchange off the critical path, see
+        # EuclideanCodebook.defer_exchange; a stage-1 config passes it under "VQ-VAE" next to sync_codebook
+        self._codebook.defer_exchange = defer_exchange       # False | True (= 2) | 1 | 2: include/tvq.h, tvq_hint_defer_exchange
         self.codebook_size = codebook_size
         self.accept_image_fmap = accept_image_fmap
         self.channel_last = channel_last

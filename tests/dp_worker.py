@@ -82,9 +82,9 @@ if world == 2:
 
 
 # ---- 2./3. configs[3] shapes against a single-process full-batch run ---------------------------------------------------
-def full_batch_case(k, d, hw, b_per_rank, channels_first, steps=3):
+def full_batch_case(k, d, hw, b_per_rank, channels_first, steps=3, defer=False):
     torch.manual_seed(7)
-    vq = tvq.VectorQuantize(d, k, sync_codebook=True).to(dev).train()       # data-parallel replica
+    vq = tvq.VectorQuantize(d, k, sync_codebook=True, defer_exchange=defer).to(dev).train()       # data-parallel replica
     solo = tvq.VectorQuantize(d, k, sync_codebook=False).to(dev).train()    # full batch on this GPU alone
     solo.load_state_dict(vq.state_dict())
     gen = torch.Generator().manual_seed(1234 + k + hw)
@@ -104,6 +104,7 @@ def full_batch_case(k, d, hw, b_per_rank, channels_first, steps=3):
             q, ind, loss, ppl = vq(z)
             qs, inds, losss, ppls = solo(zs)
         assert vq._codebook._px or k > 32, "the fused peer-exchange kernel was not used"
+        assert (vq._codebook.__dict__["_pending"] is not None) == (defer and k <= 32), "deferred finalize not scheduled as expected"
         # backward: DDP averages the ranks' gradients, each rank's loss is its local mean -> compare per shard with the
         # full-batch run whose commit loss is the global mean: g_local = g_q + (1/n_local) * ..., g_full = g_q + (1/n_full) * ...
         (q * gfull[sl].to(dev)).sum().backward()
@@ -123,6 +124,10 @@ def full_batch_case(k, d, hw, b_per_rank, channels_first, steps=3):
 for (k, d, hw, cf) in ((32, 128, 75, False), (32, 128, 18, False), (32, 128, 75, True), (32, 128, 18, True), (16, 64, 40, False),
                        (512, 64, 64, False)):
     full_batch_case(k, d, hw, 64, cf)
+# the same with the exchange deferred to tvq_ema_finalize_dp on a side stream (tvq_hint_defer_exchange)
+for mode in (1, 2):
+    for (k, d, hw, cf) in ((32, 128, 75, False), (32, 128, 18, True), (16, 64, 40, False)):
+        full_batch_case(k, d, hw, 64, cf, defer=mode)
 if rank == 0:
     print("configs[3] shapes: fused data-parallel step == full-batch single-GPU step (indices/q/grad exact, buffers 1e-5)", flush=True)
 

@@ -36,7 +36,9 @@ print("total warp-instructions", tot, "samples", ts, "SASS length", len(seq))
 print("by opcode:", ", ".join(f"{o} {100*n/tot:.1f}%" for o, n in byop.most_common(14)))
 srcdir = os.path.join(os.path.dirname(os.path.abspath(so)), "csrc")
 cache = {}
-for k, v in byline.most_common(top):
+order = bysamp.most_common(top) if os.environ.get("BY_SAMPLES") else byline.most_common(top)
+for k, _v in order:
+    v = byline[k]
     f, ln = k if k else ("?", 0)
     if f not in cache:
         pth = os.path.join(srcdir, f)
