@@ -260,6 +260,14 @@ TVQ_API int tvq_maskgit_step(const float *logits, const int64_t *s, const float 
  * utils/train_utils.py:346-349 ('b c h w -> b (h w) c' and back), as a coalesced tiled copy.                  */
 TVQ_API int tvq_transpose(const float *in, int64_t b, int r, int s, float *out, void *stream);
 
+/* Snake activation of the stage-1 conv stacks, y = x + sin^2(a_c x) / a_c (utils/train_utils.py:421-448), forward and
+ * backward in one kernel each — for the stage-1 harness, not the VQ hot path.  x, y, g, g_x [n, c, s] fp32 in NCHW order
+ * (channels_last = 0) or NHWC order (1); a, g_a [c]; g_a is ACCUMULATED into (zero it first).  c <= 1024.          */
+TVQ_API int tvq_snake_forward(const float *x, const float *a, int64_t n, int c, int64_t s, int channels_last, float *y,
+                      void *stream);
+TVQ_API int tvq_snake_backward(const float *g, const float *x, const float *a, int64_t n, int c, int64_t s,
+                       int channels_last, float *g_x, float *g_a, void *stream);
+
 /* Dead-code re-seed (vq.py:181-195): embed[j] = x[rows[j]] where cluster_size[j] < threshold.
  * Only `embed` is touched, as in the reference.  rows [k] int64 (drawn by the host).          */
 TVQ_API int tvq_reseed(const float *x, const int64_t *rows, const float *cluster_size, float threshold,

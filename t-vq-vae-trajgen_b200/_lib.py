@@ -16,7 +16,7 @@ F_TRAIN, F_WRITE_Q, F_EXACT, F_NO_UMMA, F_GIVEN_IDX = 1, 2, 4, 8, 16
 NUM_SCALARS = 8      # [0] commit, [1] perplexity, [2] weight*commit, [4:6] uint32 diagnostics
 
 EXPORTS = ("tvq_abi_version", "tvq_error_string", "tvq_device_check", "tvq_workspace_bytes", "tvq_forward",
-           "tvq_train_step", "tvq_train_step_dp", "tvq_ema_update", "tvq_exchange_bytes", "tvq_ema_update_dp", "tvq_backward", "tvq_gather", "tvq_gather_checked", "tvq_set_peer_timeout", "tvq_hint_max_ctas", "tvq_hint_defer_exchange", "tvq_ema_finalize_dp", "tvq_neg_dist", "tvq_reseed", "tvq_frontend", "tvq_band_istft", "tvq_band_istft_backward", "tvq_band_istft_frames", "tvq_band_istft_frames_backward", "tvq_maskgit_step", "tvq_transpose", "tvq_forward_qcf", "tvq_train_step_qcf", "tvq_backward_cf",
+           "tvq_train_step", "tvq_train_step_dp", "tvq_ema_update", "tvq_exchange_bytes", "tvq_ema_update_dp", "tvq_backward", "tvq_gather", "tvq_gather_checked", "tvq_set_peer_timeout", "tvq_hint_max_ctas", "tvq_snake_forward", "tvq_snake_backward", "tvq_hint_defer_exchange", "tvq_ema_finalize_dp", "tvq_neg_dist", "tvq_reseed", "tvq_frontend", "tvq_band_istft", "tvq_band_istft_backward", "tvq_band_istft_frames", "tvq_band_istft_frames_backward", "tvq_maskgit_step", "tvq_transpose", "tvq_forward_qcf", "tvq_train_step_qcf", "tvq_backward_cf",
            "tvq_forward_cf", "tvq_train_step_cf", "tvq_backward_cfx")
 
 _c = ctypes
@@ -38,6 +38,8 @@ _SIGNATURES = {
     "tvq_gather_checked": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "tvq_set_peer_timeout": (_i, [_d]),
     "tvq_hint_max_ctas": (_i, [_i]),
+    "tvq_snake_forward": (_i, [_vp, _vp, _i64, _i, _i64, _i, _vp, _vp]),
+    "tvq_snake_backward": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i, _vp, _vp, _vp]),
     "tvq_hint_defer_exchange": (_i, [_i]),
     "tvq_ema_finalize_dp": (_i, [_i, _vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _d, _d, _vp]),
     "tvq_neg_dist": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),

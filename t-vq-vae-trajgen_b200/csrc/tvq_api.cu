@@ -15,6 +15,7 @@
 #include "tvq_fwd_stream.cuh"
 #include "tvq_fwd_umma.cuh"
 #include "tvq_maskgit.cuh"
+#include "tvq_snake.cuh"
 
 using namespace tvq;
 
@@ -927,6 +928,42 @@ int tvq_transpose(const float* in, int64_t b, int r, int s, float* out, void* st
     int64_t tiles = b * ((r + 31) / 32) * ((s + 31) / 32);
     if (tiles > 32LL * di->sm_count) tiles = 32LL * di->sm_count;
     batched_transpose_kernel<<<(unsigned)tiles, 256, 0, stream>>>(in, out, b, r, s);
+    return launch_status();
+}
+
+int tvq_snake_forward(const float* x, const float* a, int64_t n, int c, int64_t s, int channels_last, float* y, void* stream_) {
+    TVQ_RANGE("tvq_snake_forward");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || c < 1 || s < 1 || c > kSnakeMaxC || s >= (int64_t(1) << 31)) return TVQ_ERR_UNSUPPORTED;
+    const int64_t total = n * c * s;
+    if (total == 0) return TVQ_OK;
+    if (!x || !a || !y) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    int64_t blocks = (total + 1023) / 1024;
+    if (blocks > 16LL * di->sm_count) blocks = 16LL * di->sm_count;
+    if (channels_last) snake_fwd_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(x, a, total, c, (int)s, y);
+    else snake_fwd_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x, a, total, c, (int)s, y);
+    return launch_status();
+}
+
+int tvq_snake_backward(const float* g, const float* x, const float* a, int64_t n, int c, int64_t s, int channels_last, float* g_x,
+                       float* g_a, void* stream_) {
+    TVQ_RANGE("tvq_snake_backward");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || c < 1 || s < 1 || c > kSnakeMaxC || s >= (int64_t(1) << 31)) return TVQ_ERR_UNSUPPORTED;
+    const int64_t total = n * c * s;
+    if (total == 0) return TVQ_OK;
+    if (!g || !x || !a || !g_x || !g_a) return TVQ_ERR_BAD_ARG;
+    DeviceInfo* di = nullptr;
+    int rc = device_info(&di);
+    if (rc != TVQ_OK) return rc;
+    int64_t blocks = (total + 2047) / 2048;
+    if (blocks > 8LL * di->sm_count) blocks = 8LL * di->sm_count;
+    const size_t smem = (size_t)c * sizeof(float);
+    if (channels_last) snake_bwd_kernel<true><<<(unsigned)blocks, 256, smem, stream>>>(g, x, a, total, c, (int)s, g_x, g_a);
+    else snake_bwd_kernel<false><<<(unsigned)blocks, 256, smem, stream>>>(g, x, a, total, c, (int)s, g_x, g_a);
     return launch_status();
 }
 

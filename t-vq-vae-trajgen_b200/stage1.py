@@ -29,6 +29,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 from torch import nn
 
+from . import functional as TF
 from . import glue
 from .vq import VectorQuantize
 
@@ -52,9 +53,39 @@ def compute_downsample_rate(input_length: int, n_fft: int, downsampled_width: in
     return round(input_length / (np.log2(n_fft) - 1) / downsampled_width)
 
 
+class _SnakeFn(torch.autograd.Function):
+    """y = x + sin^2(a x) / a on the fused kernels (tvq_snake_forward / _backward): x (b, c, h, w) contiguous in NCHW or
+    channels_last order, a (1, c, 1, 1)."""
+
+    @staticmethod
+    def forward(ctx, x, a):
+        cl = not x.is_contiguous()
+        b, c, h, w = x.shape
+        y = torch.empty_like(x)
+        TF._launch("tvq_snake_forward", x, x.data_ptr(), a.data_ptr(), b, c, h * w, 1 if cl else 0, y.data_ptr())
+        ctx.save_for_backward(x, a)
+        ctx.cl = cl
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, a = ctx.saved_tensors
+        b, c, h, w = x.shape
+        g = g.contiguous(memory_format=torch.channels_last) if ctx.cl else g.contiguous()
+        gx = torch.empty_like(x)
+        ga = torch.zeros_like(a)
+        TF._launch("tvq_snake_backward", x, g.data_ptr(), x.data_ptr(), a.data_ptr(), b, c, h * w, 1 if ctx.cl else 0,
+                   gx.data_ptr(), ga.data_ptr())
+        return gx, ga
+
+
 class SnakeActivation(nn.Module):
     """x + sin^2(a x) / a with one learnable `a` per channel (utils/train_utils.py:421-448; 2-D inputs only here).
-    `a` is drawn with numpy's global generator, as the reference does — same seed, same parameters."""
+    `a` is drawn with numpy's global generator, as the reference does — same seed, same parameters.  On CUDA fp32 tensors
+    the forward and backward are one kernel each (the reference fuses the expression with TorchScript); anything else
+    takes the torch expression."""
+
+    fused = True
 
     def __init__(self, num_features: int, a_base: float = 0.2, a_max: float = 0.5):
         super().__init__()
@@ -62,6 +93,9 @@ class SnakeActivation(nn.Module):
         self.a = nn.Parameter(torch.tensor(a, dtype=torch.float32))
 
     def forward(self, x):
+        if (SnakeActivation.fused and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and self.a.is_contiguous()
+                and (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last))):
+            return _SnakeFn.apply(x, self.a)
         return x + (1 / self.a) * torch.sin(self.a * x) ** 2
 
 
@@ -193,18 +227,42 @@ class Stage1(nn.Module):
         self.decoder_l = VQVAEDecoder(init_dim, hid_dim, c2, rate_l, nres, input_length, "lf", self.n_fft, in_channels)
         self.decoder_h = VQVAEDecoder(init_dim, hid_dim, c2, rate_h, nres, input_length, "hf", self.n_fft, in_channels)
 
+    # The LF and HF branches (encoder -> quantize -> decoder -> loss) are independent until the losses are added: on CUDA
+    # they run on two streams (autograd replays each branch's backward on the stream of its forward), so the many small
+    # kernels of the deep, narrow layers overlap.  Set to False for one stream.
+    two_streams = True
+
+    def _branch(self, enc, vq, dec, u, target, loss_fn):
+        z = enc(u)
+        z_q, s, vq_loss, ppl = glue.quantize(z, vq)
+        xhat = dec(z_q)
+        return xhat, (loss_fn(target, xhat) if target is not None else None), vq_loss, ppl
+
     def forward(self, batch, batch_idx: int = 0, return_x_rec: bool = False):
         x, _ = batch if isinstance(batch, (tuple, list)) else (batch, None)
         front = glue.lf_hf_frontend(x.contiguous(), self.n_fft, want=("enc_in_l", "enc_in_h", "x_l", "x_h"))
-        z_l = self.encoder_l(front["enc_in_l"])
-        z_q_l, s_l, vq_loss_l, ppl_l = glue.quantize(z_l, self.vq_model_l)
-        xhat_l = self.decoder_l(z_q_l)
-        z_h = self.encoder_h(front["enc_in_h"])
-        z_q_h, s_h, vq_loss_h, ppl_h = glue.quantize(z_h, self.vq_model_h)
-        xhat_h = self.decoder_h(z_q_h)
+        tl, th = (None, None) if return_x_rec else (front["x_l"], front["x_h"])
+        if self.two_streams and x.is_cuda:
+            cur = torch.cuda.current_stream(x.device)
+            if getattr(self, "_side_stream", None) is None:
+                self._side_stream = torch.cuda.Stream(x.device)
+            side = self._side_stream
+            side.wait_stream(cur)
+            for t in (front["enc_in_h"], front["x_h"]):
+                t.record_stream(side)
+            with torch.cuda.stream(side):
+                xhat_h, loss_h, vq_loss_h, ppl_h = self._branch(self.encoder_h, self.vq_model_h, self.decoder_h, front["enc_in_h"], th, F.l1_loss)
+            xhat_l, loss_l, vq_loss_l, ppl_l = self._branch(self.encoder_l, self.vq_model_l, self.decoder_l, front["enc_in_l"], tl, F.mse_loss)
+            cur.wait_stream(side)
+            for t in (xhat_h, loss_h, vq_loss_h["loss"], ppl_h):
+                if torch.is_tensor(t):
+                    t.record_stream(cur)
+        else:
+            xhat_l, loss_l, vq_loss_l, ppl_l = self._branch(self.encoder_l, self.vq_model_l, self.decoder_l, front["enc_in_l"], tl, F.mse_loss)
+            xhat_h, loss_h, vq_loss_h, ppl_h = self._branch(self.encoder_h, self.vq_model_h, self.decoder_h, front["enc_in_h"], th, F.l1_loss)
         if return_x_rec:
             return xhat_l + xhat_h
-        recons_loss = {"LF.time": F.mse_loss(front["x_l"], xhat_l), "HF.time": F.l1_loss(front["x_h"], xhat_h)}
+        recons_loss = {"LF.time": loss_l, "HF.time": loss_h}
         return recons_loss, {"LF": vq_loss_l, "HF": vq_loss_h}, {"LF": ppl_l, "HF": ppl_h}
 
     def total_loss(self, batch) -> Dict[str, torch.Tensor]:

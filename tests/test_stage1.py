@@ -123,3 +123,30 @@ def test_graph_replay_equals_eager_steps(tvq):
     for k in ("decoder_l.linear.weight", "encoder_h.encoder.0.block.0.weight"):
         torch.testing.assert_close(s1[k], s0[k], rtol=1e-3, atol=1e-5)
     assert float(s1["vq_model_h._codebook.cluster_size"].sum()) == pytest.approx(float(s0["vq_model_h._codebook.cluster_size"].sum()), rel=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,cl", [((3, 8, 3, 201), False), ((3, 8, 3, 201), True), ((5, 128, 3, 25), True), ((2, 4, 1, 7), False),
+                                      ((64, 16, 3, 100), True)])
+def test_fused_snake_matches_torch_expression(tvq, shape, cl):
+    """SnakeActivation on the fused kernels vs the reference's expression x + (1 / a) * sin(a x)^2 under torch autograd
+    (utils/train_utils.py:447), both memory formats: forward 1e-6, gradients 1e-5 (the gradient of `a` is a sum over
+    up to 1e5 elements accumulated with atomics)."""
+    from tvq_b200.stage1 import SnakeActivation
+    g = torch.Generator(device="cuda").manual_seed(5)
+    np.random.seed(1)
+    act = SnakeActivation(shape[1]).cuda()
+    x = torch.randn(shape, device="cuda", generator=g) * 3
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(shape, device="cuda", generator=g)
+    x1 = x.clone().requires_grad_(True)
+    y1 = act(x1)
+    y1.backward(gy)
+    ga1 = act.a.grad.clone(); act.a.grad = None
+    x2 = x.clone().requires_grad_(True)
+    y2 = x2 + (1 / act.a) * torch.sin(act.a * x2) ** 2
+    y2.backward(gy)
+    torch.testing.assert_close(y1, y2, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ga1, act.a.grad, rtol=1e-4, atol=1e-4 * float(act.a.grad.abs().max()))

@@ -23,7 +23,8 @@ torch.set_float32_matmul_precision("high")          # scripts/train.py:19
 torch.backends.cudnn.benchmark = True
 
 
-def run(use_graph, channels_last):
+def run(use_graph, channels_last, two_streams=True):
+    tvq.Stage1.two_streams = two_streams
     torch.manual_seed(0); np.random.seed(0)
     cfg = tvq.stage1.default_config()
     if world > 1:
@@ -46,13 +47,13 @@ def run(use_graph, channels_last):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     if rank == 0:
-        print(f"B={B} world={world} graph={use_graph} channels_last={channels_last}: {ms:.3f} ms/step = {B * world / ms * 1e3:,.0f} traj/s, "
+        print(f"B={B} world={world} graph={use_graph} channels_last={channels_last} two_streams={two_streams}: {ms:.3f} ms/step = {B * world / ms * 1e3:,.0f} traj/s, "
               f"loss {float(out['loss'].reshape(-1)[0]):.4f}", flush=True)
 
 
-for g, cl in ((False, False), (True, False), (True, True)):
+for g, cl, ts in ((True, True, False), (True, True, True), (False, True, True)):
     try:
-        run(g, cl)
+        run(g, cl, ts)
     except Exception as e:
         print("FAILED", g, cl, repr(e)[:500], flush=True)
 if world > 1:
