@@ -260,14 +260,15 @@ int make_cb_tensor_map(CUtensorMap* tm, const void* cbh, int k, int dp, int nt) 
     return r == CUDA_SUCCESS ? TVQ_OK : TVQ_ERR_BAD_ARG;
 }
 
-template <int DP, int NT, bool TRAIN, int CG>
+template <int DP, int NT, bool TRAIN, int CG, int SP>
 int launch_fwd_stream_impl(FwdParams p, const void* cbh, const void* e2h, const DeviceInfo& di, cudaStream_t stream) {
-    auto kern = fwd_stream_kernel<DP, NT, TRAIN, CG>;
-    const StreamPlan fixed = make_stream_plan(DP, NT, 0, CG);
+    auto kern = fwd_stream_kernel<DP, NT, TRAIN, CG, SP>;
+    constexpr int kSThreads = stream_threads(SP);
+    const StreamPlan fixed = make_stream_plan(DP, NT, 0, CG, SP);
     int stages = (di.max_smem_optin - fixed.total) / ((NT / CG) * 128);
     if (stages > kSMaxStages) stages = kSMaxStages;
     if (stages < 2) return TVQ_ERR_UNSUPPORTED;
-    const StreamPlan pl = make_stream_plan(DP, NT, stages, CG);
+    const StreamPlan pl = make_stream_plan(DP, NT, stages, CG, SP);
     static PerDeviceInt configured_smem(-1);
     if (int rc = ensure_dynamic_smem(kern, configured_smem, di.index, pl.total)) return rc;
     CUtensorMap tm, tm2;
@@ -308,13 +309,32 @@ inline int stream_cg(const FwdParams& p) {
     return (p.k >= 1024 && p.n > kSM) ? 2 : 1;
 }
 
+// Scan parts per quadrant (tvq_fwd_stream.cuh): 4 (20 warps) for d <= 64, and for d <= 128 from k = 2048 up; 2 (12 warps)
+// otherwise — measured at 2^20 latents: 512 x 64 1.03 -> 0.79 ms, 4096 x 64 2.25 -> 1.88, 16384 x 64 6.0 -> 5.1, 2048 x 128
+// 1.69 -> 1.54, 4096 x 128 2.28 -> 2.21, but 1024 x 128 1.12 -> 1.48 (at d = 128 the two converter warps, left with 64
+// registers, are the floor for short code streams).  TVQ_STREAM_SP=2|4 in the environment overrides the choice for d <= 128.
+inline int stream_sp(const FwdParams& p) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("TVQ_STREAM_SP");
+        forced = e ? atoi(e) : 0;
+    }
+    if (p.d > 128) return 2;
+    if (forced == 2 || forced == 4) return forced;
+    return (p.d <= 64 || p.k >= 2048) ? 4 : 2;
+}
+
 template <bool TRAIN>
 int dispatch_fwd_stream(const FwdParams& p, const void* cbh, const void* e2h, const DeviceInfo& di, cudaStream_t s) {
-    const int cg = stream_cg(p);
+    const int cg = stream_cg(p), sp = stream_sp(p);
     switch (stream_dp(p.d)) {
-        case 64: return cg == 2 ? launch_fwd_stream_impl<64, 256, TRAIN, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<64, 256, TRAIN, 1>(p, cbh, e2h, di, s);
-        case 128: return cg == 2 ? launch_fwd_stream_impl<128, 256, TRAIN, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<128, 256, TRAIN, 1>(p, cbh, e2h, di, s);
-        case 256: return cg == 2 ? launch_fwd_stream_impl<256, 256, TRAIN, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<256, 128, TRAIN, 1>(p, cbh, e2h, di, s);
+        case 64:
+            if (sp == 4) return cg == 2 ? launch_fwd_stream_impl<64, 256, TRAIN, 2, 4>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<64, 256, TRAIN, 1, 4>(p, cbh, e2h, di, s);
+            return cg == 2 ? launch_fwd_stream_impl<64, 256, TRAIN, 2, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<64, 256, TRAIN, 1, 2>(p, cbh, e2h, di, s);
+        case 128:
+            if (sp == 4) return cg == 2 ? launch_fwd_stream_impl<128, 256, TRAIN, 2, 4>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<128, 256, TRAIN, 1, 4>(p, cbh, e2h, di, s);
+            return cg == 2 ? launch_fwd_stream_impl<128, 256, TRAIN, 2, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<128, 256, TRAIN, 1, 2>(p, cbh, e2h, di, s);
+        case 256: return cg == 2 ? launch_fwd_stream_impl<256, 256, TRAIN, 2, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<256, 128, TRAIN, 1, 2>(p, cbh, e2h, di, s);
     }
     return TVQ_ERR_UNSUPPORTED;
 }

@@ -65,20 +65,26 @@ __device__ unsigned long long g_sprof[128];
 #endif
 
 constexpr int kSM = 128;                 // latents per row tile
-constexpr int kSThreads = 384;           // 12 warps: 168 registers per thread (the scan and apply phases need them)
+// Scan / apply warps: SP per TMEM lane quadrant, each taking 1/SP of the columns of every code tile ("scan part").
+//   SP = 2 (12 warps at 168 registers): d > 128, where a latent's row needs two 16-byte chunks per lane in the apply phase;
+//   SP = 4 (20 warps; setmaxnreg: 64 registers for the producer / issuer / converter warpgroup, 104 for the others): d <= 128.
+//   The scan is bound by the latency of tcgen05.ld (one load per warp in flight, ~350 clocks per 32-score chunk with two
+//   warps per scheduler), the apply phase by L2 round trips with a handful of latents in flight per warp: twice the warps
+//   is twice the loads and latents in flight.
+__host__ __device__ constexpr int stream_threads(int sp) { return 128 + 128 * sp; }
 constexpr int kSCvtWarps = 2;            // converter warps (64 latents each)
-constexpr int kSScanWarps = 8;           // two per TMEM lane quadrant
-constexpr int kSCand = 12;               // candidate slots per latent and scan half
+constexpr int kSMaxParts = 4;
+constexpr int kSCand = 12;               // candidate slots per latent and scan part
 constexpr int kSBrowRing = 4;            // row-bound buffers (converter runs up to 2 tiles ahead of the scan)
 constexpr int kSMaxStages = 8;
 constexpr int kSOvf = 32;                // spill entries per quadrant and row tile (beyond that: exhaustive scan)
-constexpr int kSScratch = 2 * kSCand + kSOvf;   // merged candidate list of one latent (general resolution path)
+constexpr int kSScratch = kSMaxParts * kSCand + kSOvf;   // merged candidate list of one latent (general resolution path)
 
 struct StreamPlan {
     int stages, stage_bytes, a_bytes;
     int a, b, aone, brow, cs, cc, drop, mfin, ncnt, ovf, scratch, red, misc, bars, tmem, total;
 };
-__host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages, int cg = 1) {
+__host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages, int cg = 1, int sp = 2) {
     StreamPlan u;
     u.stages = stages;
     u.stage_bytes = (nt / cg) * 128;     // this CTA's share of a code slab: NT/cg codes x 64 bf16
@@ -88,13 +94,13 @@ __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stage
     u.b = o;     o += stages * u.stage_bytes;
     u.aone = o;  o += kSM * 32;          // constant A block of the |e|^2 step: 128 rows x 16 bf16, SWIZZLE_32B (256-byte aligned)
     u.brow = o;  o += kSBrowRing * kSM * 4;
-    u.cs = o;    o += 2 * kSCand * kSM * 4;
-    u.cc = o;    o += 2 * kSCand * kSM * 4;
-    u.drop = o;  o += 4 * kSM * 4;           // [half][spillmin | dropmin][latent]
-    u.mfin = o;  o += 2 * kSM * 4;
-    u.ncnt = o;  o += 2 * kSM * 4;
+    u.cs = o;    o += sp * kSCand * kSM * 4;
+    u.cc = o;    o += sp * kSCand * kSM * 4;
+    u.drop = o;  o += 2 * sp * kSM * 4;      // [part][spillmin | dropmin][latent]
+    u.mfin = o;  o += sp * kSM * 4;
+    u.ncnt = o;  o += sp * kSM * 4;
     u.ovf = o;   o += 2 * 4 * kSOvf * 12;       // [row-tile parity][quadrant]: rows | scores | codes
-    u.scratch = o; o += kSScratch * 8 * 4;   // per scan warp
+    u.scratch = o; o += kSScratch * 4 * sp * 4;   // per scan warp
     u.red = o;   o += 32 * 8;
     u.misc = o;  o += 16 * 4;
     u.bars = o;  o += (2 * kSMaxStages + 4 + 8 + 2 * kSBrowRing) * 8;
@@ -433,13 +439,17 @@ __device__ __noinline__ int resolve_stream(const float4 x0, const float4 x1, con
     return arg | (1 << 30);
 }
 
-// Merge the candidates of one latent into `list` (this warp's scratch): half 0's n0 entries, half 1's n1,
-// and the quadrant's spilled entries of this latent that lie inside the final threshold.  Warp-cooperative.
-__device__ __forceinline__ int gather_cands(int* list, const int n0, const int n1, const int* lc_row, const OvfBuf ob,
+// Merge the candidates of one latent into `list` (this warp's scratch): every part's entries (cnt[part] of them, in part
+// order), and the quadrant's spilled entries of this latent that lie inside the final threshold.  Warp-cooperative.
+template <int SP>
+__device__ __forceinline__ int gather_cands(int* list, const int (&cnts)[SP], const int* lc_row, const OvfBuf ob,
                                             const int lrow, const float thr, const int lane) {
-    if (lane < n0) list[lane] = lc_row[lane * kSM];
-    if (lane < n1) list[n0 + lane] = lc_row[(kSCand + lane) * kSM];
-    int cnt = n0 + n1;
+    int cnt = 0;
+#pragma unroll
+    for (int pt = 0; pt < SP; ++pt) {
+        if (lane < cnts[pt]) list[cnt + lane] = lc_row[(pt * kSCand + lane) * kSM];
+        cnt += cnts[pt];
+    }
     const int on = min(*ob.n, kSOvf);
     for (int base = 0; base < on; base += 32) {
         const int e = base + lane;
@@ -457,24 +467,29 @@ __device__ __forceinline__ int gather_cands(int* list, const int n0, const int n
 // every code slab: the even CTA issues one M = 256 MMA for both, which reads the A rows and the B half of each
 // CTA from that CTA's shared memory.  Per SM this halves the TMA fill and the L2 traffic of the code stream and
 // takes a third off the shared-memory operand reads.
-template <int DP, int NT, bool TRAIN, int CG>
-__global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_cb,
+template <int DP, int NT, bool TRAIN, int CG, int SP>
+__global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_cb,
                                                                  const __grid_constant__ CUtensorMap tmap_e2, const FwdParams p,
                                                                  const int stages) {
     using namespace sm100;
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int KSLABS = DP / 64;             // 64-column (128-byte) bf16 slabs per row
     constexpr int SLOTS = 512 / NT;             // tensor-memory score slots
-    constexpr int NCH = NT / 64;                // 32-score chunks per code tile AND scan half
+    constexpr int NCH = NT / (32 * SP);         // 32-score chunks per code tile AND scan part
+    constexpr int kSThreads = stream_threads(SP);
+    constexpr int kSScanWarps = 4 * SP;
+    constexpr int LPW = 32 / SP;                // latents per warp in the apply phase
+    static_assert(SP == 2 || SP == 4, "two or four scan parts per quadrant");
+    static_assert(NCH >= 1, "at least one chunk per part");
     constexpr int F = DP / 4;                   // 16-byte fp32 chunks per padded row
     constexpr int NV = DP > 128 ? 2 : 1;        // 16-byte chunks per lane in the warp-per-latent phases
     constexpr int A_SLAB = kSM * 128;           // bytes of one A slab (128 rows x 128 bytes)
     static_assert(DP == 64 || DP == 128 || DP == 256, "d padded to 64, 128 or 256");
     static_assert(NT == 128 || NT == 256, "code tile of 128 or 256");
 
-    const StreamPlan pl = make_stream_plan(DP, NT, stages, CG);
+    const StreamPlan pl = make_stream_plan(DP, NT, stages, CG, SP);
     float* brow_ring = reinterpret_cast<float*>(smem + pl.brow);
-    float* cand_s = reinterpret_cast<float*>(smem + pl.cs);     // [half][slot][latent]
+    float* cand_s = reinterpret_cast<float*>(smem + pl.cs);     // [part][slot][latent]
     int* cand_c = reinterpret_cast<int*>(smem + pl.cc);
     float* mfin = reinterpret_cast<float*>(smem + pl.mfin);     // [half][latent] minimum seen by each scan half
     int* ncnt = reinterpret_cast<int*>(smem + pl.ncnt);         // [half][latent] final candidates per half (-1: incomplete)
@@ -541,6 +556,11 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
     double loss_d = 0.0;
     unsigned n_resc = 0, n_f64 = 0;
 
+    // 20 warps (SP == 4): the register file is shared out by warpgroup — 96 per thread at launch (61 440 in all: the pool setmaxnreg draws on), 64 for the producer /
+    // issuer / converter warpgroup, 104 for the scan / apply warpgroups (setmaxnreg at the head of each branch, so that the
+    // register allocator sees it dominate the branch)
+    if (warp < 4) {
+    if (SP == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
         // ============================================================ producer: code slabs (TMA) + |e|^2 slices
         // per code tile: KSLABS slabs of the (negated) bf16 codebook, then the |e|^2 / 2 slab [NT x 16 bf16] (its table in the
@@ -718,11 +738,13 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
             SP_LAP(2);
         }
         if (cw == 0 && lane == 0) SP_DUMP(24);
+    }
     } else {
+        if (SP == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ============================================================ scan + apply warps (one thread per latent)
         const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
-        const int half = (warp - 4) >> 2;                     // which half of every code tile's columns this warp scans
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (NT / 2));
+        const int half = (warp - 4) >> 2;                     // scan part: which 1/SP of every code tile's columns this warp scans
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (NT / SP));
         const int trow = quad * 32 + lane;                    // this thread's latent within the tile
         float* ls = cand_s + half * (kSCand * kSM) + trow;
         int* lc = cand_c + half * (kSCand * kSM) + trow;
@@ -736,7 +758,7 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
         // latents in flight in the apply phase (up to 4 candidates each are resolved in the batched pass).  Two candidates
         // per latent with twice the latents per L2 round trip was measured and is slower (512 x 64: 6.3 vs 4.4 ms): three-
         // and four-candidate latents are too common for the one-at-a-time second pass.
-        constexpr int R = NV > 1 ? 2 : 4;
+        constexpr int R = (NV > 1 || SP == 4) ? 2 : 4;
         SP_DECL;
         int et = 0, it = 0;
         for (int grp = unit0; grp < ngroups; grp += nunits, ++it) {
@@ -764,17 +786,22 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 tc_fence_after();
                 SP_RESET();
                 const uint32_t taddr = lane_addr + (uint32_t)(slot * NT);
-                const int code0 = ct * NT + half * (NT / 2);
+                const int code0 = ct * NT + half * (NT / SP);
                 uint32_t ra[32], rb[32];
                 tmem_ld_x32(taddr, ra);
+                if constexpr (NCH == 1) {
+                    tmem_ld_wait();
+                    scan_chunk(ra, code0, brow, st, ls, lc, sd, ob, trow);
+                } else {
 #pragma unroll 1
-                for (int c = 0; c < NCH; c += 2) {          // the next chunk's tcgen05.ld is in flight while this one is scanned
-                    tmem_ld_wait();
-                    tmem_ld_x32(taddr + (uint32_t)(c + 1) * 32u, rb);
-                    scan_chunk(ra, code0 + c * 32, brow, st, ls, lc, sd, ob, trow);
-                    tmem_ld_wait();
-                    if (c + 2 < NCH) tmem_ld_x32(taddr + (uint32_t)(c + 2) * 32u, ra);
-                    scan_chunk(rb, code0 + (c + 1) * 32, brow, st, ls, lc, sd, ob, trow);
+                    for (int c = 0; c < NCH; c += 2) {      // the next chunk's tcgen05.ld is in flight while this one is scanned
+                        tmem_ld_wait();
+                        tmem_ld_x32(taddr + (uint32_t)(c + 1) * 32u, rb);
+                        scan_chunk(ra, code0 + c * 32, brow, st, ls, lc, sd, ob, trow);
+                        tmem_ld_wait();
+                        if (c + 2 < NCH) tmem_ld_x32(taddr + (uint32_t)(c + 2) * 32u, ra);
+                        scan_chunk(rb, code0 + (c + 1) * 32, brow, st, ls, lc, sd, ob, trow);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -786,8 +813,11 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
             SP_RESET();
             // ---- merge the two halves of the quadrant: common minimum, then each half filters its own list
             mfin[half * kSM + trow] = st.m;
-            named_bar_sync(1 + quad, 64);
-            const float thr_fin = fminf(st.m, mfin[(half ^ 1) * kSM + trow]) + brow;
+            named_bar_sync(1 + quad, 32 * SP);
+            float mall = st.m;
+#pragma unroll
+            for (int pt = 0; pt < SP; ++pt) mall = fminf(mall, mfin[pt * kSM + trow]);
+            const float thr_fin = mall + brow;
             {
                 int kept = 0;
                 for (int i = 0; i < st.cnt; ++i) {
@@ -805,20 +835,20 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 }
                 ncnt[half * kSM + trow] = nres;
             }
-            named_bar_sync(1 + quad, 64);
-            if (half == 0) thrfin[trow] = thr_fin;            // (both halves have read mfin)
-            named_bar_sync(1 + quad, 64);
+            named_bar_sync(1 + quad, 32 * SP);
+            if (half == 0) thrfin[trow] = thr_fin;            // (every part has read mfin)
+            named_bar_sync(1 + quad, 32 * SP);
             SP_LAP(4);
             // ---- resolve + apply: all 32 lanes on one latent, R latents in flight, ONE round trip to L2:
             //      x rows, the first candidate's code word and (for ambiguous latents) candidates 2-4 are
             //      all requested before anything is used.  This warp takes 16 latents of its quadrant.
-            const int lrow0 = quad * 32 + half * 16;          // first latent (within the tile) of this warp
+            const int lrow0 = quad * 32 + half * LPW;         // first latent (within the tile) of this warp
             const int64_t wrow0 = (int64_t)tile * kSM + lrow0;
             int mycode = 0;
             float loss = 0.f;
             unsigned gen_mask = 0;                            // latents left to the general path (second pass)
 #pragma unroll 1
-            for (int b = 0; b < 16 / R; ++b) {
+            for (int b = 0; b < LPW / R; ++b) {
                 if (wrow0 + R * b >= p.n) break;              // warp-uniform
                 SP_MARK(sp_b0);
                 float4 xa[R], xb[R], ea[R][4], eb[R][4];
@@ -831,13 +861,22 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 {
                     const int lu = (lane >> 2) & (R - 1), lj = lane & 3;
                     const int lrow = lrow0 + R * b + lu;
-                    const int n0r = ncnt[lrow], n1r = ncnt[kSM + lrow];
-                    const int n0 = n0r & 0xff, n1 = n1r & 0xff;
                     // 1..4: the merged count, resolved right here; anything else: general path
-                    nc_l = (n0r < 0 || n1r < 0 || ((n0r | n1r) & 0x100) || n0 + n1 == 0 || n0 + n1 > 4) ? 0 : n0 + n1;
-                    // candidate j of the merged list: half 0's entries first, then half 1's
-                    const int jj = lj < nc_l ? lj : 0;
-                    const int c = jj < n0 ? cand_c[jj * kSM + lrow] : cand_c[(kSCand + ((jj - n0) & (kSCand - 1))) * kSM + lrow];
+                    int tot = 0, bad = 0, cn[SP];
+#pragma unroll
+                    for (int pt = 0; pt < SP; ++pt) {
+                        const int nr = ncnt[pt * kSM + lrow];
+                        bad |= (nr < 0) | (nr & 0x100);
+                        cn[pt] = nr & 0xff;
+                        tot += cn[pt];
+                    }
+                    nc_l = (bad || tot == 0 || tot > 4) ? 0 : tot;
+                    // candidate j of the merged list: part 0's entries first, then part 1's, ...
+                    int jj = lj < nc_l ? lj : 0, part_j = 0;
+#pragma unroll
+                    for (int pt = 0; pt < SP - 1; ++pt)
+                        if (part_j == pt && jj >= cn[pt]) { jj -= cn[pt]; part_j = pt + 1; }
+                    const int c = cand_c[(part_j * kSCand + (jj < kSCand ? jj : 0)) * kSM + lrow];
                     c_l = (c >= 0 && c < p.k) ? c : 0;
                 }
 #pragma unroll
@@ -935,10 +974,16 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)grow * p.d);
                 const float4 xa = h0 ? __ldg(xr + lane) : z4;
                 const float4 xb = h1 ? __ldg(xr + lane + 32) : z4;
-                const int n0r = ncnt[lrow], n1r = ncnt[kSM + lrow];
+                int cn[SP], badg = 0;
+#pragma unroll
+                for (int pt = 0; pt < SP; ++pt) {
+                    const int nr = ncnt[pt * kSM + lrow];
+                    badg |= nr < 0;
+                    cn[pt] = nr & 0xff;
+                }
                 int ncg = -1;
-                if (n0r >= 0 && n1r >= 0) {
-                    ncg = gather_cands(scratch, n0r & 0xff, n1r & 0xff, cand_c + lrow, ob, lrow, thrfin[lrow], lane);
+                if (!badg) {
+                    ncg = gather_cands<SP>(scratch, cn, cand_c + lrow, ob, lrow, thrfin[lrow], lane);
                     if (ncg == 0) ncg = -1;
                 }
                 const int rr = resolve_stream<NV>(xa, xb, ncg, scratch, p.cb, p.e2, p.k, p.d, emax, lane);
@@ -956,13 +1001,13 @@ __global__ void __launch_bounds__(kSThreads, 1) fwd_stream_kernel(const __grid_c
                 mycode = (lane == r) ? code : mycode;
             }
             SP_ADD(7, sp_g0);                                  // second pass (general resolution, one latent at a time)
-            if (lane < 16 && wrow0 + lane < p.n) {
+            if (lane < LPW && wrow0 + lane < p.n) {
                 p.idx[wrow0 + lane] = (int64_t)mycode;
                 atomicAdd(p.stats + mycode, 1.0f);            // counts (exact integers in fp32)
             }
             loss_d += (double)loss;
             if (half == 0 && lane == 0) misc[4 + ((it + 1) & 1) * 4 + quad] = 0;   // spill buffer of the next row tile
-            named_bar_sync(1 + quad, 64);                     // the quadrant's lists are reused by the next row tile
+            named_bar_sync(1 + quad, 32 * SP);                // the quadrant's lists are reused by the next row tile
             SP_LAP(5);
         }
         if (warp == 4 && lane == 0) SP_DUMP(16);
