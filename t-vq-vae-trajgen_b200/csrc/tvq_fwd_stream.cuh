@@ -10,21 +10,20 @@
 // row on Gaussian data) are re-scored in fp32 and, if still inseparable, in fp64.  Indices are
 // therefore bit-identical to the CUDA-core path and to the C oracle.
 //
-// One persistent CTA per SM, 12 warps, warp-specialised; a row tile is 128 latents (UMMA M = 128:
+// One persistent CTA per SM, 12 or 20 warps, warp-specialised; a row tile is 128 latents (UMMA M = 128:
 // TMEM lane = latent), a code tile is NT codes (one tcgen05.mma N), d is cut into 64-column slabs:
-//   warp 0      producer: TMA (cp.async.bulk.tensor, SWIZZLE_128B) of bf16 code slabs [NT x 64]
-//               into a ring of shared-memory stages; also stages the |e|^2 slice of each code tile
-//   warp 1      MMA issuer: per code tile d/16 tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32, M = 128,
-//               N = NT) into one of 512/NT tensor-memory score slots; tcgen05.commit
-//   warps 4-11  scan + apply, TWO warps per TMEM lane quadrant (each takes half of the columns of every
-//               code tile), ONE THREAD PER LATENT: tcgen05.ld of 32 scores at a time, score =
-//               |e|^2 - 2 x.e (packed FFMA2), 3-input-min tree, running minimum m and threshold
-//               m + bound; a 32-score chunk is looked at again only if its minimum beats the threshold
-//               (rare after the first chunks): a straight-line 8-compare mask of the groups of 4 that hold
-//               a hit, then one indexed branch per hit group; the candidates go to a small per-latent list
-//               in shared memory.  After the last code tile the two warps of a quadrant merge their minima,
-//               and each resolves 16 latents (cascade above), gathers the code words, writes idx / q
-//               (straight-through) / loss partial and adds the EMA statistics (red.global.v4).
+//   warp 0      producer: TMA (cp.async.bulk.tensor, SWIZZLE_128B) of bf16 code slabs [NT x 64] of the NEGATED codebook
+//               into a ring of shared-memory stages, then, per code tile, the [NT x 16] slab of |e|^2 / 2 pieces (SWIZZLE_32B)
+//   warp 1      MMA issuer: per code tile d/16 tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32, M = 128, N = NT) plus ONE more
+//               K step — constant A rows (1, 1, 1, 0...) against the three bf16 pieces of |e_c|^2 / 2 — into one of 512/NT
+//               tensor-memory score slots: the accumulator IS the half-score |e|^2 / 2 - x.e; tcgen05.commit
+//   warps 4-..  scan + apply, SP = 2 or 4 warps per TMEM lane quadrant (each takes 1/SP of the columns of every code tile),
+//               ONE THREAD PER LATENT: tcgen05.ld of 32 scores at a time, 3-input-min tree, running minimum m and
+//               threshold m + bound; a 32-score chunk is looked at again only if its minimum beats the threshold: a
+//               straight-line 8-compare mask of the groups of 4 that hold a hit, then one indexed branch per hit group; the
+//               candidates go to a small per-latent list in shared memory.  After the last code tile the warps of a
+//               quadrant merge their minima, and each resolves 32/SP latents (cascade above), gathers the code words,
+//               writes idx / q (straight-through) / loss partial and adds the EMA statistics (red.global.v4).
 //   warps 2-3   converters: x rows fp32 (global, L2-prefetched two tiles ahead) -> bf16 A operand in
 //               UMMA K-major SWIZZLE_128B layout, double buffered; also |x| -> the row's error bound.
 // For k >= 1024 the CTAs work in PAIRS (template parameter CG = 2: 2-CTA clusters, tcgen05 cta_group::2): see
