@@ -76,6 +76,63 @@ def test_two_rank_packed_statistics_allreduce():
         assert cerr <= 1e-5
 
 
+def _sampling_worker(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import tvq_b200 as tvq
+    from tvq_b200.vq import sample_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                            # different generators AND different batches per rank
+        data = torch.randn(50 + 10 * rank, 8)
+        rows_many = sample_rows(data, 16, True)                  # randperm branch (n >= num)
+        rows_few = sample_rows(data[:5], 16, True)               # randint branch (n < num)
+        local = sample_rows(data, 16, False)                     # single-process behaviour: a rank-local draw
+        g = [torch.empty_like(rows_many) for _ in range(world)]
+        dist.all_gather(g, rows_many)
+        g2 = [torch.empty_like(rows_few) for _ in range(world)]
+        dist.all_gather(g2, rows_few)
+        # rank 0's rows must come from rank 0's own batch
+        from_rank0 = True
+        if rank == 0:
+            from_rank0 = all(bool((data == r).all(1).any()) for r in rows_many)
+        # the peer-exchange decision on a gloo group: agreed "not used", no collective entered, all_reduce path kept
+        vq = tvq.VectorQuantize(8, 16, sync_codebook=True)
+        px = vq._codebook.setup_data_parallel(torch.device("cpu"))
+        out.put((rank, bool(torch.equal(g[0], g[1])), bool(torch.equal(g2[0], g2[1])), from_rank0,
+                 bool((local == rows_many).all()), px is None and vq._codebook._px is False))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_two_rank_sampling_is_replica_consistent():
+    """k-means seeds / dead-code replacements (vq.py:67-75) under data parallelism: every rank ends with RANK 0's rows
+    (the reference draws rank-locally: replicas would diverge, SURVEY section 8 e); without DDP the draw stays local.
+    And the peer-exchange set-up on a non-NCCL group: every rank agrees on the all_reduce path."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = 29850 + (os.getpid() % 100)
+    procs = [ctx.Process(target=_sampling_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get() for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, same_many, same_few, from0, local_equals, px_off in results:
+        assert same_many and same_few, "ranks ended with different rows"
+        assert from0, "rank 0's rows are not rows of rank 0's batch"
+        assert px_off, "a gloo group must take the all_reduce path, agreed on by all ranks"
+        if rank == 1:
+            assert not local_equals, "rank 1's local draw should differ from rank 0's broadcast rows"
+
+
 def test_sync_flag_is_inert_without_a_process_group():
     import tvq_b200 as tvq
     vq = tvq.VectorQuantize(32, 16, sync_codebook=True)

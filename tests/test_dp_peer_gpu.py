@@ -71,3 +71,28 @@ def test_two_rank_peer_exchange():
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs four or more GPUs")
 def test_all_ranks_peer_exchange():
     run_worker(torch.cuda.device_count(), 29534)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_module_on_a_device_that_is_not_current(tvq):
+    """ONE process, two GPUs: a module living on cuda:1 while cuda:0 is the current device must launch on cuda:1 (the C ABI
+    works on the current device: the wrappers switch around every call) and the per-device kernel-attribute caches must
+    configure the > 48 KB shared-memory kernels on BOTH devices.  Same seeds -> bit-identical results."""
+    torch.cuda.set_device(0)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        torch.manual_seed(3)
+        vq = tvq.VectorQuantize(128, 32).to(dev).train()
+        big = tvq.VectorQuantize(64, 512).to(dev).train()             # streamed-codebook kernel (its own attribute cache)
+        g = torch.Generator().manual_seed(4)
+        x = torch.randn(8, 75, 128, generator=g).to(dev).requires_grad_(True)
+        q, ind, loss, ppl = vq(x)
+        (q.sum() + loss["loss"].sum()).backward()
+        z = torch.randn(8, 128, 3, 25, generator=g).to(dev)
+        zq, ind2, _, _ = tvq.quantize(z, vq)
+        qb, indb, _, _ = big(torch.randn(4, 300, 64, generator=g).to(dev))
+        assert torch.cuda.current_device() == 0
+        torch.cuda.synchronize(dev)
+        outs.append([t.detach().cpu() for t in (q, ind, loss["loss"], x.grad, zq, ind2, qb, indb, vq._codebook.embed, big._codebook.embed)])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

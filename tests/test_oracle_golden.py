@@ -240,3 +240,46 @@ def test_empty_batch_is_rejected_like_the_reference():
     state = O.new_state(8, 4)
     q, ind, loss, ppl = O.vq_forward(state, torch.zeros(0, 3, 4), training=False)
     assert q.shape == (0, 3, 4) and ind.shape == (0, 3) and torch.isnan(ppl)
+
+
+# ------------------------------------------------ the restatement against the LIVE reference (when it is available)
+
+def _reference():
+    try:
+        import ref_loader
+        return ref_loader.load()[0]
+    except Exception:
+        return None
+
+
+@pytest.mark.parametrize("k,d,shape,kw", [(32, 128, (4, 75, 128), {}), (512, 64, (2, 300, 64), {"decay": 0.9, "commitment_weight": 0.25}),
+                                          (16, 32, (3, 40, 32), {"threshold_ema_dead_code": 2}), (8, 16, (2, 100, 16), {"kmeans_init": True})])
+def test_oracle_equals_live_reference(k, d, shape, kw):
+    """oracle/vq_oracle.py against the UNMODIFIED timevqvae/models/vq.py (oracle/_ref, else /root/reference) on seeded inputs,
+    three training steps and one eval call: indices equal, every float output and buffer bitwise equal.  Skipped only where
+    neither copy of the reference exists."""
+    ref_vq = _reference()
+    if ref_vq is None:
+        pytest.skip("reference not available (run oracle/build_ref.py where /root/reference exists)")
+    torch.manual_seed(k + d)
+    vq = ref_vq.VectorQuantize(d, k, **kw).train()
+    cb = vq._codebook
+    okw = {kk: v for kk, v in kw.items() if kk != "kmeans_init"}
+    state = {n: getattr(cb, n).detach().clone() for n in ("initted", "cluster_size", "embed_avg", "embed")}
+    g = torch.Generator().manual_seed(5)
+    for step in range(3):
+        x = torch.randn(shape, generator=g) * (1 + step)
+        torch.manual_seed(50 + step)
+        q, ind, loss, ppl = vq(x.clone())
+        torch.manual_seed(50 + step)
+        q2, ind2, loss2, ppl2 = O.vq_forward(state, x.clone(), training=True, **okw)
+        assert torch.equal(ind, ind2)
+        assert torch.equal(q, q2) and torch.equal(loss["loss"], loss2["loss"]) and torch.equal(ppl, ppl2)
+        for n in ("cluster_size", "embed_avg", "embed", "initted"):
+            assert torch.equal(getattr(cb, n).detach(), state[n]), (step, n)
+    vq.eval()
+    x = torch.randn(shape, generator=g)
+    with torch.no_grad():
+        q, ind, loss, ppl = vq(x)
+    q2, ind2, loss2, ppl2 = O.vq_forward(state, x, training=False, **okw)
+    assert torch.equal(ind, ind2) and torch.equal(q, q2) and torch.equal(ppl, ppl2)
