@@ -59,9 +59,14 @@ constexpr int kUSlots = 4;              // TMEM score slots
 constexpr int kUMaxStages = 8;
 constexpr int kUBatch = 4;              // rows a warp keeps in flight in the apply phase
 
+#ifdef TVQ_USPLIT
+#define TVQ_USPLIT_PLAN TVQ_USPLIT
+#else
+#define TVQ_USPLIT_PLAN 1
+#endif
 struct UmmaPlan {
     int stages, stage_bytes;
-    int x, cb, e2s, hist, keys, red, misc, tiles, bars, tmem, total;
+    int x, cb, cbh, cbl, e2s, hist, keys, red, misc, tiles, bars, tmem, total;
 };
 __host__ __device__ inline UmmaPlan make_umma_plan(int dp, int kp, int stages) {
     UmmaPlan u;
@@ -69,7 +74,10 @@ __host__ __device__ inline UmmaPlan make_umma_plan(int dp, int kp, int stages) {
     u.stage_bytes = kUM * dp * 4;
     int o = 0;
     u.x = o;    o += stages * u.stage_bytes;
-    u.cb = o;   o += kp * dp * 4;
+    u.cb = o;   o += kp * dp * 4;           // exact code words (gather, re-score)
+    // k <= 32 (every training shape): the tensor core reads the code words as hi + lo (kUSplit)
+    u.cbh = o;  o += (TVQ_USPLIT_PLAN && kp <= 32) ? kp * dp * 4 : 0;   // B operand, first MMA: the code words cut to tf32 (19 leading bits)
+    u.cbl = o;  o += (TVQ_USPLIT_PLAN && kp <= 32) ? kp * dp * 4 : 0;   // B operand, second MMA: what the cut removed (exact remainder)
     u.e2s = o;  o += kp * 4;
     u.hist = o; o += kp * 4;
     o = (o + 15) & ~15;
@@ -430,6 +438,8 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
 
     const UmmaPlan pl = make_umma_plan(DP, KP, stages);
     float* cbs = reinterpret_cast<float*>(smem + pl.cb);
+    float* cbhs = reinterpret_cast<float*>(smem + pl.cbh);
+    float* cbls = reinterpret_cast<float*>(smem + pl.cbl);
     float* e2s = reinterpret_cast<float*>(smem + pl.e2s);
     int* hist = reinterpret_cast<int*>(smem + pl.hist);
     double* red = reinterpret_cast<double*>(smem + pl.red);
@@ -439,7 +449,12 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.tmem);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kUMaxStages;
     const uint32_t bar_tfull = bar_empty + 8 * kUMaxStages, bar_tempty = bar_tfull + 8 * kUSlots;
-    const uint32_t x_base = smem_u32(smem + pl.x), cb_base = smem_u32(cbs);
+#ifndef TVQ_USPLIT
+#define TVQ_USPLIT 1
+#endif
+    constexpr bool SPLIT = TVQ_USPLIT && KP <= 32;   // eval with 33..64 codes: one MMA on the exact code words (three 32 KB copies
+                                                // would leave the tile ring 4 stages, too few for the channels-first loader)
+    const uint32_t x_base = smem_u32(smem + pl.x), cbh_base = smem_u32(SPLIT ? cbhs : cbs), cbl_base = smem_u32(cbls);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunk = p.d >> 2;
@@ -498,7 +513,22 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < CB_IT; ++j) {
             const int f = tid + j * kUThreads, row = f / DPC, c4 = f % DPC;
-            if (f < KP * DPC) *reinterpret_cast<float4*>(cbs + tile_off<KP>(row, c4)) = cv[j];
+            if (f < KP * DPC) {
+                // e = hi + lo exactly: hi keeps the 19 leading bits (sign, exponent, 10 mantissa bits: what kind::tf32 reads,
+                // so its conversion is exact whether the tensor core truncates or rounds), lo is the exact remainder
+                const float4 e = cv[j];
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(e.x) & 0xFFFFE000u); lo.x = e.x - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(e.y) & 0xFFFFE000u); lo.y = e.y - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(e.z) & 0xFFFFE000u); lo.z = e.z - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(e.w) & 0xFFFFE000u); lo.w = e.w - hi.w;
+                const int off = tile_off<KP>(row, c4);
+                *reinterpret_cast<float4*>(cbs + off) = e;
+                if (SPLIT) {
+                    *reinterpret_cast<float4*>(cbhs + off) = hi;
+                    *reinterpret_cast<float4*>(cbls + off) = lo;
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < E_IT; ++j) {
@@ -516,12 +546,15 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
     float emax2 = 0.f;
     for (int c = 0; c < KP; ++c) emax2 = fmaxf(emax2, (c < p.k) ? e2s[c] : 0.f);
     const float emax = sqrtf(emax2) * 1.0001f;
-    // |(s_a - s_b) - (d_a - d_b)| <= err_p * |x| * max|e| + err_s * (|x| + max|e|)^2: tf32 operands (each within 2^-10
-    // relative, truncated or rounded) and fp32 accumulation give 2^-9 * |x| |e| on a dot product, i.e. 2^-8 on a score
-    // and 2^-7 * |x| * max|e| on a score difference (10 % slack: 8.8e-3); err_s covers the fp32 roundings of both
-    // formulas and the 6 key bits that carry the code (64 ulps).  (The product form matters once training has pulled
-    // the code words towards the data mean: |x| >> |e| makes it half of the older (|x| + max|e|)^2 / 4 form.)
-    const float err_p = 8.8e-3f * emax, err_s = 3e-5f;
+    // |(s_a - s_b) - (d_a - d_b)| <= err_p * |x| * max|e| + err_s * (|x| + max|e|)^2.  The code words enter the tensor core
+    // as hi + lo (two MMAs per K step; the pipe is ~8 % busy): hi is exact in tf32 and lo's conversion error is 2^-20 |e|,
+    // so only x carries a tf32 error (within 2^-10 relative, truncated or rounded): 2^-10 * |x| |e| on a dot product, 2^-9 on
+    // a score and 2^-8 * |x| * max|e| on a score difference (10 % slack: 4.4e-3) — HALF of what one MMA on the raw code words
+    // gives, and half as many rows leave this level (round 2: 10 % -> 5 % of Gaussian rows, 40 % -> ~20 % of trained stage-1
+    // latents).  err_s covers the fp32 accumulation (twice as many steps now), the roundings of both formulas and the 6 key
+    // bits that carry the code (64 ulps).
+    // (!SPLIT: both operands carry a tf32 error: 2^-7 * |x| * max|e|, 8.8e-3 with the slack.)
+    const float err_p = (SPLIT ? 4.4e-3f : 8.8e-3f) * emax, err_s = 3e-5f;
 
     float loss = 0.f;
     unsigned counters = 0;                                // low 16 bits: re-scored rows, high: fp64 rows
@@ -606,9 +639,11 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < NSLAB; ++j)
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_tf32(tmem_base + slot * KP, umma_desc_sw128(a0 + j * SLAB_X + kk * 32),
-                                  umma_desc_sw128(cb_base + j * SLAB_CB + kk * 32), idesc, (j | kk) != 0);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t adesc = umma_desc_sw128(a0 + j * SLAB_X + kk * 32);
+                        umma_tf32(tmem_base + slot * KP, adesc, umma_desc_sw128(cbh_base + j * SLAB_CB + kk * 32), idesc, (j | kk) != 0);
+                        if (SPLIT) umma_tf32(tmem_base + slot * KP, adesc, umma_desc_sw128(cbl_base + j * SLAB_CB + kk * 32), idesc, 1u);
+                    }
                 umma_commit(bar_tfull + 8 * slot);
             }
         }
