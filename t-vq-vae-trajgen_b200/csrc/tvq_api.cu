@@ -276,10 +276,11 @@ int launch_fwd_stream_impl(FwdParams p, const void* cbh, const void* e2h, const 
     if (rc != TVQ_OK) return rc;
     if ((rc = make_e2_tensor_map(&tm2, e2h, p.k, NT / CG)) != TVQ_OK) return rc;
     p.num_tiles = (int)((p.n + kSM - 1) / kSM);
+    const __nv_bfloat16* e2h_bf = reinterpret_cast<const __nv_bfloat16*>(e2h);
     const int groups = (p.num_tiles + CG - 1) / CG, units = di.sm_count / CG;
     const int grid = CG * (groups < units ? groups : units);
     if (CG == 1) {
-        kern<<<grid, kSThreads, pl.total, stream>>>(tm, tm2, p, stages);
+        kern<<<grid, kSThreads, pl.total, stream>>>(tm, tm2, p, stages, e2h_bf);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
@@ -291,7 +292,7 @@ int launch_fwd_stream_impl(FwdParams p, const void* cbh, const void* e2h, const 
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, tm2, p, stages);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, tm2, p, stages, e2h_bf);
         if (e != cudaSuccess) return (int)e;
     }
     return launch_status();

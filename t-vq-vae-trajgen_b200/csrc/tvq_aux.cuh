@@ -29,13 +29,30 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ cb,
             e2c = __double2float_rn(canon_dot_global(er, er, d >> 2, lane));
         }
         if (lane == 0) e2[c] = e2c;
+        // |e_c - bf16(e_c)|^2, rounded UP to a bf16: the streamed kernel's error bound uses the ACTUAL rounding error of
+        // its bf16 operands (max over codes), not the worst case 2^-9 |e|.  It travels in column 3 of the |e|^2 / 2 slab,
+        // where the constant A rows of that K step hold a zero (0 x finite = 0).
+        float de2c = 0.f;
+        if (e2h != nullptr && c < k) {
+            const float4* er4 = reinterpret_cast<const float4*>(cb + (size_t)c * d);
+            for (int c4 = lane; c4 < (d >> 2); c4 += 32) {
+                const float4 v = __ldg(er4 + c4);
+                const float tx = v.x - __bfloat162float(__float2bfloat16_rn(v.x)), ty = v.y - __bfloat162float(__float2bfloat16_rn(v.y));
+                const float tz = v.z - __bfloat162float(__float2bfloat16_rn(v.z)), tw = v.w - __bfloat162float(__float2bfloat16_rn(v.w));
+                de2c = fmaf(tx, tx, fmaf(ty, ty, fmaf(tz, tz, fmaf(tw, tw, de2c))));
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) de2c += __shfl_xor_sync(0xffffffffu, de2c, off);
+            de2c = fminf(de2c * 1.0001f, 3e38f);
+            if (!(de2c >= 0.f)) de2c = 3e38f;                            // NaN code word: the latent bound becomes huge, never NaN x 0
+        }
         if (e2h != nullptr && lane < 16) {
             const float v = 0.5f * e2c;                                  // exact
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             const float r1 = v - __bfloat162float(h);                    // exact (Sterbenz-like: h is v rounded to 8 bits)
             const __nv_bfloat16 m = __float2bfloat16_rn(r1);
             const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
-            e2h[(size_t)c * 16 + lane] = lane == 0 ? h : lane == 1 ? m : lane == 2 ? l : __float2bfloat16_rn(0.f);
+            e2h[(size_t)c * 16 + lane] = lane == 0 ? h : lane == 1 ? m : lane == 2 ? l : lane == 3 ? __float2bfloat16_ru(de2c) : __float2bfloat16_rn(0.f);
         }
     }
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

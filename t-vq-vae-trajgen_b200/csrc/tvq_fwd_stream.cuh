@@ -81,7 +81,7 @@ constexpr int kSScratch = kSMaxParts * kSCand + kSOvf;   // merged candidate lis
 
 struct StreamPlan {
     int stages, stage_bytes, a_bytes;
-    int a, b, aone, brow, cs, cc, drop, mfin, ncnt, ovf, scratch, red, misc, bars, tmem, total;
+    int a, b, aone, brow, cs, cc, drop, mfin, mshare, ncnt, ovf, scratch, red, misc, bars, tmem, total;
 };
 __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages, int cg = 1, int sp = 2) {
     StreamPlan u;
@@ -97,6 +97,7 @@ __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stage
     u.cc = o;    o += sp * kSCand * kSM * 4;
     u.drop = o;  o += 2 * sp * kSM * 4;      // [part][spillmin | dropmin][latent]
     u.mfin = o;  o += sp * kSM * 4;
+    u.mshare = o; o += sp * kSM * 4;     // running minimum of every scan part, read by the other parts of the quadrant
     u.ncnt = o;  o += sp * kSM * 4;
     u.ovf = o;   o += 2 * 4 * kSOvf * 12;       // [row-tile parity][quadrant]: rows | scores | codes
     u.scratch = o; o += kSScratch * 4 * sp * 4;   // per scan warp
@@ -228,11 +229,14 @@ __device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) {
 }
 }  // namespace sm100
 
-// Bound on |(s_a - s_b) - (d_a - d_b) / 2| for one latent, s = the tensor-core half-scores |e|^2 / 2 - x.e (bf16 operands,
-// fp32 accumulation incl. the |e|^2 / 2 step), d = the canonical distances: half of DESIGN section 4's bf16 bound, the
-// second term widened (2e-6 -> 3e-6) for the one more accumulation the tensor core now does.
-__device__ __forceinline__ float stream_bound(const float xn, const float emax, const float sum) {
-    return 0.5f * fmaf(0.0172f * xn, emax, 3e-6f * sum * sum);
+// Bound on |(s_a - s_b) - (d_a - d_b) / 2| for one latent, s = the tensor-core half-scores |e|^2 / 2 - x^.e^ (x^, e^ the
+// bf16 operands; fp32 accumulation incl. the |e|^2 / 2 step), d = the canonical distances.  The operand term uses the
+// ACTUAL rounding errors instead of the worst case 2^-9 per operand: x.e - x^.e^ = (x - x^).e + x^.(e - e^), so
+// |.| <= |x - x^| max|e| + (|x| + |x - x^|) max|e - e^|, twice that on a score difference.  |x - x^| is measured by the
+// converter for every latent, max|e - e^| by the preparation kernel: ~0.4 * 2^-9 relative each on real data — a bound
+// 2.5 times tighter than the worst-case form, as rigorous.  Second term: fp32 roundings (accumulation, canonical rule).
+__device__ __forceinline__ float stream_bound(const float xn, const float dxn, const float emax, const float demax, const float sum) {
+    return fmaf(2.002f, fmaf(dxn, emax, (xn + dxn) * demax), 1.5e-6f * sum * sum);
 }
 
 // Spill buffer of one TMEM lane quadrant for the current row tile (shared memory).
@@ -325,6 +329,16 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], const int co
             if (d <= thr) { ls[st.cnt * kSM] = d; lc[st.cnt * kSM] = cb + 3; ++st.cnt; }
         }
     }
+}
+
+// Minimum of one chunk of 32 scores (the seed pass: no candidates are recorded).
+__device__ __forceinline__ float chunk_min(const uint32_t (&r)[32]) {
+    using namespace sm100;
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        g[i] = fminf(fmin3(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2])), __uint_as_float(r[4 * i + 3]));
+    return fmin3(fmin3(g[0], g[1], g[2]), fmin3(g[3], g[4], g[5]), fminf(g[6], g[7]));
 }
 
 // Straight-through output, commitment-loss partial, EMA statistics and q store of ONE latent
@@ -469,7 +483,7 @@ __device__ __forceinline__ int gather_cands(int* list, const int (&cnts)[SP], co
 template <int DP, int NT, bool TRAIN, int CG, int SP>
 __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_cb,
                                                                  const __grid_constant__ CUtensorMap tmap_e2, const FwdParams p,
-                                                                 const int stages) {
+                                                                 const int stages, const __nv_bfloat16* __restrict__ e2h) {
     using namespace sm100;
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int KSLABS = DP / 64;             // 64-column (128-byte) bf16 slabs per row
@@ -491,6 +505,7 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
     float* cand_s = reinterpret_cast<float*>(smem + pl.cs);     // [part][slot][latent]
     int* cand_c = reinterpret_cast<int*>(smem + pl.cc);
     float* mfin = reinterpret_cast<float*>(smem + pl.mfin);     // [half][latent] minimum seen by each scan half
+    volatile float* mshare = reinterpret_cast<volatile float*>(smem + pl.mshare);   // [part][latent] running minimum, live
     int* ncnt = reinterpret_cast<int*>(smem + pl.ncnt);         // [half][latent] final candidates per half (-1: incomplete)
     int* ovf_base = reinterpret_cast<int*>(smem + pl.ovf);      // [parity][quadrant][rows | scores | codes][kSOvf]
     int* scratch_base = reinterpret_cast<int*>(smem + pl.scratch);
@@ -536,20 +551,27 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
     }
     if (CG == 2) fence_proxy_async_all(); else fence_proxy_async_smem();
     // max |e| (error-bound constant): every CTA scans the |e|^2 table (k floats, L2 resident)
-    float emax2 = 0.f;
-    for (int c = tid; c < p.k; c += kSThreads) emax2 = fmaxf(emax2, __ldg(p.e2 + c));
+    float emax2 = 0.f, dmax2 = 0.f;
+    for (int c = tid; c < p.k; c += kSThreads) {
+        emax2 = fmaxf(emax2, __ldg(p.e2 + c));
+        dmax2 = fmaxf(dmax2, __bfloat162float(e2h[(size_t)c * 16 + 3]));    // |e_c - bf16(e_c)|^2 (prep_kernel)
+    }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) emax2 = fmaxf(emax2, __shfl_xor_sync(0xffffffffu, emax2, off));
+    for (int off = 16; off >= 1; off >>= 1) {
+        emax2 = fmaxf(emax2, __shfl_xor_sync(0xffffffffu, emax2, off));
+        dmax2 = fmaxf(dmax2, __shfl_xor_sync(0xffffffffu, dmax2, off));
+    }
     float* wmax = reinterpret_cast<float*>(red);
-    if (lane == 0) wmax[warp] = emax2;
+    if (lane == 0) { wmax[warp] = emax2; wmax[32 + warp] = dmax2; }
     tc_fence_before();
     __syncthreads();
     if (CG == 2) cluster_sync_all();                      // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    emax2 = 0.f;
-    for (int w = 0; w < kSThreads / 32; ++w) emax2 = fmaxf(emax2, wmax[w]);
+    emax2 = 0.f; dmax2 = 0.f;
+    for (int w = 0; w < kSThreads / 32; ++w) { emax2 = fmaxf(emax2, wmax[w]); dmax2 = fmaxf(dmax2, wmax[32 + w]); }
     const float emax = sqrtf(emax2) * 1.0001f;
+    const float demax = sqrtf(dmax2) * 1.0001f;
     __syncthreads();                                      // wmax (aliases red) is free again
 
     double loss_d = 0.0;
@@ -678,7 +700,7 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (grow < p.n && c4 < nchunk) v[u] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)grow * p.d) + c4);
                 }
-                float ssq[U];
+                float ssq[U], dsq[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int f = (i0 + u) * 32 + lane;
@@ -690,39 +712,52 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                                           ((((uint32_t)(c4 & 15) >> 1) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)(c4 & 1) << 3);
                     sts_v2(addr, *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
                     ssq[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
+                    // |x - bf16(x)|^2 of the chunk (the differences are exact in fp32)
+                    const float2 blo = __bfloat1622float2(lo), bhi = __bfloat1622float2(hi);
+                    const float ex = v[u].x - blo.x, ey = v[u].y - blo.y, ez = v[u].z - bhi.x, ew = v[u].w - bhi.y;
+                    dsq[u] = fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, ew * ew)));
                 }
                 // row norms -> bound of |(s_a - s_b) - (d_a - d_b)| for this latent
                 if constexpr (F == 64) {
 #pragma unroll
                     for (int u = 0; u < U; u += 2) {
-                        float t = ssq[u] + ssq[u + 1];
+                        float t = ssq[u] + ssq[u + 1], td = dsq[u] + dsq[u + 1];
 #pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            t += __shfl_xor_sync(0xffffffffu, t, off);
+                            td += __shfl_xor_sync(0xffffffffu, td, off);
+                        }
                         if (lane == 0) {
-                            const float xn = sqrtf(t) * 1.0001f, sum = xn + emax;
-                            brow[rowbase + (i0 + u) / 2] = stream_bound(xn, emax, sum);
+                            const float xn = sqrtf(t) * 1.0001f, dxn = sqrtf(td) * 1.0001f, sum = xn + emax;
+                            brow[rowbase + (i0 + u) / 2] = stream_bound(xn, dxn, emax, demax, sum);
                         }
                     }
                 } else if constexpr (F == 32) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        float t = ssq[u];
+                        float t = ssq[u], td = dsq[u];
 #pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            t += __shfl_xor_sync(0xffffffffu, t, off);
+                            td += __shfl_xor_sync(0xffffffffu, td, off);
+                        }
                         if (lane == 0) {
-                            const float xn = sqrtf(t) * 1.0001f, sum = xn + emax;
-                            brow[rowbase + i0 + u] = stream_bound(xn, emax, sum);
+                            const float xn = sqrtf(t) * 1.0001f, dxn = sqrtf(td) * 1.0001f, sum = xn + emax;
+                            brow[rowbase + i0 + u] = stream_bound(xn, dxn, emax, demax, sum);
                         }
                     }
                 } else {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        float t = ssq[u];
+                        float t = ssq[u], td = dsq[u];
 #pragma unroll
-                        for (int off = 8; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                        for (int off = 8; off >= 1; off >>= 1) {
+                            t += __shfl_xor_sync(0xffffffffu, t, off);
+                            td += __shfl_xor_sync(0xffffffffu, td, off);
+                        }
                         if ((lane & 15) == 0) {
-                            const float xn = sqrtf(t) * 1.0001f, sum = xn + emax;
-                            brow[rowbase + 2 * (i0 + u) + (lane >> 4)] = stream_bound(xn, emax, sum);
+                            const float xn = sqrtf(t) * 1.0001f, dxn = sqrtf(td) * 1.0001f, sum = xn + emax;
+                            brow[rowbase + 2 * (i0 + u) + (lane >> 4)] = stream_bound(xn, dxn, emax, demax, sum);
                         }
                     }
                 }
@@ -778,12 +813,45 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                 ob.s = reinterpret_cast<float*>(ob0 + kSOvf);
                 ob.c = ob0 + 2 * kSOvf;
             }
-            // ---- scan: this warp's half of the columns of every code tile
+            // ---- seed: the minimum over the FIRST code tile (all parts of the quadrant), before anything is recorded.  A
+            //      running minimum that starts at +inf makes every early score a "new record": with k codes a latent sets
+            //      ~ln k of them, and with 32 latents per warp nearly every chunk took the candidate path.  Seeded, the first
+            //      tile records only what lies within the bound of its own minimum, and a later chunk at position n is
+            //      entered with probability ~32 / n per latent.
+            {
+                const int slot = et % SLOTS;
+                SP_WAIT(2, bar_tfull + 8 * slot, ((uint32_t)(et / SLOTS)) & 1u);
+                tc_fence_after();
+                SP_RESET();
+                const uint32_t taddr = lane_addr + (uint32_t)(slot * NT);
+                uint32_t ra[32], rb[32];
+                float mp = INF;
+#pragma unroll 1
+                for (int c = 0; c < NCH; c += 2) {
+                    tmem_ld_x32(taddr + (uint32_t)c * 32u, ra);
+                    if (c + 1 < NCH) tmem_ld_x32(taddr + (uint32_t)(c + 1) * 32u, rb);
+                    tmem_ld_wait();
+                    mp = fminf(mp, chunk_min(ra));
+                    if (c + 1 < NCH) mp = fminf(mp, chunk_min(rb));
+                }
+                mshare[half * kSM + trow] = mp;
+                named_bar_sync(1 + quad, 32 * SP);
+#pragma unroll
+                for (int pt = 0; pt < SP; ++pt) st.m = fminf(st.m, mshare[pt * kSM + trow]);
+                SP_LAP(3);
+            }
+            // ---- scan: this warp's part of the columns of every code tile.  The parts of a quadrant share their running
+            //      minima (any score of the latent is a valid upper bound of its minimum; a stale value only costs a
+            //      candidate that the final filter drops), exchanged once per code tile through shared memory.
             for (int ct = 0; ct < n_ct; ++ct, ++et) {
                 const int slot = et % SLOTS;
                 SP_WAIT(2, bar_tfull + 8 * slot, ((uint32_t)(et / SLOTS)) & 1u);
                 tc_fence_after();
                 SP_RESET();
+                if (ct > 0) {
+#pragma unroll
+                    for (int pt = 0; pt < SP; ++pt) st.m = fminf(st.m, mshare[pt * kSM + trow]);
+                }
                 const uint32_t taddr = lane_addr + (uint32_t)(slot * NT);
                 const int code0 = ct * NT + half * (NT / SP);
                 uint32_t ra[32], rb[32];
@@ -807,6 +875,7 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                 if (lane == 0) {
                     if (CG == 2) mbar_arrive_leader_nodata(bar_tempty + 8 * slot); else mbar_arrive(bar_tempty + 8 * slot);
                 }
+                mshare[half * kSM + trow] = st.m;
                 SP_LAP(3);
             }
             SP_RESET();

@@ -1,0 +1,4 @@
+for v in "" noslow noslow_nomma; do
+for s in "1048576 512 64" "1048576 4096 128" "524288 16384 256"; do
+  timeout 120 python tools/profile_stream.py run $s 1 $v 2>&1 | grep -v Warn
+done; done
