@@ -260,15 +260,25 @@ int make_cb_tensor_map(CUtensorMap* tm, const void* cbh, int k, int dp, int nt) 
     return r == CUDA_SUCCESS ? TVQ_OK : TVQ_ERR_BAD_ARG;
 }
 
-template <int DP, int NT, bool TRAIN, int CG, int SP>
+template <int DP, int NT, bool TRAIN, int CG, int SP, int SETS = 1>
 int launch_fwd_stream_impl(FwdParams p, const void* cbh, const void* e2h, const DeviceInfo& di, cudaStream_t stream) {
-    auto kern = fwd_stream_kernel<DP, NT, TRAIN, CG, SP>;
-    constexpr int kSThreads = stream_threads(SP);
-    const StreamPlan fixed = make_stream_plan(DP, NT, 0, CG, SP);
+    auto kern = fwd_stream_kernel<DP, NT, TRAIN, CG, SP, SETS>;
+    constexpr int kSThreads = stream_threads(SP * SETS);
+    // staged x blocks for the converter (d <= 128): 3 blocks of 8 KB per converter warp at d <= 64, 2 at d <= 128;
+    // TVQ_STREAM_XD=0..4 in the environment overrides (experiments)
+    static int forced_xd = -2;
+    if (forced_xd == -2) {
+        const char* e = getenv("TVQ_STREAM_XD");
+        forced_xd = e ? atoi(e) : -1;
+    }
+    int xdepth = DP == 64 ? 3 : DP == 128 ? 2 : 0;
+    if (forced_xd >= 0 && forced_xd <= kSXMaxDepth && DP <= 128) xdepth = forced_xd;
+    if (DP <= 128 && xdepth < 2) xdepth = 2;     // the staged converter path is compiled in for d <= 128
+    const StreamPlan fixed = make_stream_plan(DP, NT, 0, CG, SP * SETS, xdepth);
     int stages = (di.max_smem_optin - fixed.total) / ((NT / CG) * 128);
     if (stages > kSMaxStages) stages = kSMaxStages;
     if (stages < 2) return TVQ_ERR_UNSUPPORTED;
-    const StreamPlan pl = make_stream_plan(DP, NT, stages, CG, SP);
+    const StreamPlan pl = make_stream_plan(DP, NT, stages, CG, SP * SETS, xdepth);
     static PerDeviceInt configured_smem(-1);
     if (int rc = ensure_dynamic_smem(kern, configured_smem, di.index, pl.total)) return rc;
     CUtensorMap tm, tm2;
@@ -280,7 +290,7 @@ int launch_fwd_stream_impl(FwdParams p, const void* cbh, const void* e2h, const 
     const int groups = (p.num_tiles + CG - 1) / CG, units = di.sm_count / CG;
     const int grid = CG * (groups < units ? groups : units);
     if (CG == 1) {
-        kern<<<grid, kSThreads, pl.total, stream>>>(tm, tm2, p, stages, e2h_bf);
+        kern<<<grid, kSThreads, pl.total, stream>>>(tm, tm2, p, stages, e2h_bf, xdepth);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
@@ -292,7 +302,7 @@ int launch_fwd_stream_impl(FwdParams p, const void* cbh, const void* e2h, const 
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, tm2, p, stages, e2h_bf);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, tm2, p, stages, e2h_bf, xdepth);
         if (e != cudaSuccess) return (int)e;
     }
     return launch_status();
@@ -325,9 +335,26 @@ inline int stream_sp(const FwdParams& p) {
     return (p.d <= 64 || p.k >= 2048) ? 4 : 2;
 }
 
+// Two scan / apply sets (tvq_fwd_stream.cuh, d <= 128) are an experiment: measured slower than one set at every shape of the
+// sweep (the halved code tile doubles the issuer's and the scan's per-tile overheads); TVQ_STREAM_SETS=2 selects them.
+inline int stream_sets(const FwdParams& p) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("TVQ_STREAM_SETS");
+        forced = e ? atoi(e) : 0;
+    }
+    if (p.d > 128) return 1;
+    return forced == 2 ? 2 : 1;
+}
+
 template <bool TRAIN>
 int dispatch_fwd_stream(const FwdParams& p, const void* cbh, const void* e2h, const DeviceInfo& di, cudaStream_t s) {
     const int cg = stream_cg(p), sp = stream_sp(p);
+    if (stream_sets(p) == 2) {
+        if (stream_dp(p.d) == 64)
+            return cg == 2 ? launch_fwd_stream_impl<64, 128, TRAIN, 2, 2, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<64, 128, TRAIN, 1, 2, 2>(p, cbh, e2h, di, s);
+        return cg == 2 ? launch_fwd_stream_impl<128, 128, TRAIN, 2, 2, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<128, 128, TRAIN, 1, 2, 2>(p, cbh, e2h, di, s);
+    }
     switch (stream_dp(p.d)) {
         case 64:
             if (sp == 4) return cg == 2 ? launch_fwd_stream_impl<64, 256, TRAIN, 2, 4>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<64, 256, TRAIN, 1, 4>(p, cbh, e2h, di, s);

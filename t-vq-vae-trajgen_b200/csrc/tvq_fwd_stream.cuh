@@ -73,17 +73,19 @@ constexpr int kSM = 128;                 // latents per row tile
 __host__ __device__ constexpr int stream_threads(int sp) { return 128 + 128 * sp; }
 constexpr int kSCvtWarps = 2;            // converter warps (64 latents each)
 constexpr int kSMaxParts = 4;
-constexpr int kSCand = 12;               // candidate slots per latent and scan part
+constexpr int kSCand = 8;                // candidate slots per latent and scan part (the running minimum is seeded: lists stay short)
+constexpr int kSXBlock = 8192;           // bytes of one staged x block (converter input, bulk-copied)
+constexpr int kSXMaxDepth = 4;           // staged blocks per converter warp, at most
 constexpr int kSBrowRing = 4;            // row-bound buffers (converter runs up to 2 tiles ahead of the scan)
-constexpr int kSMaxStages = 8;
+constexpr int kSMaxStages = 12;
 constexpr int kSOvf = 32;                // spill entries per quadrant and row tile (beyond that: exhaustive scan)
 constexpr int kSScratch = kSMaxParts * kSCand + kSOvf;   // merged candidate list of one latent (general resolution path)
 
 struct StreamPlan {
     int stages, stage_bytes, a_bytes;
-    int a, b, aone, brow, cs, cc, drop, mfin, mshare, ncnt, ovf, scratch, red, misc, bars, tmem, total;
+    int a, b, xs, aone, brow, cs, cc, drop, mfin, mshare, ncnt, ovf, scratch, red, misc, bars, tmem, total;
 };
-__host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages, int cg = 1, int sp = 2) {
+__host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages, int cg = 1, int sp = 2, int xdepth = 0) {
     StreamPlan u;
     u.stages = stages;
     u.stage_bytes = (nt / cg) * 128;     // this CTA's share of a code slab: NT/cg codes x 64 bf16
@@ -91,8 +93,9 @@ __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stage
     int o = 0;
     u.a = o;     o += 2 * u.a_bytes;
     u.b = o;     o += stages * u.stage_bytes;
+    u.xs = o;    o += kSCvtWarps * xdepth * kSXBlock;   // staged x blocks: [converter warp][xdepth]
     u.aone = o;  o += kSM * 32;          // constant A block of the |e|^2 step: 128 rows x 16 bf16, SWIZZLE_32B (256-byte aligned)
-    u.brow = o;  o += kSBrowRing * kSM * 4;
+    u.brow = o;  o += kSBrowRing * kSM * 8;     // per row: |x|^2, |x - bf16(x)|^2
     u.cs = o;    o += sp * kSCand * kSM * 4;
     u.cc = o;    o += sp * kSCand * kSM * 4;
     u.drop = o;  o += 2 * sp * kSM * 4;      // [part][spillmin | dropmin][latent]
@@ -103,7 +106,7 @@ __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stage
     u.scratch = o; o += kSScratch * 4 * sp * 4;   // per scan warp
     u.red = o;   o += 32 * 8;
     u.misc = o;  o += 16 * 4;
-    u.bars = o;  o += (2 * kSMaxStages + 4 + 8 + 2 * kSBrowRing) * 8;
+    u.bars = o;  o += (2 * kSMaxStages + 4 + 8 + 2 * kSBrowRing + kSCvtWarps * kSXMaxDepth) * 8;
     u.tmem = o;  o += 16;
     u.total = o;
     return u;
@@ -480,19 +483,27 @@ __device__ __forceinline__ int gather_cands(int* list, const int (&cnts)[SP], co
 // every code slab: the even CTA issues one M = 256 MMA for both, which reads the A rows and the B half of each
 // CTA from that CTA's shared memory.  Per SM this halves the TMA fill and the L2 traffic of the code stream and
 // takes a third off the shared-memory operand reads.
-template <int DP, int NT, bool TRAIN, int CG, int SP>
-__global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_cb,
+// SETS = 2 (d <= 128): the scan / apply warps form TWO sets of 4 x SP warps; set s takes the row tiles with it % 2 == s
+// and owns half of the tensor-memory score slots.  While one set resolves and applies its row tile (L2 round trips, no
+// tensor-memory reads) the MMA issuer already fills the other set's slots and that set scans: the apply phase no longer
+// stalls the tensor pipe (it used to: 14 k of 64 k clocks per row tile at 4096 x 128).  Storage is indexed by set * SP + part.
+template <int DP, int NT, bool TRAIN, int CG, int SP, int SETS>
+__global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_cb,
                                                                  const __grid_constant__ CUtensorMap tmap_e2, const FwdParams p,
-                                                                 const int stages, const __nv_bfloat16* __restrict__ e2h) {
+                                                                 const int stages, const __nv_bfloat16* __restrict__ e2h, const int xdepth) {
     using namespace sm100;
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int KSLABS = DP / 64;             // 64-column (128-byte) bf16 slabs per row
     constexpr int SLOTS = 512 / NT;             // tensor-memory score slots
+    constexpr int SLOTS_S = SLOTS / SETS;       // ... of one set
     constexpr int NCH = NT / (32 * SP);         // 32-score chunks per code tile AND scan part
-    constexpr int kSThreads = stream_threads(SP);
-    constexpr int kSScanWarps = 4 * SP;
+    constexpr int kSThreads = stream_threads(SP * SETS);
+    constexpr int kSetWarps = 4 * SP;           // scan / apply warps of one set
     constexpr int LPW = 32 / SP;                // latents per warp in the apply phase
+    constexpr bool WG_REGS = SP * SETS == 4;    // 20 warps: registers shared out by warpgroup (setmaxnreg)
     static_assert(SP == 2 || SP == 4, "two or four scan parts per quadrant");
+    static_assert(SETS == 1 || SETS == 2, "one or two scan / apply sets");
+    static_assert(SLOTS_S >= 2, "at least two score slots per set");
     static_assert(NCH >= 1, "at least one chunk per part");
     constexpr int F = DP / 4;                   // 16-byte fp32 chunks per padded row
     constexpr int NV = DP > 128 ? 2 : 1;        // 16-byte chunks per lane in the warp-per-latent phases
@@ -500,8 +511,8 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
     static_assert(DP == 64 || DP == 128 || DP == 256, "d padded to 64, 128 or 256");
     static_assert(NT == 128 || NT == 256, "code tile of 128 or 256");
 
-    const StreamPlan pl = make_stream_plan(DP, NT, stages, CG, SP);
-    float* brow_ring = reinterpret_cast<float*>(smem + pl.brow);
+    const StreamPlan pl = make_stream_plan(DP, NT, stages, CG, SP * SETS, xdepth);
+    float2* brow_ring = reinterpret_cast<float2*>(smem + pl.brow);
     float* cand_s = reinterpret_cast<float*>(smem + pl.cs);     // [part][slot][latent]
     int* cand_c = reinterpret_cast<int*>(smem + pl.cc);
     float* mfin = reinterpret_cast<float*>(smem + pl.mfin);     // [half][latent] minimum seen by each scan half
@@ -517,6 +528,7 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
     const uint32_t bar_afull = bar_bempty + 8 * kSMaxStages, bar_aempty = bar_afull + 16;
     const uint32_t bar_tfull = bar_aempty + 16, bar_tempty = bar_tfull + 32;
     const uint32_t bar_rfull = bar_tempty + 32, bar_rempty = bar_rfull + 8 * kSBrowRing;
+    const uint32_t bar_xfull = bar_rempty + 8 * kSBrowRing;   // [converter warp][kSXMaxDepth]
     const uint32_t a_base = smem_u32(smem + pl.a), b_base = smem_u32(smem + pl.b), aone_base = smem_u32(smem + pl.aone);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -534,8 +546,9 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
     if (tid == 0) {
         for (int s = 0; s < kSMaxStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, CG * kSCvtWarps); mbar_init(bar_aempty + 8 * s, 1); }
-        for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, CG * kSScanWarps); }
-        for (int s = 0; s < kSBrowRing; ++s) { mbar_init(bar_rfull + 8 * s, kSCvtWarps); mbar_init(bar_rempty + 8 * s, kSScanWarps); }
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, CG * kSetWarps); }
+        for (int s = 0; s < kSBrowRing; ++s) { mbar_init(bar_rfull + 8 * s, kSCvtWarps); mbar_init(bar_rempty + 8 * s, kSetWarps); }
+        for (int s = 0; s < kSCvtWarps * kSXMaxDepth; ++s) mbar_init(bar_xfull + 8 * s, 1);
         fence_mbar_init();
         tma_prefetch_desc(&tmap_cb);
         tma_prefetch_desc(&tmap_e2);
@@ -581,93 +594,145 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
     // issuer / converter warpgroup, 104 for the scan / apply warpgroups (setmaxnreg at the head of each branch, so that the
     // register allocator sees it dominate the branch)
     if (warp < 4) {
-    if (SP == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (WG_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
         // ============================================================ producer: code slabs (TMA) + |e|^2 slices
         // per code tile: KSLABS slabs of the (negated) bf16 codebook, then the |e|^2 / 2 slab [NT x 16 bf16] (its table in the
-        // workspace is padded with BIG to a multiple of 256 codes, so codes >= k can never be nominated)
-        if (lane == 0) {
+        // workspace is padded with BIG to a multiple of 256 codes, so codes >= k can never be nominated).
+        // The whole warp walks the loop (warp-uniform control flow keeps the counters in uniform registers); one elected
+        // lane issues.  Stage index and phase are carried, not divided out of a running counter.
+        {
+            const bool leader = elect_one();
             SP_DECL;
-            int ib = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (int grp = unit0; grp < ngroups; grp += nunits) {
                 for (int ct = 0; ct < n_ct; ++ct) {
-                    for (int j = 0; j <= KSLABS; ++j, ++ib) {
-                        const int s = ib % stages;
+#pragma unroll 1
+                    for (int j = 0; j <= KSLABS; ++j) {
                         const uint32_t bytes = j < KSLABS ? (uint32_t)(NT * 128) : (uint32_t)(NT * 32);
                         const CUtensorMap* tm = j < KSLABS ? &tmap_cb : &tmap_e2;
                         const int c0 = j < KSLABS ? j * 64 : 0;
-                        SP_WAIT(1, bar_bempty + 8 * s, (((uint32_t)(ib / stages)) & 1u) ^ 1u);
-                        if (CG == 2) {
-                            // the even CTA's barrier counts the bytes of both halves; each CTA fetches its half
-                            if (crank == 0) mbar_arrive_expect_tx(bar_bfull + 8 * s, bytes);
-                            tma_load_2d_pair(b_base + s * pl.stage_bytes, tm, bar_bfull + 8 * s, c0, ct * NT + crank * (NT / 2));
-                        } else {
-                            mbar_arrive_expect_tx(bar_bfull + 8 * s, bytes);
-                            tma_load_2d(b_base + s * pl.stage_bytes, tm, bar_bfull + 8 * s, c0, ct * NT);
+                        SP_WAIT(1, bar_bempty + 8 * s, ph ^ 1u);
+                        if (leader) {
+                            if (CG == 2) {
+                                // the even CTA's barrier counts the bytes of both halves; each CTA fetches its half
+                                if (crank == 0) mbar_arrive_expect_tx(bar_bfull + 8 * s, bytes);
+                                tma_load_2d_pair(b_base + s * pl.stage_bytes, tm, bar_bfull + 8 * s, c0, ct * NT + crank * (NT / 2));
+                            } else {
+                                mbar_arrive_expect_tx(bar_bfull + 8 * s, bytes);
+                                tma_load_2d(b_base + s * pl.stage_bytes, tm, bar_bfull + 8 * s, c0, ct * NT);
+                            }
                         }
+                        __syncwarp();
+                        if (++s == stages) { s = 0; ph ^= 1u; }
                     }
                 }
             }
             SP_LAP(7);
-            SP_DUMP(0);
+            if (lane == 0) SP_DUMP(0);
         }
     } else if (warp == 1) {
-        // ============================================================ MMA issuer
-        if (lane == 0 && crank == 0) {
+        // ============================================================ MMA issuer (the even CTA of a pair issues for both)
+        if (crank == 0) {
+            const bool leader = elect_one();
             constexpr uint32_t idesc = umma_idesc_bf16(CG * kSM, NT);
             SP_DECL;
-            int ib = 0, tt = 0, it = 0;
+            int s = 0, it = 0;
+            uint32_t ph = 0;
+            int tts0 = 0, tts1 = 0;                           // code tiles issued for each set
             for (int grp = unit0; grp < ngroups; grp += nunits, ++it) {
                 const int ab = it & 1;
+                const int set = SETS == 2 ? (it & 1) : 0;
                 SP_WAIT(0, bar_afull + 8 * ab, ((uint32_t)(it >> 1)) & 1u);
                 tc_fence_after();
                 const uint32_t a0 = a_base + ab * pl.a_bytes;
-                for (int ct = 0; ct < n_ct; ++ct, ++tt) {
-                    const int slot = tt % SLOTS;
-                    SP_WAIT(1, bar_tempty + 8 * slot, (((uint32_t)(tt / SLOTS)) & 1u) ^ 1u);
+                for (int ct = 0; ct < n_ct; ++ct) {
+                    const int tt = set == 0 ? tts0++ : tts1++;
+                    const int slot = set * SLOTS_S + tt % SLOTS_S;
+                    SP_WAIT(1, bar_tempty + 8 * slot, (((uint32_t)(tt / SLOTS_S)) & 1u) ^ 1u);
                     tc_fence_after();
 #pragma unroll 1
-                    for (int j = 0; j <= KSLABS; ++j, ++ib) {
-                        const int s = ib % stages;
-                        SP_WAIT(2, bar_bfull + 8 * s, ((uint32_t)(ib / stages)) & 1u);
+                    for (int j = 0; j <= KSLABS; ++j) {
+                        SP_WAIT(2, bar_bfull + 8 * s, ph);
                         tc_fence_after();
                         const uint32_t b0 = b_base + s * pl.stage_bytes;
-                        if (j < KSLABS) {
+                        if (leader) {
+                            if (j < KSLABS) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
+                                for (int kk = 0; kk < 4; ++kk) {
 #ifdef TVQ_ABL_NOMMA     // ablation build: no MMA issued (timing of the scan without tensor-pipe / operand traffic)
-                                continue;
+                                    continue;
 #endif
-                                if (CG == 2)
-                                    umma_bf16_pair(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
-                                                   umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
-                                else
-                                    umma_bf16(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
-                                              umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
+                                    if (CG == 2)
+                                        umma_bf16_pair(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
+                                                       umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
+                                    else
+                                        umma_bf16(tmem_base + slot * NT, umma_desc_sw128(a0 + j * A_SLAB + kk * 32),
+                                                  umma_desc_sw128(b0 + kk * 32), idesc, (j | kk) != 0);
+                                }
+                            } else {
+                                // + |e|^2 / 2: ONE more K step, constant A rows (1, 1, 1, 0...) x the three bf16 pieces of |e_c|^2 / 2
+                                if (CG == 2) umma_bf16_pair(tmem_base + slot * NT, umma_desc_sw32(aone_base), umma_desc_sw32(b0), idesc, 1u);
+                                else umma_bf16(tmem_base + slot * NT, umma_desc_sw32(aone_base), umma_desc_sw32(b0), idesc, 1u);
                             }
-                        } else {
-                            // + |e|^2 / 2: ONE more K step, constant A rows (1, 1, 1, 0...) x the three bf16 pieces of |e_c|^2 / 2
-                            if (CG == 2) umma_bf16_pair(tmem_base + slot * NT, umma_desc_sw32(aone_base), umma_desc_sw32(b0), idesc, 1u);
-                            else umma_bf16(tmem_base + slot * NT, umma_desc_sw32(aone_base), umma_desc_sw32(b0), idesc, 1u);
+                            // stage free (in both CTAs of a pair) once these MMAs have read it
+                            if (CG == 2) umma_commit_pair(bar_bempty + 8 * s); else umma_commit(bar_bempty + 8 * s);
+                            // scores of this code tile complete
+                            if (j == KSLABS) { if (CG == 2) umma_commit_pair(bar_tfull + 8 * slot); else umma_commit(bar_tfull + 8 * slot); }
                         }
-                        // stage free (in both CTAs of a pair) once these MMAs have read it
-                        if (CG == 2) umma_commit_pair(bar_bempty + 8 * s); else umma_commit(bar_bempty + 8 * s);
+                        __syncwarp();
+                        if (++s == stages) { s = 0; ph ^= 1u; }
                     }
-                    // scores of this code tile complete
-                    if (CG == 2) umma_commit_pair(bar_tfull + 8 * slot); else umma_commit(bar_tfull + 8 * slot);
                 }
                 // A buffer free once every MMA of the row tile is done
-                if (CG == 2) umma_commit_pair(bar_aempty + 8 * ab); else umma_commit(bar_aempty + 8 * ab);
+                if (leader) { if (CG == 2) umma_commit_pair(bar_aempty + 8 * ab); else umma_commit(bar_aempty + 8 * ab); }
+                __syncwarp();
             }
             SP_LAP(7);
-            SP_DUMP(8);
+            if (lane == 0) SP_DUMP(8);
         }
     } else if (warp < 2 + kSCvtWarps) {
-        // ============================================================ converters: x fp32 -> bf16 A operand, |x| -> bound
+        // ============================================================ converters: x fp32 -> bf16 A operand, row norms
+        // Each converter warp is ONE serial instruction stream, so what matters is how few instructions a 16-byte chunk costs
+        // (the first version spent ~100, 24 k clocks per row tile at d = 64: the floor of every k <= 1024 shape):
+        //   * d <= 128: the x rows arrive through shared memory — 8 KB blocks (512 / F rows) bulk-copied by this warp xdepth - 1
+        //     blocks ahead; per chunk one LDS.128, two cvt.rn.bf16x2, one STS.64 into the swizzled A tile, the two sums of
+        //     squares, a log2(F)-step butterfly; all index arithmetic is per lane and hoisted;
+        //   * the square roots and the bound itself are left to the scan threads (one per latent): the converter only
+        //     publishes |x|^2 and |x - bf16(x)|^2 per row.
         const int cw = warp - 2;
-        constexpr int U = 8;
+        constexpr bool STAGED = DP <= 128;
+        constexpr int U = STAGED ? 4 : 8;                     // 16-byte chunks per lane in flight
+        constexpr int XRB = STAGED ? 512 / F : 32;            // rows per block
+        constexpr int BPT = 64 / XRB;                         // blocks per row tile and converter warp
+        const uint32_t xs_base = smem_u32(smem + pl.xs) + (uint32_t)(cw * xdepth) * kSXBlock;
+        const uint32_t xbar0 = bar_xfull + 8 * (cw * kSXMaxDepth);
+        auto issue_block = [&](const int g) {                 // lane 0: bulk copy of block g of this warp's block sequence
+            const int it2 = g / BPT, blk2 = g - it2 * BPT;
+            const int64_t grp2 = (int64_t)unit0 + (int64_t)it2 * nunits;
+            if (grp2 >= ngroups) return;
+            const int64_t r0 = (CG * grp2 + crank) * kSM + cw * 64 + blk2 * XRB;
+            int64_t rows = p.n - r0;
+            rows = rows < XRB ? rows : XRB;
+            if (rows <= 0) return;
+            const uint32_t bytes = (uint32_t)rows * (uint32_t)p.d * 4u;
+            const int st = g % xdepth;
+            mbar_arrive_expect_tx(xbar0 + 8 * st, bytes);
+            bulk_load_1d(xs_base + (uint32_t)st * kSXBlock, p.x + (size_t)r0 * p.d, bytes, xbar0 + 8 * st);
+        };
+        if (STAGED && lane == 0)
+            for (int g = 0; g < xdepth - 1; ++g) issue_block(g);
+        // per-lane constants of the staged path: a warp-wide 16-byte access covers RPU rows, lane -> (row lr, chunk c4)
+        constexpr int FL = F < 32 ? F : 32;                   // lanes per row
+        constexpr int RPU = 32 / FL;
+        const int lr = lane / FL, c4l = lane % FL;
+        const bool cvalid = c4l < nchunk;
+        const uint32_t rowbytes = (uint32_t)p.d * 4u;
+        const uint32_t a_lane = (uint32_t)(c4l >> 4) * A_SLAB + ((uint32_t)(c4l & 1) << 3);
+        const uint32_t chunk_l = (uint32_t)(c4l & 15) >> 1;
         SP_DECL;
-        int it = 0;
+        int it = 0, gblk = 0;
         for (int grp = unit0; grp < ngroups; grp += nunits, ++it) {
             const int tile = CG * grp + crank;
             const int ab = it & 1;
@@ -685,10 +750,49 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
             SP_WAIT(1, bar_rempty + 8 * rs, (((uint32_t)(it / kSBrowRing)) & 1u) ^ 1u);
             SP_RESET();
             const uint32_t a0 = a_base + ab * pl.a_bytes;
-            float* brow = brow_ring + rs * kSM;
+            float2* brow = brow_ring + rs * kSM;
 #pragma unroll 1
-            for (int blk = 0; blk < 128 / (32 * kSCvtWarps); ++blk) {
-            const int rowbase = (cw * (128 / (32 * kSCvtWarps)) + blk) * 32;   // 32 latents of the tile
+            for (int blk = 0; blk < BPT; ++blk, ++gblk) {
+            const int rowbase = cw * 64 + blk * XRB;           // first latent of the block within the tile
+            if constexpr (STAGED) {
+                const int64_t left = p.n - (row0 + rowbase);
+                const int nvalid = left < XRB ? (int)(left > 0 ? left : 0) : XRB;    // rows of this block that exist
+                __syncwarp();                                 // every lane has read the block whose buffer is refilled now
+                if (lane == 0) { fence_proxy_async_smem(); issue_block(gblk + xdepth - 1); }
+                if (nvalid > 0) mbar_wait(xbar0 + 8 * (gblk % xdepth), ((uint32_t)(gblk / xdepth)) & 1u);
+                const uint32_t src = xs_base + (uint32_t)(gblk % xdepth) * kSXBlock + (uint32_t)lr * rowbytes + (uint32_t)c4l * 16u;
+                const uint32_t dst = a0 + a_lane + (uint32_t)(rowbase + lr) * 128u;
+#pragma unroll 1
+                for (int i0 = 0; i0 < XRB / RPU; i0 += U) {
+                    float4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = (i0 + u) * RPU + lr;    // row within the block
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (cvalid && r < nvalid) v[u] = lds_v4(src + (uint32_t)((i0 + u) * RPU) * rowbytes);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = (i0 + u) * RPU + lr;
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y);
+                        const __nv_bfloat162 hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+                        // element column 4*c4: slab c4/16, 16-byte chunk (c4 % 16) / 2 (XOR row & 7), half c4 & 1
+                        sts_v2(dst + (uint32_t)((i0 + u) * RPU) * 128u + ((chunk_l ^ ((uint32_t)(rowbase + r) & 7u)) << 4),
+                               *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                        float t = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
+                        // |x - bf16(x)|^2 of the chunk (the differences are exact in fp32)
+                        const float2 blo = __bfloat1622float2(lo), bhi = __bfloat1622float2(hi);
+                        const float ex = v[u].x - blo.x, ey = v[u].y - blo.y, ez = v[u].z - bhi.x, ew = v[u].w - bhi.y;
+                        float td = fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, ew * ew)));
+#pragma unroll
+                        for (int off = FL / 2; off >= 1; off >>= 1) {
+                            t += __shfl_xor_sync(0xffffffffu, t, off);
+                            td += __shfl_xor_sync(0xffffffffu, td, off);
+                        }
+                        if (c4l == 0) brow[rowbase + r] = make_float2(t, td);
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int i0 = 0; i0 < F; i0 += U) {
                 float4 v[U];
@@ -707,60 +811,27 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                     const int row = rowbase + f / F, c4 = f % F;
                     const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y);
                     const __nv_bfloat162 hi = __floats2bfloat162_rn(v[u].z, v[u].w);
-                    // element column 4*c4: slab c4/16, 16-byte chunk (c4 % 16) / 2 (XOR row & 7), half c4 & 1
                     const uint32_t addr = a0 + (uint32_t)(c4 >> 4) * A_SLAB + (uint32_t)row * 128u +
                                           ((((uint32_t)(c4 & 15) >> 1) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)(c4 & 1) << 3);
                     sts_v2(addr, *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
                     ssq[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
-                    // |x - bf16(x)|^2 of the chunk (the differences are exact in fp32)
                     const float2 blo = __bfloat1622float2(lo), bhi = __bfloat1622float2(hi);
                     const float ex = v[u].x - blo.x, ey = v[u].y - blo.y, ez = v[u].z - bhi.x, ew = v[u].w - bhi.y;
                     dsq[u] = fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, ew * ew)));
                 }
-                // row norms -> bound of |(s_a - s_b) - (d_a - d_b)| for this latent
-                if constexpr (F == 64) {
+                // F == 64 (d = 256): a row is two warp-wide accesses
+                static_assert(STAGED || F == 64, "the global-load converter path serves d = 256 only");
 #pragma unroll
-                    for (int u = 0; u < U; u += 2) {
-                        float t = ssq[u] + ssq[u + 1], td = dsq[u] + dsq[u + 1];
+                for (int u = 0; u < U; u += 2) {
+                    float t = ssq[u] + ssq[u + 1], td = dsq[u] + dsq[u + 1];
 #pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1) {
-                            t += __shfl_xor_sync(0xffffffffu, t, off);
-                            td += __shfl_xor_sync(0xffffffffu, td, off);
-                        }
-                        if (lane == 0) {
-                            const float xn = sqrtf(t) * 1.0001f, dxn = sqrtf(td) * 1.0001f, sum = xn + emax;
-                            brow[rowbase + (i0 + u) / 2] = stream_bound(xn, dxn, emax, demax, sum);
-                        }
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        t += __shfl_xor_sync(0xffffffffu, t, off);
+                        td += __shfl_xor_sync(0xffffffffu, td, off);
                     }
-                } else if constexpr (F == 32) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        float t = ssq[u], td = dsq[u];
-#pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1) {
-                            t += __shfl_xor_sync(0xffffffffu, t, off);
-                            td += __shfl_xor_sync(0xffffffffu, td, off);
-                        }
-                        if (lane == 0) {
-                            const float xn = sqrtf(t) * 1.0001f, dxn = sqrtf(td) * 1.0001f, sum = xn + emax;
-                            brow[rowbase + i0 + u] = stream_bound(xn, dxn, emax, demax, sum);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        float t = ssq[u], td = dsq[u];
-#pragma unroll
-                        for (int off = 8; off >= 1; off >>= 1) {
-                            t += __shfl_xor_sync(0xffffffffu, t, off);
-                            td += __shfl_xor_sync(0xffffffffu, td, off);
-                        }
-                        if ((lane & 15) == 0) {
-                            const float xn = sqrtf(t) * 1.0001f, dxn = sqrtf(td) * 1.0001f, sum = xn + emax;
-                            brow[rowbase + 2 * (i0 + u) + (lane >> 4)] = stream_bound(xn, dxn, emax, demax, sum);
-                        }
-                    }
+                    if (lane == 0) brow[rowbase + (i0 + u) / 2] = make_float2(t, td);
                 }
+            }
             }
             }
             if (CG == 2) fence_proxy_async_all(); else fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma
@@ -774,17 +845,20 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
         if (cw == 0 && lane == 0) SP_DUMP(24);
     }
     } else {
-        if (SP == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        if (WG_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ============================================================ scan + apply warps (one thread per latent)
         const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
-        const int half = (warp - 4) >> 2;                     // scan part: which 1/SP of every code tile's columns this warp scans
+        const int set = (warp - 4) / kSetWarps;               // which row tiles (it % SETS) and score slots this warp works on
+        const int half = ((warp - 4) >> 2) % SP;              // scan part: which 1/SP of every code tile's columns this warp scans
+        const int pbase = set * SP, pidx = pbase + half;      // storage index of the set's first part / of this part
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (NT / SP));
         const int trow = quad * 32 + lane;                    // this thread's latent within the tile
-        float* ls = cand_s + half * (kSCand * kSM) + trow;
-        int* lc = cand_c + half * (kSCand * kSM) + trow;
-        float* sd = reinterpret_cast<float*>(smem + pl.drop) + half * (2 * kSM) + trow;   // [0]: spillmin, [kSM]: dropmin
-        float* thrfin = mfin;                                 // reused after the merge: final threshold per latent (half 0 slot)
+        float* ls = cand_s + pidx * (kSCand * kSM) + trow;
+        int* lc = cand_c + pidx * (kSCand * kSM) + trow;
+        float* sd = reinterpret_cast<float*>(smem + pl.drop) + pidx * (2 * kSM) + trow;   // [0]: spillmin, [kSM]: dropmin
+        float* thrfin = mfin + pbase * kSM;                   // reused after the merge: final threshold per latent (part 0 slot)
         int* scratch = scratch_base + (warp - 4) * kSScratch;
+        const uint32_t qbar = 1u + (uint32_t)(set * 4 + quad);   // named barrier of this set's quadrant (SP warps)
         float* esum = p.stats + ((p.k + 3) & ~3);
         const bool h0 = lane < nchunk, h1 = NV > 1 && lane + 32 < nchunk;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -792,14 +866,16 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
         // latents in flight in the apply phase (up to 4 candidates each are resolved in the batched pass).  Two candidates
         // per latent with twice the latents per L2 round trip was measured and is slower (512 x 64: 6.3 vs 4.4 ms): three-
         // and four-candidate latents are too common for the one-at-a-time second pass.
-        constexpr int R = (NV > 1 || SP == 4) ? 2 : 4;
+        constexpr int R = (NV > 1 || WG_REGS) ? 2 : 4;
         SP_DECL;
-        int et = 0, it = 0;
-        for (int grp = unit0; grp < ngroups; grp += nunits, ++it) {
+        int et = 0;                                           // code tiles scanned by this set
+        for (int it = set, grp = unit0 + set * nunits; grp < ngroups; grp += SETS * nunits, it += SETS) {
             const int tile = CG * grp + crank;
             const int rs = it & (kSBrowRing - 1);
             SP_WAIT(0, bar_rfull + 8 * rs, ((uint32_t)(it / kSBrowRing)) & 1u);     // the row bounds are written
-            const float brow = brow_ring[rs * kSM + trow];
+            const float2 nrm = brow_ring[rs * kSM + trow];     // |x|^2 and |x - bf16(x)|^2 of this thread's latent (converter)
+            const float xnrm = sqrtf(nrm.x) * 1.0001f;
+            const float brow = stream_bound(xnrm, sqrtf(nrm.y) * 1.0001f, emax, demax, xnrm + emax);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);
             ScanState st;
@@ -819,8 +895,8 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
             //      tile records only what lies within the bound of its own minimum, and a later chunk at position n is
             //      entered with probability ~32 / n per latent.
             {
-                const int slot = et % SLOTS;
-                SP_WAIT(2, bar_tfull + 8 * slot, ((uint32_t)(et / SLOTS)) & 1u);
+                const int slot = set * SLOTS_S + et % SLOTS_S;
+                SP_WAIT(2, bar_tfull + 8 * slot, ((uint32_t)(et / SLOTS_S)) & 1u);
                 tc_fence_after();
                 SP_RESET();
                 const uint32_t taddr = lane_addr + (uint32_t)(slot * NT);
@@ -834,23 +910,24 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                     mp = fminf(mp, chunk_min(ra));
                     if (c + 1 < NCH) mp = fminf(mp, chunk_min(rb));
                 }
-                mshare[half * kSM + trow] = mp;
-                named_bar_sync(1 + quad, 32 * SP);
+                mshare[pidx * kSM + trow] = mp;
+                if (half == 0 && lane == 0) *ob.n = 0;        // the quadrant's spill buffer: nothing is recorded before this barrier
+                named_bar_sync(qbar, 32 * SP);
 #pragma unroll
-                for (int pt = 0; pt < SP; ++pt) st.m = fminf(st.m, mshare[pt * kSM + trow]);
+                for (int pt = 0; pt < SP; ++pt) st.m = fminf(st.m, mshare[(pbase + pt) * kSM + trow]);
                 SP_LAP(3);
             }
             // ---- scan: this warp's part of the columns of every code tile.  The parts of a quadrant share their running
             //      minima (any score of the latent is a valid upper bound of its minimum; a stale value only costs a
             //      candidate that the final filter drops), exchanged once per code tile through shared memory.
             for (int ct = 0; ct < n_ct; ++ct, ++et) {
-                const int slot = et % SLOTS;
-                SP_WAIT(2, bar_tfull + 8 * slot, ((uint32_t)(et / SLOTS)) & 1u);
+                const int slot = set * SLOTS_S + et % SLOTS_S;
+                SP_WAIT(2, bar_tfull + 8 * slot, ((uint32_t)(et / SLOTS_S)) & 1u);
                 tc_fence_after();
                 SP_RESET();
                 if (ct > 0) {
 #pragma unroll
-                    for (int pt = 0; pt < SP; ++pt) st.m = fminf(st.m, mshare[pt * kSM + trow]);
+                    for (int pt = 0; pt < SP; ++pt) st.m = fminf(st.m, mshare[(pbase + pt) * kSM + trow]);
                 }
                 const uint32_t taddr = lane_addr + (uint32_t)(slot * NT);
                 const int code0 = ct * NT + half * (NT / SP);
@@ -875,16 +952,16 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                 if (lane == 0) {
                     if (CG == 2) mbar_arrive_leader_nodata(bar_tempty + 8 * slot); else mbar_arrive(bar_tempty + 8 * slot);
                 }
-                mshare[half * kSM + trow] = st.m;
+                mshare[pidx * kSM + trow] = st.m;
                 SP_LAP(3);
             }
             SP_RESET();
             // ---- merge the two halves of the quadrant: common minimum, then each half filters its own list
-            mfin[half * kSM + trow] = st.m;
-            named_bar_sync(1 + quad, 32 * SP);
+            mfin[pidx * kSM + trow] = st.m;
+            named_bar_sync(qbar, 32 * SP);
             float mall = st.m;
 #pragma unroll
-            for (int pt = 0; pt < SP; ++pt) mall = fminf(mall, mfin[pt * kSM + trow]);
+            for (int pt = 0; pt < SP; ++pt) mall = fminf(mall, mfin[(pbase + pt) * kSM + trow]);
             const float thr_fin = mall + brow;
             {
                 int kept = 0;
@@ -901,11 +978,11 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                     lc[0] = 0;
                     nres = half == 0 ? 1 : 0;
                 }
-                ncnt[half * kSM + trow] = nres;
+                ncnt[pidx * kSM + trow] = nres;
             }
-            named_bar_sync(1 + quad, 32 * SP);
+            named_bar_sync(qbar, 32 * SP);
             if (half == 0) thrfin[trow] = thr_fin;            // (every part has read mfin)
-            named_bar_sync(1 + quad, 32 * SP);
+            named_bar_sync(qbar, 32 * SP);
             SP_LAP(4);
             // ---- resolve + apply: all 32 lanes on one latent, R latents in flight, ONE round trip to L2:
             //      x rows, the first candidate's code word and (for ambiguous latents) candidates 2-4 are
@@ -933,7 +1010,7 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                     int tot = 0, bad = 0, cn[SP];
 #pragma unroll
                     for (int pt = 0; pt < SP; ++pt) {
-                        const int nr = ncnt[pt * kSM + lrow];
+                        const int nr = ncnt[(pbase + pt) * kSM + lrow];
                         bad |= (nr < 0) | (nr & 0x100);
                         cn[pt] = nr & 0xff;
                         tot += cn[pt];
@@ -944,7 +1021,7 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
 #pragma unroll
                     for (int pt = 0; pt < SP - 1; ++pt)
                         if (part_j == pt && jj >= cn[pt]) { jj -= cn[pt]; part_j = pt + 1; }
-                    const int c = cand_c[(part_j * kSCand + (jj < kSCand ? jj : 0)) * kSM + lrow];
+                    const int c = cand_c[((pbase + part_j) * kSCand + (jj < kSCand ? jj : 0)) * kSM + lrow];
                     c_l = (c >= 0 && c < p.k) ? c : 0;
                 }
 #pragma unroll
@@ -1045,13 +1122,13 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                 int cn[SP], badg = 0;
 #pragma unroll
                 for (int pt = 0; pt < SP; ++pt) {
-                    const int nr = ncnt[pt * kSM + lrow];
+                    const int nr = ncnt[(pbase + pt) * kSM + lrow];
                     badg |= nr < 0;
                     cn[pt] = nr & 0xff;
                 }
                 int ncg = -1;
                 if (!badg) {
-                    ncg = gather_cands<SP>(scratch, cn, cand_c + lrow, ob, lrow, thrfin[lrow], lane);
+                    ncg = gather_cands<SP>(scratch, cn, cand_c + pbase * (kSCand * kSM) + lrow, ob, lrow, thrfin[lrow], lane);
                     if (ncg == 0) ncg = -1;
                 }
                 const int rr = resolve_stream<NV>(xa, xb, ncg, scratch, p.cb, p.e2, p.k, p.d, emax, lane);
@@ -1074,8 +1151,7 @@ __global__ void __launch_bounds__(stream_threads(SP), 1) fwd_stream_kernel(const
                 atomicAdd(p.stats + mycode, 1.0f);            // counts (exact integers in fp32)
             }
             loss_d += (double)loss;
-            if (half == 0 && lane == 0) misc[4 + ((it + 1) & 1) * 4 + quad] = 0;   // spill buffer of the next row tile
-            named_bar_sync(1 + quad, 32 * SP);                // the quadrant's lists are reused by the next row tile
+            named_bar_sync(qbar, 32 * SP);                // the quadrant's lists are reused by the next row tile
             SP_LAP(5);
         }
         if (warp == 4 && lane == 0) SP_DUMP(16);

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "t-vq-vae-trajgen_b200", "csrc")
 SO = os.path.join(CSRC, "_prof", "libtvq_sprof.so")
 
-VARIANTS = {"": [], "noslow": ["-DTVQ_ABL_NOSLOW"], "noslow_nomma": ["-DTVQ_ABL_NOSLOW", "-DTVQ_ABL_NOMMA"]}
+VARIANTS = {"": []}
 _OLD_VARIANTS = {"": [], "noslow": ["-DTVQ_ABL_NOSLOW"], "noe2": ["-DTVQ_ABL_NOE2"], "noslow_nold": ["-DTVQ_ABL_NOSLOW", "-DTVQ_ABL_NOLD"], "noslow_nomma": ["-DTVQ_ABL_NOSLOW", "-DTVQ_ABL_NOMMA"],
             "noslow_noe2": ["-DTVQ_ABL_NOSLOW", "-DTVQ_ABL_NOE2"]}
 
