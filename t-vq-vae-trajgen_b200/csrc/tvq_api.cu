@@ -317,7 +317,7 @@ inline int stream_cg(const FwdParams& p) {
         forced = e ? atoi(e) : 0;
     }
     if (forced == 1 || forced == 2) return forced;
-    return (p.k >= 1024 && p.n > kSM) ? 2 : 1;
+    return (p.k >= 512 && p.n > kSM) ? 2 : 1;
 }
 
 // Scan parts per quadrant (tvq_fwd_stream.cuh): 4 (20 warps) for d <= 64, and for d <= 128 from k = 2048 up; 2 (12 warps)
@@ -332,7 +332,7 @@ inline int stream_sp(const FwdParams& p) {
     }
     if (p.d > 128) return 2;
     if (forced == 2 || forced == 4) return forced;
-    return (p.d <= 64 || p.k >= 2048) ? 4 : 2;
+    return 4;
 }
 
 // Two scan / apply sets (tvq_fwd_stream.cuh, d <= 128) are an experiment: measured slower than one set at every shape of the

@@ -83,7 +83,7 @@ constexpr int kSScratch = kSMaxParts * kSCand + kSOvf;   // merged candidate lis
 
 struct StreamPlan {
     int stages, stage_bytes, a_bytes;
-    int a, b, xs, aone, brow, cs, cc, drop, mfin, mshare, ncnt, ovf, scratch, red, misc, bars, tmem, total;
+    int a, b, xs, aone, brow, cs, cc, drop, mfin, mshare, ncnt, recc, recn, ovf, scratch, red, misc, bars, tmem, total;
 };
 __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stages, int cg = 1, int sp = 2, int xdepth = 0) {
     StreamPlan u;
@@ -102,6 +102,8 @@ __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stage
     u.mfin = o;  o += sp * kSM * 4;
     u.mshare = o; o += sp * kSM * 4;     // running minimum of every scan part, read by the other parts of the quadrant
     u.ncnt = o;  o += sp * kSM * 4;
+    u.recc = o;  o += 2 * kSM * 16;          // merged record of every latent (per set): up to four candidate codes ...
+    u.recn = o;  o += 2 * kSM * 4;           // ... and how many (0: general path)
     u.ovf = o;   o += 2 * 4 * kSOvf * 12;       // [row-tile parity][quadrant]: rows | scores | codes
     u.scratch = o; o += kSScratch * 4 * sp * 4;   // per scan warp
     u.red = o;   o += 32 * 8;
@@ -518,6 +520,8 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
     float* mfin = reinterpret_cast<float*>(smem + pl.mfin);     // [half][latent] minimum seen by each scan half
     volatile float* mshare = reinterpret_cast<volatile float*>(smem + pl.mshare);   // [part][latent] running minimum, live
     int* ncnt = reinterpret_cast<int*>(smem + pl.ncnt);         // [half][latent] final candidates per half (-1: incomplete)
+    int4* recc_base = reinterpret_cast<int4*>(smem + pl.recc);
+    int* recn_base = reinterpret_cast<int*>(smem + pl.recn);
     int* ovf_base = reinterpret_cast<int*>(smem + pl.ovf);      // [parity][quadrant][rows | scores | codes][kSOvf]
     int* scratch_base = reinterpret_cast<int*>(smem + pl.scratch);
     double* red = reinterpret_cast<double*>(smem + pl.red);
@@ -859,6 +863,8 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
         float* thrfin = mfin + pbase * kSM;                   // reused after the merge: final threshold per latent (part 0 slot)
         int* scratch = scratch_base + (warp - 4) * kSScratch;
         const uint32_t qbar = 1u + (uint32_t)(set * 4 + quad);   // named barrier of this set's quadrant (SP warps)
+        int4* recc = recc_base + set * kSM;
+        int* recn = recn_base + set * kSM;
         float* esum = p.stats + ((p.k + 3) & ~3);
         const bool h0 = lane < nchunk, h1 = NV > 1 && lane + 32 < nchunk;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -981,7 +987,32 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                 ncnt[pidx * kSM + trow] = nres;
             }
             named_bar_sync(qbar, 32 * SP);
-            if (half == 0) thrfin[trow] = thr_fin;            // (every part has read mfin)
+            if (half == 0) {
+                thrfin[trow] = thr_fin;                       // (every part has read mfin)
+                // merged record of this thread's latent, built here (one thread per latent, in parallel) instead of by the
+                // apply warps: the count (1..4; 0 = general path) and the candidates in part order
+                int tot = 0, bad = 0, cn[SP];
+#pragma unroll
+                for (int pt = 0; pt < SP; ++pt) {
+                    const int nr = ncnt[(pbase + pt) * kSM + trow];
+                    bad |= (nr < 0) | (nr & 0x100);
+                    cn[pt] = nr & 0xff;
+                    tot += cn[pt];
+                }
+                const int ncr = (bad || tot == 0 || tot > 4) ? 0 : tot;
+                int cv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int jj = j < ncr ? j : 0, part_j = 0;
+#pragma unroll
+                    for (int pt = 0; pt < SP - 1; ++pt)
+                        if (part_j == pt && jj >= cn[pt]) { jj -= cn[pt]; part_j = pt + 1; }
+                    const int c = cand_c[((pbase + part_j) * kSCand + (jj < kSCand ? jj : 0)) * kSM + trow];
+                    cv[j] = (c >= 0 && c < p.k) ? c : 0;
+                }
+                recc[trow] = make_int4(cv[0], cv[1], cv[2], cv[3]);
+                recn[trow] = ncr;
+            }
             named_bar_sync(qbar, 32 * SP);
             SP_LAP(4);
             // ---- resolve + apply: all 32 lanes on one latent, R latents in flight, ONE round trip to L2:
@@ -992,6 +1023,126 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
             int mycode = 0;
             float loss = 0.f;
             unsigned gen_mask = 0;                            // latents left to the general path (second pass)
+            if constexpr (NV == 1) {
+                // d <= 128.  Lane i looks up latent i of this warp once; three passes:
+                //   1. one candidate (65 - 80 % of the latents): nothing to decide — x row and code word of EVERY such latent
+                //      are requested before the first is used (one L2 round trip for the whole warp); at d <= 64 a row is 16
+                //      lanes wide, so one warp-wide access serves two latents;
+                //   2. two to four candidates: fp32 re-score (fp64 if inseparable), two latents per round trip;
+                //   3. anything else (second pass below).
+                int nci = -1;
+                if (lane < LPW && wrow0 + lane < p.n) { nci = recn[lrow0 + lane]; mycode = recc[lrow0 + lane].x; }
+                const unsigned m1 = __ballot_sync(0xffffffffu, nci == 1);
+                unsigned m2 = __ballot_sync(0xffffffffu, nci >= 2);
+                gen_mask = __ballot_sync(0xffffffffu, nci == 0);
+                constexpr int LPI = DP == 64 ? 2 : 1;         // latents per warp-wide 16-byte access
+                constexpr int NACC = LPW / LPI;               // accesses that cover the warp's latents
+                constexpr int GU = NACC < 8 ? NACC : 8;       // ... in flight at a time
+                const int hs = LPI == 2 ? (lane >> 4) : 0;
+                const int c4 = LPI == 2 ? (lane & 15) : lane;
+                const bool hv = c4 < nchunk;
+                const float4* cb4 = reinterpret_cast<const float4*>(p.cb);
+                const int dq = p.d >> 2;
+#pragma unroll 1
+                for (int g0 = 0; g0 < NACC; g0 += GU) {
+                    if (((m1 >> (g0 * LPI)) & ((1u << (GU * LPI)) - 1u)) == 0u) continue;     // warp-uniform
+                    float4 xa[GU], ea[GU];
+                    int cu[GU];
+#pragma unroll
+                    for (int u = 0; u < GU; ++u) {
+                        const int lat = (g0 + u) * LPI + hs;
+                        xa[u] = z4; ea[u] = z4; cu[u] = 0;
+                        if ((m1 >> lat) & 1u) {
+                            cu[u] = recc[lrow0 + lat].x;
+                            if (hv) {
+                                xa[u] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)(wrow0 + lat) * p.d) + c4);
+                                ea[u] = __ldg(cb4 + (size_t)cu[u] * dq + c4);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < GU; ++u) {
+                        const int lat = (g0 + u) * LPI + hs;
+                        if (((m1 >> lat) & 1u) && (p.q != nullptr || TRAIN))
+                            apply_row<1, TRAIN>(p, esum, xa[u], z4, ea[u], z4, cu[u], wrow0 + lat, hv, false, c4, loss);
+                    }
+                }
+#pragma unroll 1
+                while (m2) {                                   // warp-uniform
+                    constexpr int R2 = 2;
+                    float4 xa[R2], ea[R2][4];
+                    float e2v[R2][4];
+                    int nc[R2], cc[R2][4], lat[R2];
+#pragma unroll
+                    for (int u = 0; u < R2; ++u) {
+                        nc[u] = 0; lat[u] = 0;
+                        if (m2) { lat[u] = __ffs((int)m2) - 1; m2 &= m2 - 1u; nc[u] = recn[lrow0 + lat[u]]; }
+                        const int4 c4v = recc[lrow0 + lat[u]];
+                        cc[u][0] = c4v.x; cc[u][1] = c4v.y; cc[u][2] = c4v.z; cc[u][3] = c4v.w;
+                        const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)(wrow0 + lat[u]) * p.d);
+                        xa[u] = (nc[u] > 0 && h0) ? __ldg(xr + lane) : z4;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            ea[u][j] = z4; e2v[u][j] = 0.f;
+                            if (j < nc[u]) {
+                                if (h0) ea[u][j] = __ldg(cb4 + (size_t)cc[u][j] * dq + lane);
+                                e2v[u][j] = __ldg(p.e2 + cc[u][j]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < R2; ++u) {
+                        if (nc[u] < 2) continue;               // (second slot of an odd batch)
+                        // fp32 re-score of the (<= 4) candidates, all lanes on this latent
+                        n_resc += 1u;
+                        int sel = 0;
+                        float dd[4];
+                        float ss = fmaf(xa[u].x, xa[u].x, fmaf(xa[u].y, xa[u].y, fmaf(xa[u].z, xa[u].z, xa[u].w * xa[u].w)));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dd[j] = fmaf(xa[u].x, ea[u][j].x, fmaf(xa[u].y, ea[u][j].y, fmaf(xa[u].z, ea[u][j].z, xa[u].w * ea[u][j].w)));
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            ss += __shfl_xor_sync(0xffffffffu, ss, off);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], off);
+                        }
+                        const float bnd = fmaf(sqrtf(ss), 1.0001f, emax);
+                        const float thr32 = 1.6e-6f * bnd * bnd;
+                        float mm1 = INF, mm2 = INF;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float sv = j < nc[u] ? fmaf(-2.f, dd[j], e2v[u][j]) : INF;
+                            if (sv < mm1) { mm2 = mm1; mm1 = sv; sel = j; }
+                            else if (sv < mm2) mm2 = sv;
+                        }
+                        if (!(mm2 - mm1 > thr32)) {
+                            // canonical fp64 rule among the candidates (code words already in registers)
+                            n_f64 += 1u;
+                            double pp = 0.0;
+                            if (h0) pp = dot4(pp, xa[u], xa[u]);
+                            const float x2 = __double2float_rn(butterfly_sum(pp));
+                            float best = INF;
+                            int arg = 0x7fffffff;
+                            sel = 0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (j < nc[u]) {
+                                    double sdd = 0.0;
+                                    if (h0) sdd = dot4(sdd, xa[u], ea[u][j]);
+                                    const float dk = canon_score(x2, butterfly_sum(sdd), e2v[u][j]);
+                                    if (dk < best || (dk == best && cc[u][j] < arg)) { best = dk; arg = cc[u][j]; sel = j; }
+                                }
+                            }
+                        }
+                        const int code = sel == 0 ? cc[u][0] : sel == 1 ? cc[u][1] : sel == 2 ? cc[u][2] : cc[u][3];
+                        const float4 wa = sel == 0 ? ea[u][0] : sel == 1 ? ea[u][1] : sel == 2 ? ea[u][2] : ea[u][3];
+                        if (p.q != nullptr || TRAIN)
+                            apply_row<1, TRAIN>(p, esum, xa[u], z4, wa, z4, code, wrow0 + lat[u], h0, false, lane, loss);
+                        mycode = (lane == lat[u]) ? code : mycode;
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int b = 0; b < LPW / R; ++b) {
                 if (wrow0 + R * b >= p.n) break;              // warp-uniform
@@ -1107,6 +1258,7 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                         mycode = (lane == R * b + u) ? code : mycode;
                     }
                 }
+            }
             }
             // ---- second pass (rare): long merged lists, spilled candidates, exhaustive scans — one latent at a time
             SP_MARK(sp_g0);
