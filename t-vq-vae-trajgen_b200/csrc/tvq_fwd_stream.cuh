@@ -102,8 +102,10 @@ __host__ __device__ inline StreamPlan make_stream_plan(int dp, int nt, int stage
     u.mfin = o;  o += sp * kSM * 4;
     u.mshare = o; o += sp * kSM * 4;     // running minimum of every scan part, read by the other parts of the quadrant
     u.ncnt = o;  o += sp * kSM * 4;
-    u.recc = o;  o += 2 * kSM * 16;          // merged record of every latent (per set): up to four candidate codes ...
-    u.recn = o;  o += 2 * kSM * 4;           // ... and how many (0: general path)
+    // merged record of every latent (per set): up to four candidate codes and how many (0: general path).  d <= 128 only:
+    // at d = 256 the 5 KB are the difference between three and four code-slab stages (8.3 vs 7.3 ms at 16384 x 256)
+    u.recc = o;  o += dp <= 128 ? 2 * kSM * 16 : 0;
+    u.recn = o;  o += dp <= 128 ? 2 * kSM * 4 : 0;
     u.ovf = o;   o += 2 * 4 * kSOvf * 12;       // [row-tile parity][quadrant]: rows | scores | codes
     u.scratch = o; o += kSScratch * 4 * sp * 4;   // per scan warp
     u.red = o;   o += 32 * 8;
@@ -987,8 +989,8 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                 ncnt[pidx * kSM + trow] = nres;
             }
             named_bar_sync(qbar, 32 * SP);
-            if (half == 0) {
-                thrfin[trow] = thr_fin;                       // (every part has read mfin)
+            if (half == 0) thrfin[trow] = thr_fin;            // (every part has read mfin)
+            if (NV == 1 && half == 0) {
                 // merged record of this thread's latent, built here (one thread per latent, in parallel) instead of by the
                 // apply warps: the count (1..4; 0 = general path) and the candidates in part order
                 int tot = 0, bad = 0, cn[SP];
