@@ -335,26 +335,9 @@ inline int stream_sp(const FwdParams& p) {
     return 4;
 }
 
-// Two scan / apply sets (tvq_fwd_stream.cuh, d <= 128) are an experiment: measured slower than one set at every shape of the
-// sweep (the halved code tile doubles the issuer's and the scan's per-tile overheads); TVQ_STREAM_SETS=2 selects them.
-inline int stream_sets(const FwdParams& p) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("TVQ_STREAM_SETS");
-        forced = e ? atoi(e) : 0;
-    }
-    if (p.d > 128) return 1;
-    return forced == 2 ? 2 : 1;
-}
-
 template <bool TRAIN>
 int dispatch_fwd_stream(const FwdParams& p, const void* cbh, const void* e2h, const DeviceInfo& di, cudaStream_t s) {
     const int cg = stream_cg(p), sp = stream_sp(p);
-    if (stream_sets(p) == 2) {
-        if (stream_dp(p.d) == 64)
-            return cg == 2 ? launch_fwd_stream_impl<64, 128, TRAIN, 2, 2, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<64, 128, TRAIN, 1, 2, 2>(p, cbh, e2h, di, s);
-        return cg == 2 ? launch_fwd_stream_impl<128, 128, TRAIN, 2, 2, 2>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<128, 128, TRAIN, 1, 2, 2>(p, cbh, e2h, di, s);
-    }
     switch (stream_dp(p.d)) {
         case 64:
             if (sp == 4) return cg == 2 ? launch_fwd_stream_impl<64, 256, TRAIN, 2, 4>(p, cbh, e2h, di, s) : launch_fwd_stream_impl<64, 256, TRAIN, 1, 4>(p, cbh, e2h, di, s);

@@ -764,8 +764,12 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                 const int64_t left = p.n - (row0 + rowbase);
                 const int nvalid = left < XRB ? (int)(left > 0 ? left : 0) : XRB;    // rows of this block that exist
                 __syncwarp();                                 // every lane has read the block whose buffer is refilled now
+                SP_MARK(sp_c0);
                 if (lane == 0) { fence_proxy_async_smem(); issue_block(gblk + xdepth - 1); }
+                SP_ADD(3, sp_c0);
+                SP_MARK(sp_c1);
                 if (nvalid > 0) mbar_wait(xbar0 + 8 * (gblk % xdepth), ((uint32_t)(gblk / xdepth)) & 1u);
+                SP_ADD(4, sp_c1);
                 const uint32_t src = xs_base + (uint32_t)(gblk % xdepth) * kSXBlock + (uint32_t)lr * rowbytes + (uint32_t)c4l * 16u;
                 const uint32_t dst = a0 + a_lane + (uint32_t)(rowbase + lr) * 128u;
 #pragma unroll 1
@@ -840,12 +844,14 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
             }
             }
             }
+            SP_MARK(sp_c2);
             if (CG == 2) fence_proxy_async_all(); else fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) {
                 if (CG == 2) mbar_arrive_leader(bar_afull + 8 * ab); else mbar_arrive(bar_afull + 8 * ab);
                 mbar_arrive(bar_rfull + 8 * rs);
             }
+            SP_ADD(5, sp_c2);
             SP_LAP(2);
         }
         if (cw == 0 && lane == 0) SP_DUMP(24);

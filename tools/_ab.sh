@@ -1,8 +1,8 @@
 L=t-vq-vae-trajgen_b200/libtvq_b200.so
 cp $L /tmp/cur.so
-for i in 1 2; do
-echo "== cur"; timeout 300 python tools/time_sweep2.py small 2>&1 | tail -4
-cp tools/_libprev.so $L
-echo "== prev"; timeout 300 python tools/time_sweep2.py small 2>&1 | tail -4
-cp /tmp/cur.so $L
+echo "== cur (sleep 64 after 8)"; timeout 300 python tools/time_sweep2.py 2>&1 | tail -9
+for v in a b c d; do
+cp tools/_lib_$v.so $L
+echo "== $v"; timeout 300 python tools/time_sweep2.py 2>&1 | tail -9
 done
+cp /tmp/cur.so $L

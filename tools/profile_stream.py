@@ -56,7 +56,7 @@ def run(n, k, d, train, variant=""):
     show("producer", 0, ["wait_e_empty", "wait_b_empty", "", "", "", "", "", "total"])
     show("mma", 8, ["wait_a_full", "wait_t_empty", "wait_b_full", "", "", "", "", "total"])
     show("scan w2", 16, ["wait_rows", "wait_e2", "wait_t_full", "scan", "merge", "apply", "apply:fetch+issue", "apply:2nd pass"])
-    show("convert", 24, ["wait_a_empty", "wait_r_empty", "work", "", "", "", "", ""])
+    show("convert", 24, ["wait_a_empty", "wait_r_empty", "work", "issue_blk", "wait_x", "fence+arrive", "", ""])
     for w in range(0):
         show(f"scan w{w+2}", 64 + 8 * w, ["wait_rows", "wait_e2", "wait_t_full", "scan", "merge", "apply", "", ""])
 
