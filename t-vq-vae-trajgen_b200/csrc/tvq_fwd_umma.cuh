@@ -601,10 +601,10 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
         // last CTA — simply takes fewer); the tile id travels with the stage.  After the last tile the producer
         // posts kUGroups end markers so that every epilogue group sees one.
         if (lane == 0) {
-            int it = grab, ends = 0;                      // stages 0 .. grab-1 were filled in the prologue
+            int ends = 0;                                 // stages 0 .. grab-1 were filled in the prologue
+            int s = grab % stages;
+            uint32_t ph = (uint32_t)(grab / stages) & 1u;
             while (ends < kUGroups) {
-                const int s = it % stages;
-                const uint32_t ph = (uint32_t)(it / stages) & 1u;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                 int tile = -1;
                 if (ends == 0) {
@@ -621,30 +621,40 @@ __global__ void __launch_bounds__(kUThreads, 1) fwd_umma_kernel(const __grid_con
                     mbar_arrive(bar_full + 8 * s);
                     ++ends;
                 }
-                ++it;
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
-        if (lane == 0) {
+        // The whole warp walks the loop and one elected lane issues: with warp-uniform control flow the descriptors live in
+        // uniform registers and the 2 * d/8 MMAs of a tile go out back to back (under `if (lane == 0)` every MMA cost a
+        // ~14-instruction elect / broadcast sequence: ~450 instructions of one thread between "tile landed" and "scores
+        // ready").  Stage / slot indices and phases are carried, not divided out of the tile counter.
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc = umma_idesc_tf32(kUM, KP);
-            for (int it = 0;; ++it) {
-                const int s = it % stages, slot = it % kUSlots;
-                const uint32_t ph = (uint32_t)(it / stages) & 1u, sph = (uint32_t)(it / kUSlots) & 1u;
+            int s = 0, slot = 0;
+            uint32_t ph = 0, sph = 0;
+            for (;;) {
                 mbar_wait(bar_full + 8 * s, ph);
                 if (stage_tile[s] < 0) break;
                 mbar_wait(bar_tempty + 8 * slot, sph ^ 1u);
                 tc_fence_after();
                 const uint32_t a0 = x_base + s * pl.stage_bytes;
+                if (leader) {
 #pragma unroll
-                for (int j = 0; j < NSLAB; ++j)
+                    for (int j = 0; j < NSLAB; ++j)
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t adesc = umma_desc_sw128(a0 + j * SLAB_X + kk * 32);
-                        umma_tf32(tmem_base + slot * KP, adesc, umma_desc_sw128(cbh_base + j * SLAB_CB + kk * 32), idesc, (j | kk) != 0);
-                        if (SPLIT) umma_tf32(tmem_base + slot * KP, adesc, umma_desc_sw128(cbl_base + j * SLAB_CB + kk * 32), idesc, 1u);
-                    }
-                umma_commit(bar_tfull + 8 * slot);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t adesc = umma_desc_sw128(a0 + j * SLAB_X + kk * 32);
+                            umma_tf32(tmem_base + slot * KP, adesc, umma_desc_sw128(cbh_base + j * SLAB_CB + kk * 32), idesc, (j | kk) != 0);
+                            if (SPLIT) umma_tf32(tmem_base + slot * KP, adesc, umma_desc_sw128(cbl_base + j * SLAB_CB + kk * 32), idesc, 1u);
+                        }
+                    umma_commit(bar_tfull + 8 * slot);
+                }
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
+                if (++slot == kUSlots) { slot = 0; sph ^= 1u; }
             }
         }
     } else if (warp >= 2 && warp < kUWarpL2) {
