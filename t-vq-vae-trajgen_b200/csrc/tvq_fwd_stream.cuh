@@ -781,25 +781,48 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (cvalid && r < nvalid) v[u] = lds_v4(src + (uint32_t)((i0 + u) * RPU) * rowbytes);
                     }
+                    float vals[2 * U];                        // [u]: |x|^2 of chunk u, [U + u]: |x - bf16(x)|^2
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const int r = (i0 + u) * RPU + lr;
                         const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y);
                         const __nv_bfloat162 hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+                        const uint32_t wlo = *reinterpret_cast<const uint32_t*>(&lo), whi = *reinterpret_cast<const uint32_t*>(&hi);
                         // element column 4*c4: slab c4/16, 16-byte chunk (c4 % 16) / 2 (XOR row & 7), half c4 & 1
-                        sts_v2(dst + (uint32_t)((i0 + u) * RPU) * 128u + ((chunk_l ^ ((uint32_t)(rowbase + r) & 7u)) << 4),
-                               *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-                        float t = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
-                        // |x - bf16(x)|^2 of the chunk (the differences are exact in fp32)
-                        const float2 blo = __bfloat1622float2(lo), bhi = __bfloat1622float2(hi);
-                        const float ex = v[u].x - blo.x, ey = v[u].y - blo.y, ez = v[u].z - bhi.x, ew = v[u].w - bhi.y;
-                        float td = fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, ew * ew)));
+                        sts_v2(dst + (uint32_t)((i0 + u) * RPU) * 128u + ((chunk_l ^ ((uint32_t)(rowbase + r) & 7u)) << 4), wlo, whi);
+                        vals[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
+                        // |x - bf16(x)|^2 of the chunk (a bf16 is the upper half of its fp32; the differences are exact)
+                        const float ex = v[u].x - __uint_as_float(wlo << 16), ey = v[u].y - __uint_as_float(wlo & 0xffff0000u);
+                        const float ez = v[u].z - __uint_as_float(whi << 16), ew = v[u].w - __uint_as_float(whi & 0xffff0000u);
+                        vals[U + u] = fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, ew * ew)));
+                    }
+                    // the 2U sums of squares of the U rows, reduced over the FL lanes of a row TOGETHER: each of the first three
+                    // butterfly steps halves the number of values a lane carries (it keeps the half its lane bit selects and
+                    // sends the other), so the U rows cost 4 + 2 + 1 + ... shuffles instead of 2U * log2(FL)
+                    static_assert(U == 4, "the folded reduction below is written for four rows at a time");
+                    {
+                        const bool b0 = (lane & (FL / 2)) != 0, b1 = (lane & (FL / 4)) != 0, b2 = (lane & (FL / 8)) != 0;
 #pragma unroll
-                        for (int off = FL / 2; off >= 1; off >>= 1) {
-                            t += __shfl_xor_sync(0xffffffffu, t, off);
-                            td += __shfl_xor_sync(0xffffffffu, td, off);
+                        for (int i = 0; i < 4; ++i) {
+                            const float keep = b0 ? vals[i + 4] : vals[i], send = b0 ? vals[i] : vals[i + 4];
+                            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, FL / 2);
                         }
-                        if (c4l == 0) brow[rowbase + r] = make_float2(t, td);
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float keep = b1 ? vals[i + 2] : vals[i], send = b1 ? vals[i] : vals[i + 2];
+                            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, FL / 4);
+                        }
+                        {
+                            const float keep = b2 ? vals[1] : vals[0], send = b2 ? vals[0] : vals[1];
+                            vals[0] = keep + __shfl_xor_sync(0xffffffffu, send, FL / 8);
+                        }
+#pragma unroll
+                        for (int off = FL / 16; off >= 1; off >>= 1) vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], off);
+                        // holder lanes: kind (|x|^2 or the residual) = b0, row u = 2 * b1 + b2
+                        if ((lane & (FL / 8 - 1)) == 0) {
+                            const int r = (i0 + 2 * (int)b1 + (int)b2) * RPU + lr;
+                            reinterpret_cast<float*>(brow)[2 * (rowbase + r) + (int)b0] = vals[0];
+                        }
                     }
                 }
             } else {
