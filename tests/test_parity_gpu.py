@@ -566,6 +566,30 @@ def test_stream_path_duplicated_codes(tvq, n, k, d, dup, noise):
         assert bool((idx_u % dup == 0).all()), "exact duplicates: the first copy must be chosen"
 
 
+@pytest.mark.parametrize("n,k,d", [(6000, 512, 64), (4000, 1024, 128), (3000, 2304, 256)])
+def test_stream_path_worst_case_bf16_rounding(tvq, n, k, d):
+    """The streamed kernel's nomination bound uses the MEASURED bf16 rounding errors of its operands (|x - bf16(x)| per
+    latent, max |e - bf16(e)| over the codebook).  Latents and code words whose every component sits half a bf16 ulp above
+    a representable value make those errors as large as they can be (2^-9 relative in every coordinate, all of one sign),
+    and near-duplicate code words put many candidates inside the bound: the indices must still be the canonical ones."""
+    torch.manual_seed(n + 3 * k + d)
+    def worst(t):                       # magnitude (1 + j / 128 + 1 / 256 - tiny) * 2^e: halfway between two bf16 values
+        sign = torch.where(t >= 0, 1.0, -1.0)
+        ex = torch.floor(torch.log2(t.abs().clamp_min(1e-3)))
+        frac = torch.floor((t.abs() / 2.0 ** ex - 1.0) * 128.0) / 128.0
+        return (sign * (1.0 + frac + 1.0 / 256.0 - 2.0 ** -20) * 2.0 ** ex).float()
+    x = worst(torch.randn(n, d) * 1.7)
+    base = torch.randn(k // 3, d)
+    e = worst(torch.cat([base, base + 2e-3 * torch.randn_like(base), base - 2e-3 * torch.randn_like(base)], 0))
+    k = e.shape[0]
+    x, e = x.to(DEV), e.to(DEV)
+    ws = tvq.Workspace(k, d, torch.device(DEV))
+    idx_u, q_u, sc_u = tvq.vq_forward_raw(x, e, ws, train=True)
+    idx_s, q_s, _ = tvq.vq_forward_raw(x, e, ws, train=True, flags=tvq._lib.F_NO_UMMA)
+    assert torch.equal(idx_u, idx_s) and torch.equal(q_u, q_s)
+    assert np.array_equal(idx_u.cpu().numpy(), C.assign(x.cpu().numpy(), e.cpu().numpy()))
+
+
 @pytest.mark.parametrize("k,d", [(32, 128), (640, 64), (2048, 128)])
 def test_non_finite_latents_do_not_derail(tvq, k, d):
     """NaN / Inf latents (a diverged encoder) must neither hang nor slow the kernels down (no exhaustive scans),
