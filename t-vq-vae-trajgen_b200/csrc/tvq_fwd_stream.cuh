@@ -969,10 +969,28 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                 const uint32_t taddr = lane_addr + (uint32_t)(slot * NT);
                 const int code0 = ct * NT + half * (NT / SP);
                 uint32_t ra[32], rb[32];
+                // The score slot goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld of the code tile has
+                // completed — before the scores are looked at.  A slot is released by the slowest of the (pair's) scan warps,
+                // and some warp takes the candidate path in nearly every code tile: held through the scan, the slot paid for
+                // that path every time.
+                auto release_slot = [&]() {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_leader_nodata(bar_tempty + 8 * slot); else mbar_arrive(bar_tempty + 8 * slot);
+                    }
+                };
                 tmem_ld_x32(taddr, ra);
                 if constexpr (NCH == 1) {
                     tmem_ld_wait();
+                    release_slot();
                     scan_chunk(ra, code0, brow, st, ls, lc, sd, ob, trow);
+                } else if constexpr (NCH == 2) {
+                    tmem_ld_x32(taddr + 32u, rb);
+                    tmem_ld_wait();
+                    release_slot();
+                    scan_chunk(ra, code0, brow, st, ls, lc, sd, ob, trow);
+                    scan_chunk(rb, code0 + 32, brow, st, ls, lc, sd, ob, trow);
                 } else {
 #pragma unroll 1
                     for (int c = 0; c < NCH; c += 2) {      // the next chunk's tcgen05.ld is in flight while this one is scanned
@@ -981,13 +999,9 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                         scan_chunk(ra, code0 + c * 32, brow, st, ls, lc, sd, ob, trow);
                         tmem_ld_wait();
                         if (c + 2 < NCH) tmem_ld_x32(taddr + (uint32_t)(c + 2) * 32u, ra);
+                        else release_slot();
                         scan_chunk(rb, code0 + (c + 1) * 32, brow, st, ls, lc, sd, ob, trow);
                     }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 2) mbar_arrive_leader_nodata(bar_tempty + 8 * slot); else mbar_arrive(bar_tempty + 8 * slot);
                 }
                 mshare[pidx * kSM + trow] = st.m;
                 SP_LAP(3);
