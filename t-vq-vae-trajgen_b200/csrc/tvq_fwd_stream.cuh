@@ -16,17 +16,23 @@
 //               into a ring of shared-memory stages, then, per code tile, the [NT x 16] slab of |e|^2 / 2 pieces (SWIZZLE_32B)
 //   warp 1      MMA issuer: per code tile d/16 tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32, M = 128, N = NT) plus ONE more
 //               K step — constant A rows (1, 1, 1, 0...) against the three bf16 pieces of |e_c|^2 / 2 — into one of 512/NT
-//               tensor-memory score slots: the accumulator IS the half-score |e|^2 / 2 - x.e; tcgen05.commit
+//               tensor-memory score slots: the accumulator IS the half-score |e|^2 / 2 - x.e; tcgen05.commit.
+//               (Producer and issuer are warp-uniform loops with one elected lane: uniform-register descriptors, carried
+//               stage index / phase — under `if (lane == 0)` the issuer was instruction-bound.)
+//   warps 2-3   converters: x rows fp32 -> bf16 A operand in UMMA K-major SWIZZLE_128B layout, double buffered; at d <= 128
+//               the rows arrive through shared memory (8 KB blocks, cp.async.bulk issued two blocks ahead by the warp
+//               itself); per latent |x|^2 and |x - bf16(x)|^2, from which the scan thread of the latent takes its bound.
 //   warps 4-..  scan + apply, SP = 2 or 4 warps per TMEM lane quadrant (each takes 1/SP of the columns of every code tile),
-//               ONE THREAD PER LATENT: tcgen05.ld of 32 scores at a time, 3-input-min tree, running minimum m and
-//               threshold m + bound; a 32-score chunk is looked at again only if its minimum beats the threshold: a
-//               straight-line 8-compare mask of the groups of 4 that hold a hit, then one indexed branch per hit group; the
-//               candidates go to a small per-latent list in shared memory.  After the last code tile the warps of a
-//               quadrant merge their minima, and each resolves 32/SP latents (cascade above), gathers the code words,
-//               writes idx / q (straight-through) / loss partial and adds the EMA statistics (red.global.v4).
-//   warps 2-3   converters: x rows fp32 (global, L2-prefetched two tiles ahead) -> bf16 A operand in
-//               UMMA K-major SWIZZLE_128B layout, double buffered; also |x| -> the row's error bound.
-// For k >= 1024 the CTAs work in PAIRS (template parameter CG = 2: 2-CTA clusters, tcgen05 cta_group::2): see
+//               ONE THREAD PER LATENT: the running minimum m is SEEDED from a recording-free pass over the first code tile
+//               and shared by the parts of a quadrant; then tcgen05.ld of 32 scores at a time (the score slot is handed
+//               back as soon as the warp's last load of the code tile has completed), 3-input-min tree, threshold m + bound;
+//               a 32-score chunk is looked at again only if its minimum beats the threshold: a straight-line 8-compare
+//               mask of the groups of 4 that hold a hit, then one indexed branch per hit group; the candidates go to a
+//               small per-latent list in shared memory.  After the last code tile the parts merge their minima, every
+//               latent gets a record (count + up to four candidates), and each warp resolves 32/SP latents: one-candidate
+//               latents need no decision (x row and code word of all of them in flight at once), ambiguous ones take the
+//               cascade above; then idx / q (straight-through) / loss partial / EMA statistics (red.global.v4).
+// For k >= 512 the CTAs work in PAIRS (template parameter CG = 2: 2-CTA clusters, tcgen05 cta_group::2): see
 // the comment at the kernel.
 // Algorithmic cost per latent: 8d + 8 bytes of HBM (x is re-read once from L2 by the apply phase),
 // 2*k*d tensor FLOP.
