@@ -1096,6 +1096,7 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                 const int dq = p.d >> 2;
 #pragma unroll 1
                 for (int g0 = 0; g0 < NACC; g0 += GU) {
+                    if (!TRAIN && p.q == nullptr) break;      // assignment only: a one-candidate latent needs nothing more
                     if (((m1 >> (g0 * LPI)) & ((1u << (GU * LPI)) - 1u)) == 0u) continue;     // warp-uniform
                     float4 xa[GU], ea[GU];
                     int cu[GU];
@@ -1106,7 +1107,7 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                         if ((m1 >> lat) & 1u) {
                             cu[u] = recc[lrow0 + lat].x;
                             if (hv) {
-                                xa[u] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)(wrow0 + lat) * p.d) + c4);
+                                if (TRAIN) xa[u] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)(wrow0 + lat) * p.d) + c4);   // (eval: q = e)
                                 ea[u] = __ldg(cb4 + (size_t)cu[u] * dq + c4);
                             }
                         }
