@@ -832,45 +832,63 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                     }
                 }
             } else {
+                // d = 256 (no room for staged blocks): global loads, eight 16-byte chunks per lane in flight = four rows per
+                // iteration (a row is two warp-wide accesses); the same hoisted per-lane indexing and folded reduction
+                static_assert(STAGED || (F == 64 && U == 8), "the global-load converter path serves d = 256 only");
+                const int64_t left = p.n - (row0 + rowbase);
+                const int nvalid = left < XRB ? (int)(left > 0 ? left : 0) : XRB;    // rows of this block that exist
+                const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)(row0 + rowbase) * p.d) + lane;
+                const uint32_t dst = a0 + (uint32_t)rowbase * 128u + ((uint32_t)(lane & 1) << 3);
+                const uint32_t slab_l = (uint32_t)(lane >> 4) * A_SLAB, chunk_g = (uint32_t)(lane & 15) >> 1;
+                const bool cv0 = lane < nchunk, cv1 = lane + 32 < nchunk;
 #pragma unroll 1
-            for (int i0 = 0; i0 < F; i0 += U) {
-                float4 v[U];
+                for (int i0 = 0; i0 < XRB; i0 += 4) {          // four rows
+                    float4 v[8];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int f = (i0 + u) * 32 + lane;
-                    const int row = rowbase + f / F, c4 = f % F;
-                    const int64_t grow = row0 + row;
-                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (grow < p.n && c4 < nchunk) v[u] = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)grow * p.d) + c4);
-                }
-                float ssq[U], dsq[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int f = (i0 + u) * 32 + lane;
-                    const int row = rowbase + f / F, c4 = f % F;
-                    const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y);
-                    const __nv_bfloat162 hi = __floats2bfloat162_rn(v[u].z, v[u].w);
-                    const uint32_t addr = a0 + (uint32_t)(c4 >> 4) * A_SLAB + (uint32_t)row * 128u +
-                                          ((((uint32_t)(c4 & 15) >> 1) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)(c4 & 1) << 3);
-                    sts_v2(addr, *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-                    ssq[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
-                    const float2 blo = __bfloat1622float2(lo), bhi = __bfloat1622float2(hi);
-                    const float ex = v[u].x - blo.x, ey = v[u].y - blo.y, ez = v[u].z - bhi.x, ew = v[u].w - bhi.y;
-                    dsq[u] = fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, ew * ew)));
-                }
-                // F == 64 (d = 256): a row is two warp-wide accesses
-                static_assert(STAGED || F == 64, "the global-load converter path serves d = 256 only");
-#pragma unroll
-                for (int u = 0; u < U; u += 2) {
-                    float t = ssq[u] + ssq[u + 1], td = dsq[u] + dsq[u + 1];
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        t += __shfl_xor_sync(0xffffffffu, t, off);
-                        td += __shfl_xor_sync(0xffffffffu, td, off);
+                    for (int u = 0; u < 8; ++u) {
+                        const int r = i0 + (u >> 1);
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r < nvalid && ((u & 1) ? cv1 : cv0)) v[u] = __ldg(src + (size_t)r * (size_t)(p.d >> 2) + 32 * (u & 1));
                     }
-                    if (lane == 0) brow[rowbase + (i0 + u) / 2] = make_float2(t, td);
+                    float vals[8];                            // [r]: |x|^2 of row i0 + r, [4 + r]: |x - bf16(x)|^2
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int r = i0 + (u >> 1);
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y);
+                        const __nv_bfloat162 hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+                        const uint32_t wlo = *reinterpret_cast<const uint32_t*>(&lo), whi = *reinterpret_cast<const uint32_t*>(&hi);
+                        // chunk c4 = lane + 32 (u & 1): slab c4 / 16, 16-byte chunk (c4 % 16) / 2 (XOR row & 7), half c4 & 1
+                        sts_v2(dst + slab_l + (uint32_t)(2 * (u & 1)) * A_SLAB + (uint32_t)r * 128u + ((chunk_g ^ ((uint32_t)(rowbase + r) & 7u)) << 4),
+                               wlo, whi);
+                        const float t = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
+                        const float ex = v[u].x - __uint_as_float(wlo << 16), ey = v[u].y - __uint_as_float(wlo & 0xffff0000u);
+                        const float ez = v[u].z - __uint_as_float(whi << 16), ew = v[u].w - __uint_as_float(whi & 0xffff0000u);
+                        const float td = fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, ew * ew)));
+                        if (u & 1) { vals[u >> 1] += t; vals[4 + (u >> 1)] += td; }
+                        else { vals[u >> 1] = t; vals[4 + (u >> 1)] = td; }
+                    }
+                    {
+                        const bool b0 = (lane & 16) != 0, b1 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float keep = b0 ? vals[i + 4] : vals[i], send = b0 ? vals[i] : vals[i + 4];
+                            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float keep = b1 ? vals[i + 2] : vals[i], send = b1 ? vals[i] : vals[i + 2];
+                            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+                        {
+                            const float keep = b2 ? vals[1] : vals[0], send = b2 ? vals[0] : vals[1];
+                            vals[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+                        vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], 2);
+                        vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], 1);
+                        if ((lane & 3) == 0)
+                            reinterpret_cast<float*>(brow)[2 * (rowbase + i0 + 2 * (int)b1 + (int)b2) + (int)b0] = vals[0];
+                    }
                 }
-            }
             }
             }
             SP_MARK(sp_c2);
@@ -909,7 +927,6 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
         // latents in flight in the apply phase (up to 4 candidates each are resolved in the batched pass).  Two candidates
         // per latent with twice the latents per L2 round trip was measured and is slower (512 x 64: 6.3 vs 4.4 ms): three-
         // and four-candidate latents are too common for the one-at-a-time second pass.
-        constexpr int R = (NV > 1 || WG_REGS) ? 2 : 4;
         SP_DECL;
         int et = 0;                                           // code tiles scanned by this set
         for (int it = set, grp = unit0 + set * nunits; grp < ngroups; grp += SETS * nunits, it += SETS) {
@@ -1195,21 +1212,12 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                     }
                 }
             } else {
-#pragma unroll 1
-            for (int b = 0; b < LPW / R; ++b) {
-                if (wrow0 + R * b >= p.n) break;              // warp-uniform
-                SP_MARK(sp_b0);
-                float4 xa[R], xb[R], ea[R][4], eb[R][4];
-                float e2v[R][4];
-                int nc[R], cc[R][4];
-                bool valid[R];
-                // the merged counts and candidate codes of the batch are warp-uniform: lane 4u + j fetches candidate j
-                // of latent u once (one shared-memory round trip for the whole batch) and shuffles hand them out
-                int nc_l, c_l;
-                {
-                    const int lu = (lane >> 2) & (R - 1), lj = lane & 3;
-                    const int lrow = lrow0 + R * b + lu;
-                    // 1..4: the merged count, resolved right here; anything else: general path
+                // d = 256: the same three passes, but the merged record of latent i lives in the registers of lane i (its
+                // 5 KB in shared memory would cost the fourth code-slab stage) and is handed out by shuffles.
+                int rn = -1;
+                int rc0 = 0, rc1 = 0, rc2 = 0, rc3 = 0;
+                if (lane < LPW && wrow0 + lane < p.n) {
+                    const int lrow = lrow0 + lane;
                     int tot = 0, bad = 0, cn[SP];
 #pragma unroll
                     for (int pt = 0; pt < SP; ++pt) {
@@ -1218,51 +1226,91 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                         cn[pt] = nr & 0xff;
                         tot += cn[pt];
                     }
-                    nc_l = (bad || tot == 0 || tot > 4) ? 0 : tot;
-                    // candidate j of the merged list: part 0's entries first, then part 1's, ...
-                    int jj = lj < nc_l ? lj : 0, part_j = 0;
-#pragma unroll
-                    for (int pt = 0; pt < SP - 1; ++pt)
-                        if (part_j == pt && jj >= cn[pt]) { jj -= cn[pt]; part_j = pt + 1; }
-                    const int c = cand_c[((pbase + part_j) * kSCand + (jj < kSCand ? jj : 0)) * kSM + lrow];
-                    c_l = (c >= 0 && c < p.k) ? c : 0;
-                }
-#pragma unroll
-                for (int u = 0; u < R; ++u) {
-                    const int64_t grow = wrow0 + R * b + u;
-                    valid[u] = grow < p.n;
-                    nc[u] = __shfl_sync(0xffffffffu, nc_l, 4 * u);
-                    if (valid[u] && nc[u] == 0) gen_mask |= 1u << (R * b + u);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) cc[u][j] = __shfl_sync(0xffffffffu, c_l, 4 * u + j);
-                    const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)(valid[u] ? grow : 0) * p.d);
-                    xa[u] = (valid[u] && h0) ? __ldg(xr + lane) : z4;
-                    xb[u] = (valid[u] && h1) ? __ldg(xr + lane + 32) : z4;
+                    rn = (bad || tot == 0 || tot > 4) ? 0 : tot;
+                    int cv[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        ea[u][j] = z4; eb[u][j] = z4; e2v[u][j] = 0.f;
-                        if (j < nc[u]) {
-                            const float4* er = reinterpret_cast<const float4*>(p.cb + (size_t)cc[u][j] * p.d);
-                            if (h0) ea[u][j] = __ldg(er + lane);
-                            if (h1) eb[u][j] = __ldg(er + lane + 32);
-                            if (nc[u] >= 2) e2v[u][j] = __ldg(p.e2 + cc[u][j]);
+                        int jj = j < rn ? j : 0, part_j = 0;
+#pragma unroll
+                        for (int pt = 0; pt < SP - 1; ++pt)
+                            if (part_j == pt && jj >= cn[pt]) { jj -= cn[pt]; part_j = pt + 1; }
+                        const int c = cand_c[((pbase + part_j) * kSCand + (jj < kSCand ? jj : 0)) * kSM + lrow];
+                        cv[j] = (c >= 0 && c < p.k) ? c : 0;
+                    }
+                    rc0 = cv[0]; rc1 = cv[1]; rc2 = cv[2]; rc3 = cv[3];
+                    mycode = rc0;
+                }
+                const unsigned m1 = __ballot_sync(0xffffffffu, rn == 1);
+                unsigned m2 = __ballot_sync(0xffffffffu, rn >= 2);
+                gen_mask = __ballot_sync(0xffffffffu, rn == 0);
+                const float4* cb4 = reinterpret_cast<const float4*>(p.cb);
+                const int dq = p.d >> 2;
+                constexpr int GU = 4;                         // one-candidate latents in flight (16 registers each)
+#pragma unroll 1
+                for (int g0 = 0; g0 < LPW; g0 += GU) {
+                    if (!TRAIN && p.q == nullptr) break;      // assignment only: a one-candidate latent needs nothing more
+                    if (((m1 >> g0) & ((1u << GU) - 1u)) == 0u) continue;     // warp-uniform
+                    float4 xa[GU], xb[GU], ea[GU], eb[GU];
+                    int cu[GU];
+#pragma unroll
+                    for (int u = 0; u < GU; ++u) {
+                        const int lat = g0 + u;
+                        cu[u] = __shfl_sync(0xffffffffu, rc0, lat);
+                        xa[u] = z4; xb[u] = z4; ea[u] = z4; eb[u] = z4;
+                        if ((m1 >> lat) & 1u) {
+                            const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)(wrow0 + lat) * p.d);
+                            const float4* er = cb4 + (size_t)cu[u] * dq;
+                            if (h0) { if (TRAIN) xa[u] = __ldg(xr + lane); ea[u] = __ldg(er + lane); }
+                            if (h1) { if (TRAIN) xb[u] = __ldg(xr + lane + 32); eb[u] = __ldg(er + lane + 32); }
                         }
                     }
-                }
-                SP_ADD(6, sp_b0);                              // candidate fetch + loads issued (nothing used yet)
 #pragma unroll
-                for (int u = 0; u < R; ++u) {
-                    int sel = 0;
-                    if (valid[u] && nc[u] >= 2) {
-                        // fp32 re-score of the (<= 4) candidates, all lanes on this latent
+                    for (int u = 0; u < GU; ++u) {
+                        const int lat = g0 + u;
+                        if ((m1 >> lat) & 1u)
+                            apply_row<NV, TRAIN>(p, esum, xa[u], xb[u], ea[u], eb[u], cu[u], wrow0 + lat, h0, h1, lane, loss);
+                    }
+                }
+#pragma unroll 1
+                while (m2) {                                   // warp-uniform
+                    constexpr int R2 = 2;
+                    float4 xa[R2], xb[R2], ea[R2][4], eb[R2][4];
+                    float e2v[R2][4];
+                    int nc[R2], cc[R2][4], lat[R2];
+#pragma unroll
+                    for (int u = 0; u < R2; ++u) {
+                        nc[u] = 0; lat[u] = 0;
+                        if (m2) { lat[u] = __ffs((int)m2) - 1; m2 &= m2 - 1u; nc[u] = 1; }
+                        const int nrec = __shfl_sync(0xffffffffu, rn, lat[u]);
+                        nc[u] = nc[u] ? nrec : 0;
+                        cc[u][0] = __shfl_sync(0xffffffffu, rc0, lat[u]); cc[u][1] = __shfl_sync(0xffffffffu, rc1, lat[u]);
+                        cc[u][2] = __shfl_sync(0xffffffffu, rc2, lat[u]); cc[u][3] = __shfl_sync(0xffffffffu, rc3, lat[u]);
+                        const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)(wrow0 + lat[u]) * p.d);
+                        xa[u] = (nc[u] > 0 && h0) ? __ldg(xr + lane) : z4;
+                        xb[u] = (nc[u] > 0 && h1) ? __ldg(xr + lane + 32) : z4;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            ea[u][j] = z4; eb[u][j] = z4; e2v[u][j] = 0.f;
+                            if (j < nc[u]) {
+                                const float4* er = cb4 + (size_t)cc[u][j] * dq;
+                                if (h0) ea[u][j] = __ldg(er + lane);
+                                if (h1) eb[u][j] = __ldg(er + lane + 32);
+                                e2v[u][j] = __ldg(p.e2 + cc[u][j]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < R2; ++u) {
+                        if (nc[u] < 2) continue;               // (second slot of an odd batch)
                         n_resc += 1u;
+                        int sel = 0;
                         float dd[4];
                         float ss = fmaf(xa[u].x, xa[u].x, fmaf(xa[u].y, xa[u].y, fmaf(xa[u].z, xa[u].z, xa[u].w * xa[u].w)));
-                        if (NV > 1) ss = fmaf(xb[u].x, xb[u].x, fmaf(xb[u].y, xb[u].y, fmaf(xb[u].z, xb[u].z, fmaf(xb[u].w, xb[u].w, ss))));
+                        ss = fmaf(xb[u].x, xb[u].x, fmaf(xb[u].y, xb[u].y, fmaf(xb[u].z, xb[u].z, fmaf(xb[u].w, xb[u].w, ss))));
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             dd[j] = fmaf(xa[u].x, ea[u][j].x, fmaf(xa[u].y, ea[u][j].y, fmaf(xa[u].z, ea[u][j].z, xa[u].w * ea[u][j].w)));
-                            if (NV > 1) dd[j] = fmaf(xb[u].x, eb[u][j].x, fmaf(xb[u].y, eb[u][j].y, fmaf(xb[u].z, eb[u][j].z, fmaf(xb[u].w, eb[u][j].w, dd[j]))));
+                            dd[j] = fmaf(xb[u].x, eb[u][j].x, fmaf(xb[u].y, eb[u][j].y, fmaf(xb[u].z, eb[u][j].z, fmaf(xb[u].w, eb[u][j].w, dd[j]))));
                         }
 #pragma unroll
                         for (int off = 16; off >= 1; off >>= 1) {
@@ -1272,14 +1320,14 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                         }
                         const float bnd = fmaf(sqrtf(ss), 1.0001f, emax);
                         const float thr32 = 1.6e-6f * bnd * bnd;
-                        float m1 = INF, m2 = INF;
+                        float mm1 = INF, mm2 = INF;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float sv = j < nc[u] ? fmaf(-2.f, dd[j], e2v[u][j]) : INF;
-                            if (sv < m1) { m2 = m1; m1 = sv; sel = j; }
-                            else if (sv < m2) m2 = sv;
+                            if (sv < mm1) { mm2 = mm1; mm1 = sv; sel = j; }
+                            else if (sv < mm2) mm2 = sv;
                         }
-                        if (!(m2 - m1 > thr32)) {
+                        if (!(mm2 - mm1 > thr32)) {
                             // canonical fp64 rule among the candidates (code words already in registers)
                             n_f64 += 1u;
                             double pp = 0.0;
@@ -1292,25 +1340,22 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 if (j < nc[u]) {
-                                    double sd = 0.0;
-                                    if (h0) sd = dot4(sd, xa[u], ea[u][j]);
-                                    if (h1) sd = dot4(sd, xb[u], eb[u][j]);
-                                    const float dk = canon_score(x2, butterfly_sum(sd), e2v[u][j]);
+                                    double sdd = 0.0;
+                                    if (h0) sdd = dot4(sdd, xa[u], ea[u][j]);
+                                    if (h1) sdd = dot4(sdd, xb[u], eb[u][j]);
+                                    const float dk = canon_score(x2, butterfly_sum(sdd), e2v[u][j]);
                                     if (dk < best || (dk == best && cc[u][j] < arg)) { best = dk; arg = cc[u][j]; sel = j; }
                                 }
                             }
                         }
-                    }
-                    if (valid[u] && nc[u] >= 1) {
                         const int code = sel == 0 ? cc[u][0] : sel == 1 ? cc[u][1] : sel == 2 ? cc[u][2] : cc[u][3];
                         const float4 wa = sel == 0 ? ea[u][0] : sel == 1 ? ea[u][1] : sel == 2 ? ea[u][2] : ea[u][3];
                         const float4 wb = sel == 0 ? eb[u][0] : sel == 1 ? eb[u][1] : sel == 2 ? eb[u][2] : eb[u][3];
                         if (p.q != nullptr || TRAIN)
-                            apply_row<NV, TRAIN>(p, esum, xa[u], xb[u], wa, wb, code, wrow0 + R * b + u, h0, h1, lane, loss);
-                        mycode = (lane == R * b + u) ? code : mycode;
+                            apply_row<NV, TRAIN>(p, esum, xa[u], xb[u], wa, wb, code, wrow0 + lat[u], h0, h1, lane, loss);
+                        mycode = (lane == lat[u]) ? code : mycode;
                     }
                 }
-            }
             }
             // ---- second pass (rare): long merged lists, spilled candidates, exhaustive scans — one latent at a time
             SP_MARK(sp_g0);
