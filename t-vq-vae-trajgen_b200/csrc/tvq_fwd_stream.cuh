@@ -709,8 +709,8 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
         // Each converter warp is ONE serial instruction stream, so what matters is how few instructions a 16-byte chunk costs
         // (the first version spent ~100, 24 k clocks per row tile at d = 64: the floor of every k <= 1024 shape):
         //   * d <= 128: the x rows arrive through shared memory — 8 KB blocks (512 / F rows) bulk-copied by this warp xdepth - 1
-        //     blocks ahead; per chunk one LDS.128, two cvt.rn.bf16x2, one STS.64 into the swizzled A tile, the two sums of
-        //     squares, a log2(F)-step butterfly; all index arithmetic is per lane and hoisted;
+        //     blocks ahead; a lane owns a ROW (or half of one), so per chunk it is one LDS.128, two cvt.rn.bf16x2, one STS.64
+        //     into the swizzled A tile and the two sums of squares as per-lane accumulations; all index arithmetic is hoisted;
         //   * the square roots and the bound itself are left to the scan threads (one per latent): the converter only
         //     publishes |x|^2 and |x - bf16(x)|^2 per row.
         const int cw = warp - 2;
@@ -735,14 +735,14 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
         };
         if (STAGED && lane == 0)
             for (int g = 0; g < xdepth - 1; ++g) issue_block(g);
-        // per-lane constants of the staged path: a warp-wide 16-byte access covers RPU rows, lane -> (row lr, chunk c4)
-        constexpr int FL = F < 32 ? F : 32;                   // lanes per row
-        constexpr int RPU = 32 / FL;
-        const int lr = lane / FL, c4l = lane % FL;
-        const bool cvalid = c4l < nchunk;
+        // per-lane constants of the staged path: lane -> (row brw of a block, part sub of the row), see the loop
+        constexpr int LPR = STAGED ? 32 / XRB : 1;            // lanes per row
+        static_assert(!STAGED || (F / LPR == 16 && (LPR == 1 || LPR == 2)), "a lane converts 16 chunks of one row");
+        const int brw = lane / LPR;
+        const uint32_t sub = (uint32_t)(lane % LPR);
+        const uint32_t rx = (uint32_t)brw & 7u;               // row & 7 of the A tile (blocks start at multiples of 16 rows)
+        const int rot = brw + 8 * (int)sub;
         const uint32_t rowbytes = (uint32_t)p.d * 4u;
-        const uint32_t a_lane = (uint32_t)(c4l >> 4) * A_SLAB + ((uint32_t)(c4l & 1) << 3);
-        const uint32_t chunk_l = (uint32_t)(c4l & 15) >> 1;
         SP_DECL;
         int it = 0, gblk = 0;
         for (int grp = unit0; grp < ngroups; grp += nunits, ++it) {
@@ -776,61 +776,45 @@ __global__ void __launch_bounds__(stream_threads(SP * SETS), 1) fwd_stream_kerne
                 SP_MARK(sp_c1);
                 if (nvalid > 0) mbar_wait(xbar0 + 8 * (gblk % xdepth), ((uint32_t)(gblk / xdepth)) & 1u);
                 SP_ADD(4, sp_c1);
-                const uint32_t src = xs_base + (uint32_t)(gblk % xdepth) * kSXBlock + (uint32_t)lr * rowbytes + (uint32_t)c4l * 16u;
-                const uint32_t dst = a0 + a_lane + (uint32_t)(rowbase + lr) * 128u;
+                // lane <-> ROW: a lane converts 16 chunks of one row of the block (d <= 64: 32 rows of 16 chunks, one lane per
+                // row; d <= 128: 16 rows of 32 chunks, two lanes per row), so the two sums of squares of a row are plain
+                // per-lane accumulations — no shuffle butterfly, no select network (the lane <-> chunk form spent half of its
+                // ~42 instructions per chunk and all of its dependent latency there: 20 k clocks per row tile at d = 128, the
+                // floor of every k <= 1024 shape at d >= 128).  The chunk order is rotated by the row (+ 8 for the second lane
+                // of a row): LDS.128 at most 2-way and STS.64 not at all bank-conflicted, although the rows are 256 / 512 B apart.
+                const bool rvalid = brw < nvalid;
+                const uint32_t src = xs_base + (uint32_t)(gblk % xdepth) * kSXBlock + (uint32_t)brw * rowbytes + (uint32_t)sub * 256u;
+                const uint32_t dst = a0 + (uint32_t)sub * A_SLAB + (uint32_t)(rowbase + brw) * 128u;
+                float s1 = 0.f, s2 = 0.f;                     // |x|^2 and |x - bf16(x)|^2 of this lane's part of the row
 #pragma unroll 1
-                for (int i0 = 0; i0 < XRB / RPU; i0 += U) {
+                for (int j0 = 0; j0 < 16; j0 += U) {
                     float4 v[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const int r = (i0 + u) * RPU + lr;    // row within the block
+                        const uint32_t ccl = (uint32_t)(j0 + u + rot) & 15u;
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (cvalid && r < nvalid) v[u] = lds_v4(src + (uint32_t)((i0 + u) * RPU) * rowbytes);
+                        if (rvalid && (int)(sub * 16u + ccl) < nchunk) v[u] = lds_v4(src + ccl * 16u);
                     }
-                    float vals[2 * U];                        // [u]: |x|^2 of chunk u, [U + u]: |x - bf16(x)|^2
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const int r = (i0 + u) * RPU + lr;
+                        const uint32_t ccl = (uint32_t)(j0 + u + rot) & 15u;
                         const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y);
                         const __nv_bfloat162 hi = __floats2bfloat162_rn(v[u].z, v[u].w);
                         const uint32_t wlo = *reinterpret_cast<const uint32_t*>(&lo), whi = *reinterpret_cast<const uint32_t*>(&hi);
-                        // element column 4*c4: slab c4/16, 16-byte chunk (c4 % 16) / 2 (XOR row & 7), half c4 & 1
-                        sts_v2(dst + (uint32_t)((i0 + u) * RPU) * 128u + ((chunk_l ^ ((uint32_t)(rowbase + r) & 7u)) << 4), wlo, whi);
-                        vals[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
+                        // element column 4 * (16 sub + ccl): slab sub, 16-byte chunk ccl / 2 (XOR row & 7), half ccl & 1
+                        sts_v2(dst + ((((ccl >> 1) ^ rx)) << 4) + ((ccl & 1u) << 3), wlo, whi);
+                        s1 += fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
                         // |x - bf16(x)|^2 of the chunk (a bf16 is the upper half of its fp32; the differences are exact)
                         const float ex = v[u].x - __uint_as_float(wlo << 16), ey = v[u].y - __uint_as_float(wlo & 0xffff0000u);
                         const float ez = v[u].z - __uint_as_float(whi << 16), ew = v[u].w - __uint_as_float(whi & 0xffff0000u);
-                        vals[U + u] = fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, ew * ew)));
-                    }
-                    // the 2U sums of squares of the U rows, reduced over the FL lanes of a row TOGETHER: each of the first three
-                    // butterfly steps halves the number of values a lane carries (it keeps the half its lane bit selects and
-                    // sends the other), so the U rows cost 4 + 2 + 1 + ... shuffles instead of 2U * log2(FL)
-                    static_assert(U == 4, "the folded reduction below is written for four rows at a time");
-                    {
-                        const bool b0 = (lane & (FL / 2)) != 0, b1 = (lane & (FL / 4)) != 0, b2 = (lane & (FL / 8)) != 0;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float keep = b0 ? vals[i + 4] : vals[i], send = b0 ? vals[i] : vals[i + 4];
-                            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, FL / 2);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const float keep = b1 ? vals[i + 2] : vals[i], send = b1 ? vals[i] : vals[i + 2];
-                            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, FL / 4);
-                        }
-                        {
-                            const float keep = b2 ? vals[1] : vals[0], send = b2 ? vals[0] : vals[1];
-                            vals[0] = keep + __shfl_xor_sync(0xffffffffu, send, FL / 8);
-                        }
-#pragma unroll
-                        for (int off = FL / 16; off >= 1; off >>= 1) vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], off);
-                        // holder lanes: kind (|x|^2 or the residual) = b0, row u = 2 * b1 + b2
-                        if ((lane & (FL / 8 - 1)) == 0) {
-                            const int r = (i0 + 2 * (int)b1 + (int)b2) * RPU + lr;
-                            reinterpret_cast<float*>(brow)[2 * (rowbase + r) + (int)b0] = vals[0];
-                        }
+                        s2 += fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, ew * ew)));
                     }
                 }
+                if (LPR == 2) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+                }
+                if (sub == 0) brow[rowbase + brw] = make_float2(s1, s2);
             } else {
                 // d = 256 (no room for staged blocks): global loads, eight 16-byte chunks per lane in flight = four rows per
                 // iteration (a row is two warp-wide accesses); the same hoisted per-lane indexing and folded reduction
