@@ -516,7 +516,9 @@ def test_umma_path_equals_simt_path(tvq, n, k, d, train):
 
 STREAM_CASES = [(128, 64, 64), (130, 100, 128), (1000, 256, 64), (777, 33, 64), (5000, 100, 100), (600, 16, 256),
                 (3000, 512, 64), (2049, 1000, 128), (1500, 70, 256), (4096, 2500, 32), (20000, 4096, 128), (9000, 777, 252),
-                (300000, 512, 64), (70000, 16384, 256)]
+                (300000, 512, 64), (70000, 16384, 256),
+                # ragged rows of the staged converter blocks (a lane owns a row or half a row of 16 chunks)
+                (131, 600, 36), (1000, 700, 68), (257, 520, 124), (4111, 1030, 12)]
 
 
 @pytest.mark.parametrize("n,k,d", STREAM_CASES)
