@@ -455,9 +455,11 @@ def undecidable_report(name, n, mismatches, undecidable):
         json.dump(d, open(path, "w"), indent=1)
 
 
-@pytest.mark.parametrize("n,k,d", [(18432, 32, 128), (76800, 32, 128), (1 << 20, 512, 64), (1 << 18, 4096, 128)])
+@pytest.mark.parametrize("n,k,d", [(18432, 32, 128), (76800, 32, 128), (1 << 20, 512, 64), (1 << 18, 4096, 128),
+                                   (1 << 20, 1024, 128), (1 << 17, 16384, 256)])
 def test_baseline_sizes_every_row_vs_torch_oracle(tvq, n, k, d):
-    """BASELINE configs[1] (LF 18 432 / HF 76 800 x 32 x 128) and configs[2] (2^20 x 512 x 64, 2^18 x 4096 x 128): ALL rows
+    """BASELINE configs[1] (LF 18 432 / HF 76 800 x 32 x 128) and configs[2] (2^20 x 512 x 64, 2^18 x 4096 x 128, 2^20 x 1024 x 128,
+    2^17 x 16384 x 256 — the smallest, the ridge and the largest codebook of the sweep): ALL rows
     against the reference's own formula (vq.py:210-218) evaluated by torch on the CPU in row chunks (O.assign_chunked;
     chunking does not change a row's distances).  A mismatch is tolerated only on a row whose two best reference scores
     are within 2 ulps (un-decidable between two fp32 summation orders); the count is reported."""
